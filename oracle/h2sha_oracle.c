@@ -1,0 +1,934 @@
+/*
+ * h2sha_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A cell-exact restatement, in plain C, of the witness generation performed by
+ * zhmolly/halo2-dynamic-sha256 for one `Sha256DynamicConfig::digest` call chain:
+ *
+ *   src/lib.rs:71-349          Sha256DynamicConfig::digest
+ *   src/compression.rs:19-213  sha256_compression (+ helpers :215-882)
+ *   src/spread.rs:76-233       SpreadConfig::{spread, spread_limb, decompose_even_and_odd_unchecked}
+ *   src/utils.rs:6-30          fe_to_bits_le / bits_le_to_fe
+ *
+ * The reference delegates every cell placement to the third-party crate
+ * `halo2-base` (zkmove/halo2-lib rev 40ba7e3, Cargo.toml:10-13), whose source is
+ * NOT under /root/reference and cannot be built here (no cargo, no network).
+ * The op -> cell patterns below (`g_add`, `g_mul_add`, `range_check`, ...)
+ * restate the published halo2-lib v0.2.x `FlexGateConfig` / `RangeConfig`
+ * (Vertical strategy) algorithm, see SURVEY.md section 8a Table B.
+ *
+ * PARITY STATUS: digests are pinned by the reference's own known-answer tests
+ * (src/lib.rs:497-611); constraint satisfaction (gates, copies, both lookups)
+ * is pinned by oracle/mock_prover.py; the column budgets NUM_ADVICE=3 (lib.rs:490)
+ * and 9 (benches/digest.rs:105) are reproduced.  The (column,row) placement of
+ * individual cells is "parity unpinned": no reference test pins it and the real
+ * crate cannot be run in this environment.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this file.  The product (CUDA) path never does.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+/* ------------------------------------------------------------------------- */
+/* BN254 scalar field Fr, Montgomery form (halo2curves bn256::Fr layout:      */
+/* 4 x u64 little-endian limbs holding v * 2^256 mod p).                      */
+/* ------------------------------------------------------------------------- */
+typedef struct { uint64_t l[4]; } fr_t;
+
+static const uint64_t P[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL,
+                              0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+static uint64_t P_INV;   /* -p^-1 mod 2^64   (derived, not trusted) */
+static fr_t FR_R;        /* 2^256 mod p  == Montgomery(1)           */
+static fr_t FR_R2;       /* 2^512 mod p                             */
+static fr_t FR_ZERO;
+static int fr_ready = 0;
+
+static int ge_p(const uint64_t a[4]) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] > P[i]) return 1;
+    if (a[i] < P[i]) return 0;
+  }
+  return 1;
+}
+static void sub_p(uint64_t a[4]) {
+  u128 b = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)a[i] - P[i] - (uint64_t)b;
+    a[i] = (uint64_t)t;
+    b = (t >> 64) & 1;
+  }
+}
+static fr_t fr_add(fr_t a, fr_t b) {
+  fr_t r; u128 c = 0;
+  for (int i = 0; i < 4; i++) { c += (u128)a.l[i] + b.l[i]; r.l[i] = (uint64_t)c; c >>= 64; }
+  /* p < 2^254 so a+b < 2^255: no carry out */
+  if (ge_p(r.l)) sub_p(r.l);
+  return r;
+}
+static int fr_is_zero(fr_t a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+static fr_t fr_neg(fr_t a) {
+  if (fr_is_zero(a)) return a;
+  fr_t r; u128 b = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 t = (u128)P[i] - a.l[i] - (uint64_t)b;
+    r.l[i] = (uint64_t)t; b = (t >> 64) & 1;
+  }
+  return r;
+}
+static fr_t fr_sub(fr_t a, fr_t b) { return fr_add(a, fr_neg(b)); }
+static int fr_eq(fr_t a, fr_t b) { return memcmp(&a, &b, sizeof a) == 0; }
+
+/* CIOS Montgomery multiplication: a*b*2^-256 mod p */
+static fr_t fr_mul(fr_t a, fr_t b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a.l[j] * b.l[i] + t[j];
+      t[j] = (uint64_t)c; c >>= 64;
+    }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * P_INV;
+    c = (u128)m * P[0] + t[0]; c >>= 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * P[j] + t[j];
+      t[j - 1] = (uint64_t)c; c >>= 64;
+    }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  fr_t r = {{t[0], t[1], t[2], t[3]}};
+  if (t[4] || ge_p(r.l)) sub_p(r.l);
+  return r;
+}
+
+static void fr_init(void) {
+  if (fr_ready) return;
+  /* -p^-1 mod 2^64 by Newton iteration */
+  uint64_t inv = 1;
+  for (int i = 0; i < 6; i++) inv *= 2 - P[0] * inv;
+  P_INV = (uint64_t)0 - inv;
+  /* R = 2^256 mod p by 256 modular doublings of 1; R2 by 256 more. */
+  uint64_t x[4] = {1, 0, 0, 0};
+  for (int k = 0; k < 512; k++) {
+    uint64_t c = 0;
+    for (int i = 0; i < 4; i++) { uint64_t n = (x[i] << 1) | c; c = x[i] >> 63; x[i] = n; }
+    if (c || ge_p(x)) sub_p(x);
+    if (k == 255) memcpy(FR_R.l, x, sizeof x);
+  }
+  memcpy(FR_R2.l, x, sizeof x);
+  memset(&FR_ZERO, 0, sizeof FR_ZERO);
+  fr_ready = 1;
+}
+
+/* F::from(u64): canonical -> Montgomery, one Montgomery multiply by R^2 (as halo2curves does). */
+static fr_t fr_from_u64(uint64_t v) {
+  fr_t a = {{v, 0, 0, 0}};
+  return fr_mul(a, FR_R2);
+}
+/* canonical (non-Montgomery) little-endian limbs of a field element */
+static void fr_canon(fr_t a, uint64_t out[4]) {
+  fr_t one = {{1, 0, 0, 0}};
+  fr_t c = fr_mul(a, one);
+  memcpy(out, c.l, 32);
+}
+static fr_t fr_pow(fr_t a, const uint64_t e[4]) {
+  fr_t r = FR_R;
+  for (int i = 255; i >= 0; i--) {
+    r = fr_mul(r, r);
+    if ((e[i / 64] >> (i % 64)) & 1) r = fr_mul(r, a);
+  }
+  return r;
+}
+static fr_t fr_inv(fr_t a) {
+  uint64_t e[4] = {P[0] - 2, P[1], P[2], P[3]};
+  return fr_pow(a, e);
+}
+/* halo2-base ScalarField::get_lower_32 / get_lower_64 (canonical repr, low bits) */
+static uint32_t fr_lower_32(fr_t a) { uint64_t c[4]; fr_canon(a, c); return (uint32_t)c[0]; }
+static uint64_t fr_lower_64(fr_t a) { uint64_t c[4]; fr_canon(a, c); return c[0]; }
+
+/* ------------------------------------------------------------------------- */
+/* Emulated halo2-base Context (Vertical strategy, 1 context id).             */
+/* ------------------------------------------------------------------------- */
+typedef struct { uint32_t idx; fr_t v; } av_t;            /* AssignedValue: gate-stream index + value */
+enum { QC_EXISTING = 0, QC_CONSTANT = 1, QC_WITNESS = 2 };
+typedef struct { int kind; av_t ex; fr_t v; } qc_t;        /* QuantumCell */
+static qc_t EX(av_t a) { qc_t q; q.kind = QC_EXISTING; q.ex = a; q.v = a.v; return q; }
+static qc_t CONST_FR(fr_t c) { qc_t q; q.kind = QC_CONSTANT; q.v = c; q.ex.idx = 0; q.ex.v = c; return q; }
+static qc_t CONST64(uint64_t c) { return CONST_FR(fr_from_u64(c)); }
+static qc_t WIT(fr_t w) { qc_t q; q.kind = QC_WITNESS; q.v = w; q.ex.idx = 0; q.ex.v = w; return q; }
+
+/* kinds of "other" cells a copy constraint can point at */
+enum { CP_GATE = 0, CP_FIXED = 1, CP_LOOKUP = 2, CP_DENSE = 3, CP_SPREAD = 4 };
+typedef struct { uint32_t a_kind, a_idx, b_kind, b_idx; } copy_t;
+
+typedef struct {
+  /* parameters */
+  uint32_t max_rows;        /* range.gate.max_rows                       (lib.rs:355) */
+  uint32_t lookup_bits;     /* RangeConfig lookup_bits                   (lib.rs:415) */
+  uint32_t limb_bits;       /* SpreadConfig num_bits_lookup              (lib.rs:425) */
+  uint32_t spread_cols;     /* SpreadConfig num_advice_columns           (lib.rs:426) */
+  int record_shape;         /* 0: lean (values only)                                  */
+  /* gate advice stream, in assignment order */
+  fr_t* gate; uint8_t* sel; size_t n_gate, cap_gate;
+  uint32_t col, row;        /* advice_alloc[0] = (column, row)                        */
+  uint32_t* brk; size_t n_brk, cap_brk;  /* stream index where column c starts       */
+  /* lookups */
+  uint32_t* lk; size_t n_lk, cap_lk;     /* cells_to_lookup: gate stream indices      */
+  /* spread columns: limb n -> column n % spread_cols, row n / spread_cols            */
+  fr_t* dense; fr_t* spread; size_t n_limb, cap_limb;
+  uint32_t* limb_gate_dense;             /* gate idx copy-constrained to dense cell   */
+  uint32_t* limb_gate_spread;            /* gate idx copy-constrained to spread cell  */
+  /* SpreadConfig mutable state (spread.rs:26-27) is n_limb (num_limb_sum); row_offset = n_limb / cols */
+  /* shape */
+  copy_t* copies; size_t n_copy, cap_copy;
+  fr_t* consts; size_t n_const, cap_const;   /* de-duplicated fixed cells, first-use order */
+  int has_zero; av_t zero_cell;              /* ctx.zero_cell cache                        */
+} ctx_t;
+
+static void* xrealloc(void* p, size_t n) { void* q = realloc(p, n); if (!q) { fprintf(stderr, "oracle: OOM\n"); abort(); } return q; }
+#define PUSH(ctx, arr, n, cap, val) do { if ((ctx)->n == (ctx)->cap) { (ctx)->cap = (ctx)->cap ? (ctx)->cap * 2 : 4096; \
+  (ctx)->arr = xrealloc((ctx)->arr, (ctx)->cap * sizeof *(ctx)->arr); } (ctx)->arr[(ctx)->n++] = (val); } while (0)
+
+static void ctx_copy(ctx_t* c, uint32_t ak, uint32_t ai, uint32_t bk, uint32_t bi) {
+  if (!c->record_shape) return;
+  copy_t cp = {ak, ai, bk, bi};
+  PUSH(c, copies, n_copy, cap_copy, cp);
+}
+/* Context::assign_fixed: de-duplicated constants in first-use order (linear probe is fine: < 100 consts) */
+static uint32_t ctx_fixed(ctx_t* c, fr_t v) {
+  for (size_t i = 0; i < c->n_const; i++) if (fr_eq(c->consts[i], v)) return (uint32_t)i;
+  PUSH(c, consts, n_const, cap_const, v);
+  return (uint32_t)(c->n_const - 1);
+}
+
+/* FlexGateConfig::assign_region_in (halo2-lib v0.2.x flex_gate.rs): move to the next column if
+ * `row + len >= max_rows`, then append the cells vertically; gate selectors at `gate_offs`. */
+static void assign_region(ctx_t* c, const qc_t* cells, int n, const int* gate_offs, int n_offs, av_t* out) {
+  if (c->n_brk == 0) { PUSH(c, brk, n_brk, cap_brk, 0u); }
+  if (c->row + (uint32_t)n >= c->max_rows) {
+    c->row = 0; c->col += 1;
+    PUSH(c, brk, n_brk, cap_brk, (uint32_t)c->n_gate);
+  }
+  size_t base = c->n_gate;
+  if (c->n_gate + (size_t)n > c->cap_gate) {
+    while (c->n_gate + (size_t)n > c->cap_gate) c->cap_gate = c->cap_gate ? c->cap_gate * 2 : (1u << 16);
+    c->gate = xrealloc(c->gate, c->cap_gate * sizeof(fr_t));
+    c->sel = xrealloc(c->sel, c->cap_gate);
+  }
+  for (int i = 0; i < n; i++) {
+    c->gate[base + i] = cells[i].v;
+    c->sel[base + i] = 0;
+    if (cells[i].kind == QC_EXISTING) ctx_copy(c, CP_GATE, (uint32_t)(base + i), CP_GATE, cells[i].ex.idx);
+    else if (cells[i].kind == QC_CONSTANT && c->record_shape)
+      ctx_copy(c, CP_GATE, (uint32_t)(base + i), CP_FIXED, ctx_fixed(c, cells[i].v));
+    if (out) { out[i].idx = (uint32_t)(base + i); out[i].v = cells[i].v; }
+  }
+  for (int k = 0; k < n_offs; k++) c->sel[base + gate_offs[k]] = 1;
+  c->n_gate += n; c->row += n;
+}
+static const int OFF0[1] = {0};
+
+/* GateInstructions (halo2-lib v0.2.x flex_gate.rs); patterns in SURVEY.md 8a Table B */
+static av_t g_load_witness(ctx_t* c, fr_t w) { qc_t q = WIT(w); av_t o; assign_region(c, &q, 1, NULL, 0, &o); return o; }
+static av_t g_load_zero(ctx_t* c) {
+  if (c->has_zero) return c->zero_cell;
+  qc_t q = CONST_FR(FR_ZERO); av_t o; assign_region(c, &q, 1, NULL, 0, &o);
+  c->has_zero = 1; c->zero_cell = o; return o;
+}
+/* | a | b | 1 | a+b | */
+static av_t g_add(ctx_t* c, qc_t a, qc_t b) {
+  qc_t cells[4] = {a, b, CONST_FR(FR_R), WIT(fr_add(a.v, b.v))}; av_t o[4];
+  assign_region(c, cells, 4, OFF0, 1, o); return o[3];
+}
+/* | a-b | b | 1 | a | */
+static av_t g_sub(ctx_t* c, qc_t a, qc_t b) {
+  qc_t cells[4] = {WIT(fr_sub(a.v, b.v)), b, CONST_FR(FR_R), a}; av_t o[4];
+  assign_region(c, cells, 4, OFF0, 1, o); return o[0];
+}
+/* | a | -a | 1 | 0 | */
+static av_t g_neg(ctx_t* c, qc_t a) {
+  qc_t cells[4] = {a, WIT(fr_neg(a.v)), CONST_FR(FR_R), CONST_FR(FR_ZERO)}; av_t o[4];
+  assign_region(c, cells, 4, OFF0, 1, o); return o[1];
+}
+/* | 0 | a | b | a*b | */
+static av_t g_mul(ctx_t* c, qc_t a, qc_t b) {
+  qc_t cells[4] = {CONST_FR(FR_ZERO), a, b, WIT(fr_mul(a.v, b.v))}; av_t o[4];
+  assign_region(c, cells, 4, OFF0, 1, o); return o[3];
+}
+/* | c | a | b | a*b+c | */
+static av_t g_mul_add(ctx_t* c, qc_t a, qc_t b, qc_t cc) {
+  qc_t cells[4] = {cc, a, b, WIT(fr_add(fr_mul(a.v, b.v), cc.v))}; av_t o[4];
+  assign_region(c, cells, 4, OFF0, 1, o); return o[3];
+}
+/* | a-b | 1 | b | a |  | b | sel | a-b | out |, cells 0 and 6 copy-constrained */
+static av_t g_select(ctx_t* c, qc_t a, qc_t b, qc_t sel) {
+  fr_t diff = fr_sub(a.v, b.v);
+  fr_t outv = fr_add(fr_mul(diff, sel.v), b.v);
+  qc_t cells[8] = {WIT(diff), CONST_FR(FR_R), b, a, b, sel, WIT(diff), WIT(outv)}; av_t o[8];
+  static const int offs[2] = {0, 4};
+  assign_region(c, cells, 8, offs, 2, o);
+  ctx_copy(c, CP_GATE, o[0].idx, CP_GATE, o[6].idx);
+  return o[7];
+}
+/* | z | a | inv | 1 |  | 0 | a | z | 0 |, cells 0 and 6 copy-constrained */
+static av_t g_is_zero(ctx_t* c, av_t a) {
+  fr_t z, inv;
+  if (fr_is_zero(a.v)) { z = FR_R; inv = FR_R; } else { z = FR_ZERO; inv = fr_inv(a.v); }
+  qc_t cells[8] = {WIT(z), EX(a), WIT(inv), CONST_FR(FR_R), CONST_FR(FR_ZERO), EX(a), WIT(z), CONST_FR(FR_ZERO)}; av_t o[8];
+  static const int offs[2] = {0, 4};
+  assign_region(c, cells, 8, offs, 2, o);
+  ctx_copy(c, CP_GATE, o[0].idx, CP_GATE, o[6].idx);
+  return o[0];
+}
+static av_t g_is_equal(ctx_t* c, qc_t a, qc_t b) { av_t d = g_sub(c, a, b); return g_is_zero(c, d); }
+static void g_assert_equal(ctx_t* c, av_t a, av_t b) {
+  if (!fr_eq(a.v, b.v)) { fprintf(stderr, "oracle: assert_equal would fail (cells %u,%u)\n", a.idx, b.idx); abort(); }
+  ctx_copy(c, CP_GATE, a.idx, CP_GATE, b.idx);
+}
+static void g_assert_is_const(ctx_t* c, av_t a, fr_t k) {
+  if (!fr_eq(a.v, k)) { fprintf(stderr, "oracle: assert_is_const would fail\n"); abort(); }
+  if (c->record_shape) ctx_copy(c, CP_GATE, a.idx, CP_FIXED, ctx_fixed(c, k));
+}
+
+static void lk_push(ctx_t* c, av_t a) { PUSH(c, lk, n_lk, cap_lk, a.idx); }
+
+/* RangeConfig::range_check (halo2-lib v0.2.x range.rs, Vertical) */
+static void range_check(ctx_t* c, av_t a, uint32_t range_bits) {
+  uint32_t lb = c->lookup_bits;
+  uint32_t k = (range_bits + lb - 1) / lb;
+  uint32_t rem = range_bits % lb;
+  av_t last = a;
+  if (k == 1) {
+    lk_push(c, a);
+  } else {
+    /* decompose into k limbs of lookup_bits; inner product with limb_bases (first base == 1):
+     * | l0 | l1 | 2^lb | l0 + l1 2^lb | l2 | 2^2lb | acc | ... */
+    uint64_t canon[4]; fr_canon(a.v, canon);
+    qc_t cells[3 * 8 + 1]; int gate_offs[8]; int n = 0, ng = 0;
+    fr_t acc = FR_ZERO; av_t o[3 * 8 + 1]; int limb_pos[9];
+    if (k > 8) { fprintf(stderr, "oracle: range_check too wide\n"); abort(); }
+    for (uint32_t i = 0; i < k; i++) {
+      uint32_t bit = i * lb;
+      uint64_t limb = (canon[bit / 64] >> (bit % 64));
+      if (bit % 64 + lb > 64 && bit / 64 < 3) limb |= canon[bit / 64 + 1] << (64 - bit % 64);
+      limb &= (lb == 64) ? ~0ULL : ((1ULL << lb) - 1);
+      fr_t lf = fr_from_u64(limb);
+      if (i == 0) { acc = lf; limb_pos[0] = n; cells[n++] = WIT(lf); }
+      else {
+        fr_t base = FR_R; for (uint32_t s = 0; s < bit; s++) base = fr_add(base, base);
+        acc = fr_add(acc, fr_mul(lf, base));
+        gate_offs[ng++] = n - 1;
+        limb_pos[i] = n; cells[n++] = WIT(lf); cells[n++] = CONST_FR(base); cells[n++] = WIT(acc);
+      }
+    }
+    assign_region(c, cells, n, gate_offs, ng, o);
+    for (uint32_t i = 0; i < k; i++) lk_push(c, o[limb_pos[i]]);
+    last = o[limb_pos[k - 1]];
+    if (!fr_eq(acc, a.v)) { fprintf(stderr, "oracle: range_check(%u) value out of range\n", range_bits); abort(); }
+    ctx_copy(c, CP_GATE, a.idx, CP_GATE, o[n - 1].idx);
+  }
+  if (rem == 1) { fprintf(stderr, "oracle: assert_bit path not used by the reference\n"); abort(); }
+  if (rem > 1) {
+    /* | 0 | limb | 2^(lb-rem) | limb * 2^(lb-rem) |, result also looked up */
+    fr_t mult = fr_from_u64(1ULL << (lb - rem));
+    qc_t cells[4] = {CONST_FR(FR_ZERO), EX(last), CONST_FR(mult), WIT(fr_mul(last.v, mult))}; av_t o[4];
+    assign_region(c, cells, 4, OFF0, 1, o);
+    lk_push(c, o[3]);
+  }
+}
+
+static uint32_t bit_length(uint64_t x) { uint32_t n = 0; while (x) { n++; x >>= 1; } return n; }
+
+/* RangeConfig::is_less_than (Vertical) */
+static av_t range_is_less_than(ctx_t* c, qc_t a, qc_t b, uint32_t num_bits) {
+  uint32_t lb = c->lookup_bits;
+  uint32_t k = (num_bits + lb - 1) / lb;
+  uint32_t padded_bits = k * lb;
+  fr_t pow_padded = FR_R; for (uint32_t s = 0; s < padded_bits; s++) pow_padded = fr_add(pow_padded, pow_padded);
+  fr_t shift_a = fr_add(pow_padded, a.v);
+  fr_t shifted = fr_sub(shift_a, b.v);
+  qc_t cells[7] = {WIT(shifted), b, CONST_FR(FR_R), WIT(shift_a), CONST_FR(fr_neg(pow_padded)), CONST_FR(FR_R), a};
+  av_t o[7]; static const int offs[2] = {0, 3};
+  assign_region(c, cells, 7, offs, 2, o);
+  range_check(c, o[0], padded_bits + lb);
+  /* the last looked-up cell is the (k+1)-th limb of a - b + 2^padded: zero iff a < b */
+  av_t last; last.idx = c->lk[c->n_lk - 1]; last.v = c->gate[last.idx];
+  return g_is_zero(c, last);
+}
+/* RangeConfig::is_less_than_safe */
+static av_t range_is_less_than_safe(ctx_t* c, av_t a, uint64_t b) {
+  uint32_t lb = c->lookup_bits;
+  uint32_t range_bits = (bit_length(b) + lb - 1) / lb * lb;
+  range_check(c, a, range_bits);
+  return range_is_less_than(c, EX(a), CONST64(b), range_bits);
+}
+
+/* ------------------------------------------------------------------------- */
+/* src/utils.rs                                                               */
+/* ------------------------------------------------------------------------- */
+/* utils.rs:6-14 fe_to_bits_le: canonical bytes (BigUint::to_bytes_le, minimal length) -> LE bits, padded to size.
+ * Returns the number of bits; aborts where the Rust would underflow-panic. */
+static int fe_to_bits_le(fr_t v, int size, uint8_t* bits) {
+  uint64_t c[4]; fr_canon(v, c);
+  int nbytes = 32;
+  while (nbytes > 1 && ((c[(nbytes - 1) / 8] >> (8 * ((nbytes - 1) % 8))) & 0xff) == 0) nbytes--;
+  int n = nbytes * 8;
+  if (n > size) { fprintf(stderr, "oracle: fe_to_bits_le overflow (%d > %d)\n", n, size); abort(); }
+  for (int i = 0; i < n; i++) bits[i] = (c[i / 64] >> (i % 64)) & 1;
+  for (int i = n; i < size; i++) bits[i] = 0;
+  return size;
+}
+/* utils.rs:16-30 bits_le_to_fe (all call sites pass <= 64 bits, a multiple of 8) */
+static fr_t bits_le_to_fe(const uint8_t* bits, int n) {
+  if (n % 8 || n > 64) { fprintf(stderr, "oracle: bits_le_to_fe bad length %d\n", n); abort(); }
+  uint64_t v = 0;
+  for (int i = 0; i < n; i++) v |= (uint64_t)bits[i] << i;
+  return fr_from_u64(v);
+}
+
+/* ------------------------------------------------------------------------- */
+/* src/spread.rs                                                              */
+/* ------------------------------------------------------------------------- */
+/* spread.rs:196-233 spread_limb */
+static av_t spread_limb(ctx_t* c, av_t limb) {
+  size_t n = c->n_limb;
+  if (n == c->cap_limb) {
+    c->cap_limb = c->cap_limb ? c->cap_limb * 2 : 8192;
+    c->dense = xrealloc(c->dense, c->cap_limb * sizeof(fr_t));
+    c->spread = xrealloc(c->spread, c->cap_limb * sizeof(fr_t));
+    c->limb_gate_dense = xrealloc(c->limb_gate_dense, c->cap_limb * 4);
+    c->limb_gate_spread = xrealloc(c->limb_gate_spread, c->cap_limb * 4);
+  }
+  c->dense[n] = limb.v;                                  /* :203-210 */
+  uint8_t vb[32], sb[64];
+  fe_to_bits_le(limb.v, 32, vb);                          /* :212 */
+  memset(sb, 0, sizeof sb);
+  for (int i = 0; i < 32; i++) sb[2 * i] = vb[i];         /* :213-216 */
+  fr_t sv = bits_le_to_fe(sb, 64);                        /* :217 */
+  c->spread[n] = sv;                                      /* :219-224 */
+  av_t as = g_load_witness(c, sv);                        /* :225 */
+  c->limb_gate_dense[n] = limb.idx;                       /* :209-210 constrain_equal */
+  c->limb_gate_spread[n] = as.idx;                        /* :226-227 */
+  c->n_limb = n + 1;                                      /* :228-231 */
+  return as;
+}
+/* spread.rs:76-123 spread */
+static av_t spread_spread(ctx_t* c, av_t dense) {
+  uint32_t lb = c->limb_bits, nl = 16 / lb;
+  uint64_t canon[4]; fr_canon(dense.v, canon);
+  av_t limbs[16];
+  for (uint32_t i = 0; i < nl; i++) {                    /* :85-88 decompose + load_witness */
+    uint64_t l = (canon[0] >> (lb * i)) & ((1ULL << lb) - 1);
+    limbs[i] = g_load_witness(c, fr_from_u64(l));
+  }
+  av_t sum = g_load_zero(c);                              /* :90 */
+  for (uint32_t i = 0; i < nl; i++)                       /* :91-98 */
+    sum = g_mul_add(c, EX(limbs[i]), CONST64(1ULL << (lb * i)), EX(sum));
+  g_assert_equal(c, sum, dense);                          /* :104-108 */
+  av_t acc = g_load_zero(c);                              /* :110 */
+  for (uint32_t i = 0; i < nl; i++) {                     /* :112-121 */
+    av_t sl = spread_limb(c, limbs[i]);
+    acc = g_mul_add(c, EX(sl), CONST64(1ULL << (2 * lb * i)), EX(acc));
+  }
+  return acc;
+}
+/* spread.rs:139-163 decompose_even_and_odd_unchecked */
+static void decompose_even_odd(ctx_t* c, av_t spread, av_t* even, av_t* odd) {
+  uint8_t bits[32], eb[16], ob[16];
+  fe_to_bits_le(spread.v, 32, bits);                      /* :145 */
+  for (int i = 0; i < 16; i++) { eb[i] = bits[2 * i]; ob[i] = bits[2 * i + 1]; }
+  *even = g_load_witness(c, bits_le_to_fe(eb, 16));       /* :158 */
+  *odd = g_load_witness(c, bits_le_to_fe(ob, 16));        /* :159 */
+  range_check(c, *even, 16);                              /* :160 */
+  range_check(c, *odd, 16);                               /* :161 */
+}
+
+/* ------------------------------------------------------------------------- */
+/* src/compression.rs                                                         */
+/* ------------------------------------------------------------------------- */
+static const uint32_t ROUND_CONSTANTS[64] = {  /* FIPS 180-4 4.2.2; compression.rs:992-1001 */
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+static const uint32_t INIT_STATE[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a,   /* compression.rs:1003-1012 */
+                                       0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+
+typedef struct { av_t lo, hi; } spread_u32_t;             /* compression.rs:17 SpreadU32 */
+
+/* compression.rs:215-246 */
+static spread_u32_t state_to_spread_u32(ctx_t* c, av_t x) {
+  uint32_t x32 = fr_lower_32(x.v);
+  av_t lo = g_load_witness(c, fr_from_u64(x32 & 0xffff));       /* :222-230 */
+  av_t hi = g_load_witness(c, fr_from_u64(x32 >> 16));          /* :226-231 */
+  av_t composed = g_mul_add(c, EX(hi), CONST64(1ULL << 16), EX(lo));  /* :232-237 */
+  g_assert_equal(c, x, composed);                                /* :238-242 */
+  spread_u32_t s;
+  s.lo = spread_spread(c, lo);                                   /* :243 */
+  s.hi = spread_spread(c, hi);                                   /* :244 */
+  return s;
+}
+/* compression.rs:266-295 */
+static av_t mod_u32(ctx_t* c, av_t x) {
+  uint64_t x64 = fr_lower_64(x.v);
+  av_t lo = g_load_witness(c, fr_from_u64((uint32_t)x64));      /* :272-280 */
+  av_t hi = g_load_witness(c, fr_from_u64((x64 >> 32) & 0xffffffffULL)); /* :276-281 */
+  range_check(c, lo, 32);                                        /* :282 */
+  av_t composed = g_mul_add(c, EX(hi), CONST64(1ULL << 32), EX(lo));  /* :283-288 */
+  g_assert_equal(c, x, composed);                                /* :289-293 */
+  return lo;
+}
+/* compression.rs:521-530 */
+static av_t three_add(ctx_t* c, qc_t x, qc_t y, qc_t z) {
+  av_t add1 = g_add(c, x, y);
+  return g_add(c, EX(add1), z);
+}
+/* shared tail of ch / maj / sigma_generic: spread(even), spread(odd), 2*odd_spread + even_spread == v */
+static void check_even_odd(ctx_t* c, av_t even, av_t odd, av_t v) {
+  av_t es = spread_spread(c, even);
+  av_t os = spread_spread(c, odd);
+  av_t sum = g_mul_add(c, CONST64(2), EX(os), EX(es));
+  g_assert_equal(c, sum, v);
+}
+/* compression.rs:297-405 */
+static av_t ch(ctx_t* c, spread_u32_t x, spread_u32_t y, spread_u32_t z) {
+  av_t p_lo = g_add(c, EX(x.lo), EX(y.lo));                     /* :309-313 */
+  av_t p_hi = g_add(c, EX(x.hi), EX(y.hi));                     /* :314-318 */
+  const uint64_t MASK_EVEN_32 = 0x55555555ULL;                   /* :319 */
+  av_t x_neg_lo = g_neg(c, EX(x.lo));                           /* :320 */
+  av_t x_neg_hi = g_neg(c, EX(x.hi));                           /* :321 */
+  av_t q_lo = three_add(c, CONST64(MASK_EVEN_32), EX(x_neg_lo), EX(z.lo));  /* :322-328 */
+  av_t q_hi = three_add(c, CONST64(MASK_EVEN_32), EX(x_neg_hi), EX(z.hi));  /* :329-335 */
+  av_t p_lo_e, p_lo_o, p_hi_e, p_hi_o, q_lo_e, q_lo_o, q_hi_e, q_hi_o;
+  decompose_even_odd(c, p_lo, &p_lo_e, &p_lo_o);                 /* :336-343 */
+  decompose_even_odd(c, p_hi, &p_hi_e, &p_hi_o);
+  decompose_even_odd(c, q_lo, &q_lo_e, &q_lo_o);
+  decompose_even_odd(c, q_hi, &q_hi_e, &q_hi_o);
+  check_even_odd(c, p_lo_e, p_lo_o, p_lo);                       /* :344-354 */
+  check_even_odd(c, p_hi_e, p_hi_o, p_hi);                       /* :355-365 */
+  check_even_odd(c, q_lo_e, q_lo_o, q_lo);                       /* :366-376 */
+  check_even_odd(c, q_hi_e, q_hi_o, q_hi);                       /* :377-387 */
+  av_t out_lo = g_add(c, EX(p_lo_o), EX(q_lo_o));               /* :388-392 */
+  av_t out_hi = g_add(c, EX(p_hi_o), EX(q_hi_o));               /* :393-397 */
+  return g_mul_add(c, EX(out_hi), CONST64(1ULL << 16), EX(out_lo));  /* :398-403 */
+}
+/* compression.rs:460-519 */
+static av_t maj(ctx_t* c, spread_u32_t x, spread_u32_t y, spread_u32_t z) {
+  av_t m_lo = three_add(c, EX(x.lo), EX(y.lo), EX(z.lo));       /* :472-478 */
+  av_t m_hi = three_add(c, EX(x.hi), EX(y.hi), EX(z.hi));       /* :479-485 */
+  av_t m_lo_e, m_lo_o, m_hi_e, m_hi_o;
+  decompose_even_odd(c, m_lo, &m_lo_e, &m_lo_o);                 /* :486-489 */
+  decompose_even_odd(c, m_hi, &m_hi_e, &m_hi_o);
+  check_even_odd(c, m_lo_e, m_lo_o, m_lo);                       /* :490-500 */
+  check_even_odd(c, m_hi_e, m_hi_o, m_hi);                       /* :501-511 */
+  return g_mul_add(c, EX(m_hi_o), CONST64(1ULL << 16), EX(m_lo_o));  /* :512-517 */
+}
+/* compression.rs:702-882 */
+static av_t sigma_generic(ctx_t* c, const spread_u32_t* xs, const int starts[4], const int ends[4], const uint64_t coeffs[4]) {
+  uint8_t bits[64];
+  fe_to_bits_le(xs->lo.v, 32, bits);                             /* :714-718 */
+  fe_to_bits_le(xs->hi.v, 32, bits + 32);
+  av_t piece[4];
+  for (int k = 0; k < 4; k++) {                                  /* :719-734 assign_bits */
+    uint8_t pb[64]; memset(pb, 0, sizeof pb);
+    int n = 2 * ends[k] - 2 * starts[k];
+    memcpy(pb, bits + 2 * starts[k], n);
+    piece[k] = g_load_witness(c, bits_le_to_fe(pb, 64));
+  }
+  {                                                              /* :735-766 */
+    av_t sum = piece[0];
+    for (int k = 1; k < 4; k++)
+      sum = g_mul_add(c, EX(piece[k]), CONST64(1ULL << (2 * starts[k])), EX(sum));
+    av_t x_composed = g_mul_add(c, EX(xs->hi), CONST64(1ULL << 32), EX(xs->lo));
+    g_assert_equal(c, x_composed, sum);
+  }
+  av_t r_spread = g_load_zero(c);                                /* :775-810 */
+  for (int k = 0; k < 4; k++)
+    r_spread = g_mul_add(c, CONST64(coeffs[k]), EX(piece[k]), EX(r_spread));
+  uint64_t r64 = fr_lower_64(r_spread.v);                        /* :811-836 */
+  av_t r_lo = g_load_witness(c, fr_from_u64((uint32_t)r64));
+  av_t r_hi = g_load_witness(c, fr_from_u64((r64 >> 32) & 0xffffffffULL));
+  range_check(c, r_lo, 32);
+  range_check(c, r_hi, 32);
+  av_t composed = g_mul_add(c, EX(r_hi), CONST64(1ULL << 32), EX(r_lo));
+  g_assert_equal(c, r_spread, composed);
+  av_t lo_e, lo_o, hi_e, hi_o;
+  decompose_even_odd(c, r_lo, &lo_e, &lo_o);                     /* :843-846 */
+  decompose_even_odd(c, r_hi, &hi_e, &hi_o);
+  check_even_odd(c, lo_e, lo_o, r_lo);                           /* :852-862 */
+  check_even_odd(c, hi_e, hi_o, r_hi);                           /* :863-873 */
+  return g_mul_add(c, EX(hi_e), CONST64(1ULL << 16), EX(lo_e));  /* :874-879 */
+}
+#define B(n) (1ULL << (n))
+static av_t sigma_upper0(ctx_t* c, const spread_u32_t* x) {      /* compression.rs:594-619 */
+  static const int S[4] = {0, 2, 13, 22}, E[4] = {2, 13, 22, 32};
+  static const uint64_t K[4] = {B(60) + B(38) + B(20), B(0) + B(42) + B(24), B(22) + B(0) + B(46), B(40) + B(18) + B(0)};
+  return sigma_generic(c, x, S, E, K);
+}
+static av_t sigma_upper1(ctx_t* c, const spread_u32_t* x) {      /* compression.rs:621-646 */
+  static const int S[4] = {0, 6, 11, 25}, E[4] = {6, 11, 25, 32};
+  static const uint64_t K[4] = {B(52) + B(42) + B(14), B(0) + B(54) + B(26), B(10) + B(0) + B(36), B(38) + B(28) + B(0)};
+  return sigma_generic(c, x, S, E, K);
+}
+static av_t sigma_lower0(ctx_t* c, const spread_u32_t* x) {      /* compression.rs:648-673 */
+  static const int S[4] = {0, 3, 7, 18}, E[4] = {3, 7, 18, 32};
+  static const uint64_t K[4] = {B(50) + B(28), B(0) + B(56) + B(34), B(8) + B(0) + B(42), B(30) + B(22) + B(0)};
+  return sigma_generic(c, x, S, E, K);
+}
+static av_t sigma_lower1(ctx_t* c, const spread_u32_t* x) {      /* compression.rs:675-700 */
+  static const int S[4] = {0, 10, 17, 19}, E[4] = {10, 17, 19, 32};
+  static const uint64_t K[4] = {B(30) + B(26), B(0) + B(50) + B(46), B(14) + B(0) + B(60), B(18) + B(4) + B(0)};
+  return sigma_generic(c, x, S, E, K);
+}
+
+/* compression.rs:19-213 */
+static void sha256_compression(ctx_t* c, const av_t in_bytes[64], const av_t pre[8], av_t next[8]) {
+  av_t w[64]; spread_u32_t ws[64];
+  for (int i = 0; i < 16; i++) {                                 /* :31-47 */
+    av_t sum = g_load_zero(c);
+    for (int idx = 0; idx < 4; idx++)
+      sum = g_mul_add(c, EX(in_bytes[4 * i + 3 - idx]), CONST64(1ULL << (8 * idx)), EX(sum));
+    w[i] = sum;
+  }
+  for (int i = 0; i < 16; i++) ws[i] = state_to_spread_u32(c, w[i]);   /* :53-56 */
+  for (int idx = 16; idx < 64; idx++) {                          /* :57-96 */
+    av_t term1 = sigma_lower1(c, &ws[idx - 2]);
+    av_t term3 = sigma_lower0(c, &ws[idx - 15]);
+    av_t sum = g_add(c, EX(term1), EX(w[idx - 7]));
+    sum = g_add(c, EX(sum), EX(term3));
+    sum = g_add(c, EX(sum), EX(w[idx - 16]));
+    w[idx] = mod_u32(c, sum);
+    ws[idx] = state_to_spread_u32(c, w[idx]);
+  }
+  av_t a = pre[0], b = pre[1], cc = pre[2], d = pre[3], e = pre[4], f = pre[5], g = pre[6], h = pre[7];  /* :99-108 */
+  spread_u32_t a_s = state_to_spread_u32(c, a);                  /* :109-115 */
+  spread_u32_t b_s = state_to_spread_u32(c, b);
+  spread_u32_t c_s = state_to_spread_u32(c, cc);
+  spread_u32_t e_s = state_to_spread_u32(c, e);
+  spread_u32_t f_s = state_to_spread_u32(c, f);
+  spread_u32_t g_s = state_to_spread_u32(c, g);
+  g_load_zero(c); g_load_zero(c);                                /* :123-124 */
+  for (int idx = 0; idx < 64; idx++) {                           /* :125-196 */
+    av_t sigma_term = sigma_upper1(c, &e_s);
+    av_t ch_term = ch(c, e_s, f_s, g_s);
+    av_t add1 = g_add(c, EX(h), EX(sigma_term));
+    av_t add2 = g_add(c, EX(add1), EX(ch_term));
+    av_t add3 = g_add(c, EX(add2), CONST64(ROUND_CONSTANTS[idx]));
+    av_t add4 = g_add(c, EX(add3), EX(w[idx]));
+    av_t t1 = mod_u32(c, add4);
+    av_t sigma0 = sigma_upper0(c, &a_s);
+    av_t maj_term = maj(c, a_s, b_s, c_s);
+    av_t addt2 = g_add(c, EX(sigma0), EX(maj_term));
+    av_t t2 = mod_u32(c, addt2);
+    h = g; g = f; g_s = f_s; f = e; f_s = e_s;
+    av_t adde = g_add(c, EX(d), EX(t1));
+    e = mod_u32(c, adde);
+    e_s = state_to_spread_u32(c, e);
+    d = cc; cc = b; c_s = b_s; b = a; b_s = a_s;
+    av_t adda = g_add(c, EX(t1), EX(t2));
+    a = mod_u32(c, adda);
+    a_s = state_to_spread_u32(c, a);
+  }
+  av_t ns[8] = {a, b, cc, d, e, f, g, h};                        /* :197-212 */
+  for (int i = 0; i < 8; i++) {
+    av_t add = g_add(c, EX(ns[i]), EX(pre[i]));
+    next[i] = mod_u32(c, add);
+  }
+}
+
+/* plain SHA-256 compression (sha2::compress256, used un-constrained at lib.rs:160) */
+static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void plain_compress(uint32_t st[8], const uint8_t blk[64]) {
+  uint32_t w[64];
+  for (int i = 0; i < 16; i++) w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+  for (int i = 16; i < 64; i++) {
+    uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+    uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+    w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+  }
+  uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+  for (int i = 0; i < 64; i++) {
+    uint32_t t1 = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + ROUND_CONSTANTS[i] + w[i];
+    uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+/* ------------------------------------------------------------------------- */
+/* src/lib.rs:71-349  Sha256DynamicConfig::digest                             */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t input_len_idx;         /* AssignedHashResult.input_len   (gate stream index) */
+  uint32_t* input_bytes_idx;      /* .input_bytes, max_bytes entries                    */
+  uint32_t output_bytes_idx[32];  /* .output_bytes                                      */
+  uint8_t digest[32];
+} digest_result_t;
+
+/* returns 0, or a negative code where the Rust would panic (lib.rs:89-90) */
+static int digest(ctx_t* c, uint32_t max_bytes, int is_input_range_check, const uint8_t* input, size_t input_len,
+                  size_t precomputed_input_len, digest_result_t* res) {
+  const size_t one = 64;
+  size_t with9 = input_len + 9;                                   /* :77-78 */
+  size_t num_round = (with9 % one == 0) ? with9 / one : with9 / one + 1;   /* :80-84 */
+  size_t padded_size = one * num_round;                           /* :85 */
+  size_t max_round = max_bytes / one;                             /* :87 */
+  if (precomputed_input_len % one != 0) return -1;                /* :89 */
+  if (padded_size < precomputed_input_len || padded_size - precomputed_input_len > max_bytes) return -2;   /* :90 */
+  size_t zero_padding = padded_size - with9;                      /* :91 */
+  size_t remaining = max_bytes + precomputed_input_len - padded_size;   /* :92 */
+  size_t precomputed_round = precomputed_input_len / one;         /* :93 */
+  if (remaining != one * (max_round + precomputed_round - num_round)) return -3;   /* :94-97 */
+  size_t total = max_bytes + precomputed_input_len;
+  uint8_t* padded = calloc(total ? total : 1, 1);
+  memcpy(padded, input, input_len);                               /* :98 */
+  padded[input_len] = 0x80;                                       /* :99 */
+  (void)zero_padding;                                             /* :100-102 zeros already there */
+  uint64_t bitlen = 8 * (uint64_t)input_len;                      /* :103-108 big-endian bit length */
+  for (int i = 0; i < 8; i++) padded[padded_size - 1 - i] = (uint8_t)(bitlen >> (8 * i));
+
+  av_t a_len = g_load_witness(c, fr_from_u64(input_len));        /* :124-125 */
+  av_t a_num_round = g_load_witness(c, fr_from_u64(num_round));  /* :126 */
+  av_t a_padded = g_mul(c, EX(a_num_round), CONST64(one));       /* :127-131 */
+  av_t a_with9 = g_add(c, EX(a_len), CONST64(9));                /* :132-136 */
+  av_t padding_size = g_sub(c, EX(a_padded), EX(a_with9));       /* :137-141 */
+  av_t lt = range_is_less_than_safe(c, padding_size, one);       /* :142-143 */
+  g_assert_is_const(c, lt, FR_R);                                 /* :144 */
+  av_t a_pre_round = g_load_witness(c, fr_from_u64(precomputed_round));   /* :145-146 */
+  av_t a_target = g_sub(c, EX(a_num_round), EX(a_pre_round));    /* :147-151 */
+
+  uint32_t st[8]; memcpy(st, INIT_STATE, sizeof st);              /* :153-160 */
+  for (size_t blk = 0; blk < precomputed_round; blk++) plain_compress(st, padded + 64 * blk);
+
+  av_t (*states)[8] = malloc((max_round + 1) * sizeof *states);
+  for (int i = 0; i < 8; i++) states[0][i] = g_load_witness(c, fr_from_u64(st[i]));   /* :162-165 */
+  av_t* in_bytes = malloc((max_bytes ? max_bytes : 1) * sizeof(av_t));
+  for (size_t i = 0; i < max_bytes; i++)                          /* :170-173 */
+    in_bytes[i] = g_load_witness(c, fr_from_u64(padded[precomputed_input_len + i]));
+  if (is_input_range_check)                                       /* :174-178 */
+    for (size_t i = 0; i < max_bytes; i++) range_check(c, in_bytes[i], 8);
+  size_t n_state = 1;
+  for (size_t off = 0; off < max_bytes; off += one) {             /* :179-238 */
+    sha256_compression(c, in_bytes + off, states[n_state - 1], states[n_state]);
+    n_state++;
+  }
+  av_t zero = g_load_zero(c);                                     /* :294 */
+  av_t out_h[8]; for (int i = 0; i < 8; i++) out_h[i] = zero;     /* :295 */
+  for (size_t n = 0; n < n_state; n++) {                          /* :296-310 */
+    av_t selector = g_is_equal(c, CONST64(n), EX(a_target));
+    for (int i = 0; i < 8; i++) out_h[i] = g_select(c, EX(states[n][i]), EX(out_h[i]), EX(selector));
+  }
+  for (int wi = 0; wi < 8; wi++) {                                /* :311-341 */
+    uint32_t word = fr_lower_32(out_h[wi].v);
+    av_t bytes[4];
+    for (int idx = 0; idx < 4; idx++) {
+      uint8_t bv = (uint8_t)(word >> (24 - 8 * idx));             /* to_be_bytes()[idx] */
+      bytes[idx] = g_load_witness(c, fr_from_u64(bv));
+      range_check(c, bytes[idx], 8);
+      res->digest[4 * wi + idx] = bv;
+      res->output_bytes_idx[4 * wi + idx] = bytes[idx].idx;
+    }
+    av_t sum = g_load_zero(c);
+    for (int idx = 0; idx < 4; idx++)
+      sum = g_mul_add(c, EX(bytes[idx]), CONST64(1ULL << (24 - 8 * idx)), EX(sum));
+    g_assert_equal(c, out_h[wi], sum);
+  }
+  res->input_len_idx = a_len.idx;
+  res->input_bytes_idx = malloc((max_bytes ? max_bytes : 1) * 4);
+  for (size_t i = 0; i < max_bytes; i++) res->input_bytes_idx[i] = in_bytes[i].idx;
+  free(in_bytes); free(states); free(padded);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* C API (ctypes / bench)                                                     */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t n_digests;            /* digest() calls sharing one Context (tests: 2, bench: 1) */
+  const uint32_t* max_bytes;     /* max_variable_byte_sizes, one per digest                 */
+  uint32_t max_rows;             /* range.gate.max_rows = 2^k - minimum_rows                */
+  uint32_t lookup_bits;
+  uint32_t limb_bits;
+  uint32_t spread_cols;
+  uint32_t is_input_range_check;
+} h2o_cfg_t;
+
+typedef struct {
+  ctx_t ctx;
+  digest_result_t* res;
+  uint32_t n_digests;
+} h2o_run_t;
+
+static void ctx_free(ctx_t* c) {
+  free(c->gate); free(c->sel); free(c->brk); free(c->lk); free(c->dense); free(c->spread);
+  free(c->limb_gate_dense); free(c->limb_gate_spread); free(c->copies); free(c->consts);
+  memset(c, 0, sizeof *c);
+}
+
+/* Synthesize one region (one Context): cfg->n_digests digest() calls, then range.finalize.
+ * msgs[d] / lens[d] / pre_lens[d] per digest.  Returns NULL + *err on a would-be panic. */
+h2o_run_t* h2o_synthesize(const h2o_cfg_t* cfg, const uint8_t* const* msgs, const uint32_t* lens, const uint32_t* pre_lens,
+                          int record_shape, int* err) {
+  fr_init();
+  h2o_run_t* r = calloc(1, sizeof *r);
+  r->ctx.max_rows = cfg->max_rows; r->ctx.lookup_bits = cfg->lookup_bits; r->ctx.limb_bits = cfg->limb_bits;
+  r->ctx.spread_cols = cfg->spread_cols; r->ctx.record_shape = record_shape;
+  r->res = calloc(cfg->n_digests, sizeof *r->res);
+  r->n_digests = cfg->n_digests;
+  for (uint32_t d = 0; d < cfg->n_digests; d++) {
+    int rc = digest(&r->ctx, cfg->max_bytes[d], (int)cfg->is_input_range_check, msgs[d], lens[d], pre_lens ? pre_lens[d] : 0, &r->res[d]);
+    if (rc) { if (err) *err = rc; ctx_free(&r->ctx); free(r->res); free(r); return NULL; }
+  }
+  if (err) *err = 0;
+  return r;
+}
+void h2o_free(h2o_run_t* r) {
+  if (!r) return;
+  for (uint32_t d = 0; d < r->n_digests; d++) free(r->res[d].input_bytes_idx);
+  ctx_free(&r->ctx); free(r->res); free(r);
+}
+/* sizes: [n_gate, n_lookup, n_limb, n_copy, n_const, n_cols] */
+void h2o_sizes(const h2o_run_t* r, uint64_t out[6]) {
+  out[0] = r->ctx.n_gate; out[1] = r->ctx.n_lk; out[2] = r->ctx.n_limb; out[3] = r->ctx.n_copy;
+  out[4] = r->ctx.n_const; out[5] = r->ctx.n_brk;
+}
+const uint64_t* h2o_gate(const h2o_run_t* r) { return (const uint64_t*)r->ctx.gate; }       /* n_gate x 4 u64, stream order */
+const uint8_t* h2o_selectors(const h2o_run_t* r) { return r->ctx.sel; }
+const uint32_t* h2o_breaks(const h2o_run_t* r) { return r->ctx.brk; }                         /* stream idx where column c starts */
+const uint32_t* h2o_lookup_idx(const h2o_run_t* r) { return r->ctx.lk; }                      /* cells_to_lookup (gate stream idx) */
+const uint64_t* h2o_dense(const h2o_run_t* r) { return (const uint64_t*)r->ctx.dense; }     /* limb order */
+const uint64_t* h2o_spread(const h2o_run_t* r) { return (const uint64_t*)r->ctx.spread; }
+const uint32_t* h2o_limb_gate_dense(const h2o_run_t* r) { return r->ctx.limb_gate_dense; }
+const uint32_t* h2o_limb_gate_spread(const h2o_run_t* r) { return r->ctx.limb_gate_spread; }
+const uint32_t* h2o_copies(const h2o_run_t* r) { return (const uint32_t*)r->ctx.copies; }    /* n_copy x (a_kind,a_idx,b_kind,b_idx) */
+const uint64_t* h2o_consts(const h2o_run_t* r) { return (const uint64_t*)r->ctx.consts; }
+const uint8_t* h2o_digest(const h2o_run_t* r, uint32_t d) { return r->res[d].digest; }
+uint32_t h2o_input_len_idx(const h2o_run_t* r, uint32_t d) { return r->res[d].input_len_idx; }
+const uint32_t* h2o_input_bytes_idx(const h2o_run_t* r, uint32_t d) { return r->res[d].input_bytes_idx; }
+const uint32_t* h2o_output_bytes_idx(const h2o_run_t* r, uint32_t d) { return r->res[d].output_bytes_idx; }
+
+/* Field helpers exported for tests (Montgomery <-> canonical, constants) */
+void h2o_fr_from_u64(uint64_t v, uint64_t out[4]) { fr_init(); fr_t f = fr_from_u64(v); memcpy(out, f.l, 32); }
+void h2o_fr_canon(const uint64_t in[4], uint64_t out[4]) { fr_init(); fr_t f; memcpy(f.l, in, 32); fr_canon(f, out); }
+void h2o_fr_consts(uint64_t r[4], uint64_t r2[4], uint64_t* inv) { fr_init(); memcpy(r, FR_R.l, 32); memcpy(r2, FR_R2.l, 32); *inv = P_INV; }
+
+/* ------------------------------------------------------------------------- */
+/* Column-major witness writer + checksums: the same output contract as the   */
+/* CUDA engine (include/h2sha_b200.h), used for parity tests and as the CPU   */
+/* baseline.  One instance = one Context.                                     */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t n_gate_cols, gate_col_rows;      /* gate:   [n_gate_cols][gate_col_rows] Fr        */
+  uint32_t n_lookup_cols, lookup_col_rows;  /* lookup: [n_lookup_cols][lookup_col_rows] Fr    */
+  uint32_t spread_rows;                     /* spread: [2*spread_cols][spread_rows] Fr (dense_0.., spread_0..) */
+} h2o_layout_t;
+
+/* cell checksum: sum over cells of (sum_k limb32_k * M_k mod 2^32) * (2*pos+1 mod 2^32), mod 2^64; pos = index in the
+ * instance's column-major buffer of that kind (see include/h2sha_b200.h) */
+static const uint32_t CK_M[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+static uint64_t cell_ck(const fr_t* v, uint64_t pos) {
+  const uint32_t* w = (const uint32_t*)v->l;
+  uint32_t h = 0;
+  for (int k = 0; k < 8; k++) h += w[k] * CK_M[k];
+  return (uint64_t)h * (uint64_t)(uint32_t)(2 * pos + 1);
+}
+
+/* Writes one synthesized region into column-major buffers (zero elsewhere) and returns checksums
+ * ck[0]=gate, ck[1]=lookup, ck[2]=spread, ck[3]=sum of the three. Buffers may be NULL (checksums only). */
+int h2o_emit(const h2o_run_t* r, const h2o_layout_t* L, uint64_t* gate, uint64_t* lookup, uint64_t* spread, uint64_t ck[4]) {
+  const ctx_t* c = &r->ctx;
+  uint64_t cg = 0, cl = 0, cs = 0;
+  if (c->n_brk > L->n_gate_cols) return -10;
+  if (gate) memset(gate, 0, (size_t)L->n_gate_cols * L->gate_col_rows * 32);
+  if (lookup) memset(lookup, 0, (size_t)L->n_lookup_cols * L->lookup_col_rows * 32);
+  if (spread) memset(spread, 0, (size_t)2 * c->spread_cols * L->spread_rows * 32);
+  for (size_t col = 0; col < c->n_brk; col++) {
+    size_t s = c->brk[col], e = (col + 1 < c->n_brk) ? c->brk[col + 1] : c->n_gate;
+    if (e - s > L->gate_col_rows) return -11;
+    for (size_t i = s; i < e; i++) {
+      uint64_t pos = (uint64_t)col * L->gate_col_rows + (i - s);
+      if (gate) memcpy(gate + 4 * pos, c->gate[i].l, 32);
+      cg += cell_ck(&c->gate[i], pos);
+    }
+  }
+  /* range.finalize -> Context::copy_and_lookup_cells: column after column, rows 0..max_rows-1 */
+  for (size_t i = 0; i < c->n_lk; i++) {
+    size_t col = i / c->max_rows, row = i % c->max_rows;
+    if (col >= L->n_lookup_cols || row >= L->lookup_col_rows) return -12;
+    uint64_t pos = (uint64_t)col * L->lookup_col_rows + row;
+    if (lookup) memcpy(lookup + 4 * pos, c->gate[c->lk[i]].l, 32);
+    cl += cell_ck(&c->gate[c->lk[i]], pos);
+  }
+  for (size_t n = 0; n < c->n_limb; n++) {
+    size_t col = n % c->spread_cols, row = n / c->spread_cols;     /* spread.rs:202,228-231 */
+    if (row >= L->spread_rows) return -13;
+    uint64_t pd = (uint64_t)col * L->spread_rows + row;
+    uint64_t ps = (uint64_t)(c->spread_cols + col) * L->spread_rows + row;
+    if (spread) { memcpy(spread + 4 * pd, c->dense[n].l, 32); memcpy(spread + 4 * ps, c->spread[n].l, 32); }
+    cs += cell_ck(&c->dense[n], pd) + cell_ck(&c->spread[n], ps);
+  }
+  if (ck) { ck[0] = cg; ck[1] = cl; ck[2] = cs; ck[3] = cg + cl + cs; }
+  return 0;
+}
+
+/* Batch runner (CPU baseline): n_inst instances, each cfg->n_digests messages; message m = inst*n_digests + d is
+ * bytes[offs[m] .. offs[m]+lens[m]).  Writes digests [n_msgs][32] and checksums [n_inst][4]; optionally the full
+ * column-major witness of every instance into gate/lookup/spread (instance-major).  n_threads pthreads. */
+typedef struct {
+  const h2o_cfg_t* cfg; const h2o_layout_t* L;
+  const uint8_t* bytes; const uint64_t* offs; const uint32_t* lens; const uint32_t* pre_lens;
+  uint64_t first, last;
+  uint8_t* digests; uint64_t* cks; uint64_t* gate; uint64_t* lookup; uint64_t* spread;
+  int err;
+} job_t;
+
+static void* batch_worker(void* arg) {
+  job_t* j = arg;
+  uint32_t D = j->cfg->n_digests;
+  const uint8_t** msgs = malloc(D * sizeof *msgs);
+  size_t gsz = (size_t)j->L->n_gate_cols * j->L->gate_col_rows * 4;
+  size_t lsz = (size_t)j->L->n_lookup_cols * j->L->lookup_col_rows * 4;
+  size_t ssz = (size_t)2 * j->cfg->spread_cols * j->L->spread_rows * 4;
+  for (uint64_t i = j->first; i < j->last; i++) {
+    for (uint32_t d = 0; d < D; d++) msgs[d] = j->bytes + j->offs[i * D + d];
+    int err = 0;
+    h2o_run_t* r = h2o_synthesize(j->cfg, msgs, j->lens + i * D, j->pre_lens ? j->pre_lens + i * D : NULL, 0, &err);
+    if (!r) { j->err = err; break; }
+    for (uint32_t d = 0; d < D; d++) memcpy(j->digests + (i * D + d) * 32, r->res[d].digest, 32);
+    int rc = h2o_emit(r, j->L, j->gate ? j->gate + i * gsz : NULL, j->lookup ? j->lookup + i * lsz : NULL,
+                      j->spread ? j->spread + i * ssz : NULL, j->cks + 4 * i);
+    h2o_free(r);
+    if (rc) { j->err = rc; break; }
+  }
+  free(msgs);
+  return NULL;
+}
+
+int h2o_batch(const h2o_cfg_t* cfg, const h2o_layout_t* L, uint64_t n_inst, const uint8_t* bytes, const uint64_t* offs,
+              const uint32_t* lens, const uint32_t* pre_lens, uint8_t* digests, uint64_t* cks,
+              uint64_t* gate, uint64_t* lookup, uint64_t* spread, int n_threads) {
+  fr_init();
+  if (n_threads < 1) n_threads = 1;
+  if ((uint64_t)n_threads > n_inst) n_threads = n_inst ? (int)n_inst : 1;
+  job_t* jobs = calloc(n_threads, sizeof *jobs);
+  pthread_t* th = calloc(n_threads, sizeof *th);
+  for (int t = 0; t < n_threads; t++) {
+    jobs[t] = (job_t){cfg, L, bytes, offs, lens, pre_lens, n_inst * t / n_threads, n_inst * (t + 1) / n_threads,
+                      digests, cks, gate, lookup, spread, 0};
+    if (n_threads == 1) batch_worker(&jobs[t]); else pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+  }
+  int err = 0;
+  for (int t = 0; t < n_threads; t++) { if (n_threads > 1) pthread_join(th[t], NULL); if (jobs[t].err) err = jobs[t].err; }
+  free(jobs); free(th);
+  return err;
+}
