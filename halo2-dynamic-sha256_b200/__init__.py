@@ -1,0 +1,308 @@
+"""halo2-dynamic-sha256_b200 -- host-side mirror of the reference's chip API over the C-ABI engine.
+
+The reference (zhmolly/halo2-dynamic-sha256) is a Rust crate; no Rust toolchain exists in this image, so the
+host side above the C-ABI (include/h2sha_b200.h, built from csrc/) is mirrored here in Python for the tests
+and the benchmark, and in C++ (csrc/host_api.hpp) / Rust source (rust/) for integrators.  Names, argument
+meaning and error behaviour follow `Sha256DynamicConfig` (reference src/lib.rs:38-369):
+
+    configure(max_variable_byte_sizes, range..., num_bits_lookup, num_advice_columns, is_input_range_check)   lib.rs:49-56
+    digest(input, precomputed_input_len) -> AssignedHashResult{input_len, input_bytes, output_bytes}          lib.rs:71-76
+
+PyTorch is used only to own device memory and streams; all compute happens in libh2sha_b200.so.  There is no
+CPU fallback: without a GPU only the static plan (layout, shape, handles) can be queried (`device=-1`); every
+witness-generating call raises `EngineError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libh2sha_b200.so")
+
+H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3, -4
+
+# symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape",
+    "h2sha_digest_batch", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_last_launch_count", "H2SHA_CK_M",
+]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"h2sha error {code}: {msg}")
+        self.code = code
+
+
+class ReferencePanic(EngineError):
+    """Input on which the reference panics (lib.rs:89-90)."""
+
+
+class _Config(C.Structure):
+    _fields_ = [("n_digests", C.c_uint32), ("max_variable_byte_sizes", C.POINTER(C.c_uint32)), ("max_rows", C.c_uint32),
+                ("lookup_bits", C.c_uint32), ("num_bits_lookup", C.c_uint32), ("num_advice_columns", C.c_uint32),
+                ("is_input_range_check", C.c_uint32), ("gate_col_rows", C.c_uint32), ("lookup_col_rows", C.c_uint32),
+                ("spread_rows", C.c_uint32), ("device", C.c_int32), ("build_shape", C.c_uint32)]
+
+
+class _Layout(C.Structure):
+    _fields_ = [("n_digests", C.c_uint32), ("n_gate_cells", C.c_uint32), ("n_lookup_cells", C.c_uint32), ("n_spread_limbs", C.c_uint32),
+                ("n_gate_cols", C.c_uint32), ("gate_col_rows", C.c_uint32), ("n_lookup_cols", C.c_uint32), ("lookup_col_rows", C.c_uint32),
+                ("n_spread_cols", C.c_uint32), ("spread_rows", C.c_uint32), ("n_blocks", C.c_uint32), ("n_fixed", C.c_uint32),
+                ("n_copies", C.c_uint32), ("n_selectors_on", C.c_uint32), ("cells_per_instance", C.c_uint64), ("gate_bytes", C.c_uint64),
+                ("lookup_bytes", C.c_uint64), ("spread_bytes", C.c_uint64)]
+
+
+class _Batch(C.Structure):
+    _fields_ = [("n_instances", C.c_uint64), ("msgs", C.c_void_p), ("msgs_on_device", C.c_int32), ("msgs_bytes", C.c_uint64),
+                ("offsets", C.c_void_p), ("lens", C.c_void_p), ("precomputed_lens", C.c_void_p), ("gate", C.c_void_p), ("lookup", C.c_void_p),
+                ("spread", C.c_void_p), ("digests_dev", C.c_void_p), ("checksums_dev", C.c_void_p), ("digests_host", C.c_void_p),
+                ("checksums_host", C.c_void_p), ("stream", C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree engine; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.h2sha_create.restype = C.c_int
+    L.h2sha_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    L.h2sha_destroy.argtypes = [C.c_void_p]
+    L.h2sha_last_error.restype = C.c_char_p
+    L.h2sha_get_layout.argtypes = [C.c_void_p, C.POINTER(_Layout)]
+    L.h2sha_get_breaks.argtypes = [C.c_void_p, C.c_void_p]
+    L.h2sha_get_handles.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.h2sha_get_shape.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
+    L.h2sha_zero_outputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.h2sha_debug_mont_from_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.h2sha_last_launch_count.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != H2SHA_OK:
+        msg = load_library().h2sha_last_error().decode()
+        raise (ReferencePanic if rc == H2SHA_EPANIC else EngineError)(rc, msg)
+
+
+@dataclass
+class Layout:
+    n_digests: int
+    n_gate_cells: int
+    n_lookup_cells: int
+    n_spread_limbs: int
+    n_gate_cols: int
+    gate_col_rows: int
+    n_lookup_cols: int
+    lookup_col_rows: int
+    n_spread_cols: int
+    spread_rows: int
+    n_blocks: int
+    n_fixed: int
+    n_copies: int
+    n_selectors_on: int
+    cells_per_instance: int
+    gate_bytes: int
+    lookup_bytes: int
+    spread_bytes: int
+
+    @property
+    def bytes_per_instance(self) -> int:
+        return self.gate_bytes + self.lookup_bytes + self.spread_bytes
+
+
+@dataclass
+class Shape:
+    selectors: np.ndarray        # [n_gate] u8
+    copies: np.ndarray           # [n_copies,4] u32
+    fixed: np.ndarray            # [n_fixed,4] u64 canonical
+    lookup_src: np.ndarray       # [n_lookup] u32
+    limb_dense_src: np.ndarray   # [n_limb] u32
+    limb_spread_src: np.ndarray  # [n_limb] u32
+
+
+@dataclass
+class AssignedHashResult:
+    """lib.rs:31-36: handles are gate-stream indices (map to (column,row) with `Sha256DynamicConfig.cell_position`)."""
+    input_len: int
+    input_bytes: np.ndarray
+    output_bytes: np.ndarray
+
+
+@dataclass
+class BatchResult:
+    digests: Optional[np.ndarray]      # [n_msgs,32] u8 (host) when requested
+    checksums: Optional[np.ndarray]    # [n_inst,4] u64 (host) when requested
+    gate: object = None                # torch tensors [n_inst, cols, rows, 4] int64 (device) when requested
+    lookup: object = None
+    spread: object = None
+
+
+def pack_messages(instances: Sequence[Sequence[bytes]]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """[[msg_d0, msg_d1, ...] per instance] -> (blob u8, offsets u64, lens u32)."""
+    flat = [bytes(m) for inst in instances for m in inst]
+    lens = np.array([len(m) for m in flat], dtype=np.uint32)
+    offs = np.zeros(len(flat), dtype=np.uint64)
+    if len(flat) > 1:
+        offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(flat), dtype=np.uint8).copy() if lens.sum() else np.zeros(0, dtype=np.uint8)
+    return blob, offs, lens
+
+
+class Sha256DynamicConfig:
+    """Mirror of the reference's `Sha256DynamicConfig<F>` (lib.rs:38-45) for F = bn256::Fr, batch-oriented."""
+
+    ONE_ROUND_INPUT_BYTES = 64  # lib.rs:48
+
+    def __init__(self, handle, max_variable_byte_sizes, device):
+        self._h = handle
+        self.max_variable_byte_sizes = list(max_variable_byte_sizes)
+        self.device = device
+        self._layout = None
+
+    # lib.rs:49-69 (+ RangeConfig::configure's lookup_bits / k -> max_rows, lib.rs:409-418)
+    @classmethod
+    def configure(cls, max_variable_byte_sizes: Sequence[int], *, max_rows: int = (1 << 17) - 9, lookup_bits: int = 16,
+                  num_bits_lookup: int = 8, num_advice_columns: int = 2, is_input_range_check: bool = True, device: int = 0,
+                  build_shape: bool = False, gate_col_rows: int = 0, lookup_col_rows: int = 0, spread_rows: int = 0) -> "Sha256DynamicConfig":
+        L = load_library()
+        sizes = (C.c_uint32 * len(max_variable_byte_sizes))(*max_variable_byte_sizes)
+        cfg = _Config(len(max_variable_byte_sizes), sizes, max_rows, lookup_bits, num_bits_lookup, num_advice_columns,
+                      1 if is_input_range_check else 0, gate_col_rows, lookup_col_rows, spread_rows, device, 1 if build_shape else 0)
+        h = C.c_void_p()
+        _check(L.h2sha_create(C.byref(cfg), C.byref(h)))
+        return cls(h, max_variable_byte_sizes, device)
+
+    def close(self):
+        if self._h:
+            load_library().h2sha_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def layout(self) -> Layout:
+        if self._layout is None:
+            l = _Layout()
+            _check(load_library().h2sha_get_layout(self._h, C.byref(l)))
+            self._layout = Layout(*[int(getattr(l, f[0])) for f in _Layout._fields_])
+        return self._layout
+
+    def breaks(self) -> np.ndarray:
+        b = np.zeros(self.layout.n_gate_cols, dtype=np.uint32)
+        _check(load_library().h2sha_get_breaks(self._h, b.ctypes.data_as(C.c_void_p)))
+        return b
+
+    def cell_position(self, stream_idx):
+        """gate-stream index -> (column, row)."""
+        b = self.breaks()
+        col = np.searchsorted(b, stream_idx, side="right") - 1
+        return col, np.asarray(stream_idx) - b[col]
+
+    def handles(self, d: int = 0) -> AssignedHashResult:
+        il = C.c_uint32()
+        ib = np.zeros(self.max_variable_byte_sizes[d], dtype=np.uint32)
+        ob = np.zeros(32, dtype=np.uint32)
+        _check(load_library().h2sha_get_handles(self._h, d, C.byref(il), ib.ctypes.data_as(C.c_void_p), ob.ctypes.data_as(C.c_void_p)))
+        return AssignedHashResult(int(il.value), ib, ob)
+
+    def shape(self) -> Shape:
+        lay = self.layout
+        sel = np.zeros(lay.n_gate_cells, dtype=np.uint8)
+        cp = np.zeros((lay.n_copies, 4), dtype=np.uint32)
+        fx = np.zeros((lay.n_fixed, 4), dtype=np.uint64)
+        ls = np.zeros(lay.n_lookup_cells, dtype=np.uint32)
+        ld = np.zeros(lay.n_spread_limbs, dtype=np.uint32)
+        lsp = np.zeros(lay.n_spread_limbs, dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _check(load_library().h2sha_get_shape(self._h, p(sel), p(cp), p(fx), p(ls), p(ld), p(lsp)))
+        return Shape(sel, cp, fx, ls, ld, lsp)
+
+    # ------------------------------------------------------------------------------------------------
+    def alloc_outputs(self, n_instances: int, zero: bool = True):
+        """Device buffers [n_inst, cols, rows, 4] int64 for gate / lookup / spread."""
+        import torch
+        lay = self.layout
+        dev = torch.device("cuda", self.device)
+        mk = (torch.zeros if zero else torch.empty)
+        gate = mk((n_instances, lay.n_gate_cols, lay.gate_col_rows, 4), dtype=torch.int64, device=dev)
+        lookup = mk((n_instances, lay.n_lookup_cols, lay.lookup_col_rows, 4), dtype=torch.int64, device=dev)
+        spread = mk((n_instances, lay.n_spread_cols, lay.spread_rows, 4), dtype=torch.int64, device=dev)
+        return gate, lookup, spread
+
+    def digest_batch_raw(self, n_instances: int, msgs_ptr: int, msgs_on_device: bool, msgs_bytes: int, offsets: np.ndarray, lens: np.ndarray,
+                         precomputed_lens: Optional[np.ndarray], *, gate_ptr: int = 0, lookup_ptr: int = 0, spread_ptr: int = 0,
+                         digests_dev_ptr: int = 0, checksums_dev_ptr: int = 0, digests_host_ptr: int = 0, checksums_host_ptr: int = 0,
+                         stream: int = 0):
+        """Thin wrapper over h2sha_digest_batch (all pointers are integers)."""
+        assert offsets.dtype == np.uint64 and lens.dtype == np.uint32
+        b = _Batch(n_instances, msgs_ptr, 1 if msgs_on_device else 0, msgs_bytes, offsets.ctypes.data, lens.ctypes.data,
+                   precomputed_lens.ctypes.data if precomputed_lens is not None else None, gate_ptr or None, lookup_ptr or None,
+                   spread_ptr or None, digests_dev_ptr or None, checksums_dev_ptr or None, digests_host_ptr or None,
+                   checksums_host_ptr or None, stream or None)
+        _check(load_library().h2sha_digest_batch(self._h, C.byref(b)))
+
+    def digest_batch(self, instances: Sequence[Sequence[bytes]], precomputed_input_lens: Optional[Sequence[Sequence[int]]] = None, *,
+                     want_cells: bool = True, outputs=None) -> BatchResult:
+        """digest() (lib.rs:71-349) for every message of every instance.  instances[i][d] is the input of the d-th
+        digest call of instance i; precomputed_input_lens[i][d] its `precomputed_input_len` (None = no prefix)."""
+        import torch
+        D = len(self.max_variable_byte_sizes)
+        n = len(instances)
+        for inst in instances:
+            if len(inst) != D:
+                raise EngineError(H2SHA_EINVAL, f"each instance needs {D} messages")
+        blob, offs, lens = pack_messages(instances)
+        pre = None
+        if precomputed_input_lens is not None:
+            pre = np.array([p for inst in precomputed_input_lens for p in inst], dtype=np.uint32)
+        digests = np.zeros((n * D, 32), dtype=np.uint8)
+        cks = np.zeros((n, 4), dtype=np.uint64)
+        gate = lookup = spread = None
+        if want_cells:
+            gate, lookup, spread = outputs if outputs is not None else self.alloc_outputs(n)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.digest_batch_raw(n, blob.ctypes.data if blob.size else 0, False, int(blob.size), offs, lens, pre,
+                              gate_ptr=gate.data_ptr() if gate is not None else 0, lookup_ptr=lookup.data_ptr() if lookup is not None else 0,
+                              spread_ptr=spread.data_ptr() if spread is not None else 0, digests_host_ptr=digests.ctypes.data,
+                              checksums_host_ptr=cks.ctypes.data, stream=stream)
+        torch.cuda.current_stream(self.device).synchronize()
+        return BatchResult(digests, cks, gate, lookup, spread)
+
+    def digest(self, input: bytes, precomputed_input_len: Optional[int] = None) -> Tuple[AssignedHashResult, BatchResult]:
+        """Single-message convenience with the reference's signature (only for n_digests == 1 configurations)."""
+        if len(self.max_variable_byte_sizes) != 1:
+            raise EngineError(H2SHA_EINVAL, "digest() needs a single-digest configuration; use digest_batch")
+        res = self.digest_batch([[input]], [[precomputed_input_len or 0]] if precomputed_input_len is not None else None)
+        return self.handles(0), res
+
+    def launches_last_batch(self) -> int:
+        return int(load_library().h2sha_last_launch_count(self._h))
+
+    def mont_from_u64(self, vals: np.ndarray) -> np.ndarray:
+        """Test hook: device Montgomery conversion of raw u64 values -> [n,4] u64."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        v = torch.from_numpy(vals.astype(np.uint64).view(np.int64)).to(dev)
+        out = torch.empty((v.numel(), 4), dtype=torch.int64, device=dev)
+        _check(load_library().h2sha_debug_mont_from_u64(self._h, v.data_ptr(), out.data_ptr(), v.numel(),
+                                                       torch.cuda.current_stream(self.device).cuda_stream))
+        torch.cuda.current_stream(self.device).synchronize()
+        return out.cpu().numpy().view(np.uint64)

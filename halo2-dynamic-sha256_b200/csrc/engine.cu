@@ -1,0 +1,925 @@
+// engine.cu -- sm_100a kernels and the C-ABI of the SHA-256 witness-generation engine (include/h2sha_b200.h).
+//
+// Kernels (see DESIGN.md for the roofline of each):
+//   k_trace   one thread per message: padding (lib.rs:77-117), precomputed-prefix state (lib.rs:153-160),
+//             then the scalar SHA-256 of every block with register-resident state, writing the 200-word
+//             per-block trace (W[64], a/e working variables) and the digest.
+//   k_expand  persistent CTAs; one job = one sha256_compression (69 348 gate + 3 184 lookup + 8 240
+//             spread-column cells) or one digest prologue/epilogue.  Phase 1 runs the planner's slot
+//             programs (lanes = unit instances), phase 2 expands the templates: raw value -> BN254 Fr
+//             Montgomery form -> one 256-bit store per cell (st.global.v8.b32, sm_100+), checksums folded
+//             from registers.
+// There is no CPU path: every entry point fails with H2SHA_ECUDA when no device is usable.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/h2sha_b200.h"
+#include "h2sha_defs.h"
+#include "planner.h"
+
+using namespace h2sha;
+
+extern "C" const uint32_t H2SHA_CK_M[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+
+namespace {
+
+thread_local std::string g_err;
+int set_err(int code, const std::string& m) { g_err = m; return code; }
+#define CUDA_TRY(x)                                                                                         \
+  do {                                                                                                      \
+    cudaError_t e_ = (x);                                                                                   \
+    if (e_ != cudaSuccess) return set_err(H2SHA_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// device-side plan view
+// ---------------------------------------------------------------------------------------------------
+struct DevDigest {
+  DigestPlace dp;
+  uint32_t blk_prefix;    // blocks of digests < d in one instance
+  uint32_t dtrace_off;    // word offset of this digest's trace inside the instance's digest-trace area
+};
+
+struct DevPlan {
+  // one contiguous blob in global memory, copied to shared memory by every CTA at start
+  const uint8_t* blob;
+  uint32_t blob_bytes;
+  // byte offsets inside the blob (all 16-byte aligned)
+  uint32_t off_tmpl, off_table, off_prog, off_groups, off_tasks, off_types, off_classes, off_raw, off_breaks, off_digests;
+  uint32_t n_breaks, n_digests;
+  // dynamic shared memory layout after the blob
+  uint32_t off_trace, off_slots, off_misc, smem_bytes;
+  // layout
+  uint32_t max_rows, spread_cols, n_gate_cols, gate_col_rows, n_lookup_cols, lookup_col_rows, spread_rows;
+  uint32_t blocks_per_inst, dtrace_words_per_inst;
+  uint64_t gate_inst_cells, lookup_inst_cells, spread_inst_cells;
+};
+
+struct JobArgs {
+  uint64_t n_inst;
+  const uint32_t* btrace;   // [n_inst * blocks_per_inst][TR_BLOCK_WORDS]
+  const uint32_t* dtrace;   // [n_inst][dtrace_words_per_inst]
+  uint32_t* gate;           // Fr as 8 x u32
+  uint32_t* lookup;
+  uint32_t* spread;
+  unsigned long long* cks;  // [n_inst][4] or null
+  unsigned long long* job_counter;
+};
+
+__constant__ uint32_t c_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+__constant__ uint32_t c_H0[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+__constant__ uint32_t c_CKM[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+
+// Field constants, derived on the host from p at engine creation (fr_host.h) and uploaded here.
+struct FrConsts {
+  uint64_t p[4];    // modulus
+  uint64_t r1[4];   // 2^256 mod p  (Montgomery form of 1)
+  uint64_t mu;      // floor(2^317 / p)
+};
+__constant__ FrConsts c_fr;
+
+// ---------------------------------------------------------------------------------------------------
+// Montgomery form of a raw value v < 2^64:  v * 2^256 mod p, by one 64x256 multiply and a Barrett
+// reduction with a 64-bit quotient estimate (q_hat in {q-2, q-1, q}; checked exhaustively on edge
+// cases in tests/test_field.py).  Replaces halo2curves `Fr::from(u64)` (one full Montgomery multiply).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mont_from_u64(uint64_t v, uint64_t r[4]) {
+  const uint64_t R0 = c_fr.r1[0], R1 = c_fr.r1[1], R2 = c_fr.r1[2], R3 = c_fr.r1[3];
+  uint64_t p0, p1, p2, p3, p4;
+  {
+    uint64_t l1 = v * R1, l2 = v * R2, l3 = v * R3;
+    uint64_t h0 = __umul64hi(v, R0), h1 = __umul64hi(v, R1), h2 = __umul64hi(v, R2), h3 = __umul64hi(v, R3);
+    p0 = v * R0;
+    asm("add.cc.u64 %0, %4, %5;\n\t"
+        "addc.cc.u64 %1, %6, %7;\n\t"
+        "addc.cc.u64 %2, %8, %9;\n\t"
+        "addc.u64 %3, %10, 0;"
+        : "=l"(p1), "=l"(p2), "=l"(p3), "=l"(p4)
+        : "l"(l1), "l"(h0), "l"(l2), "l"(h1), "l"(l3), "l"(h2), "l"(h3));
+  }
+  // quotient estimate: q = floor( (P >> 254) * mu / 2^63 )
+  uint64_t ph = (p3 >> 62) | (p4 << 2);
+  uint64_t qh = __umul64hi(ph, c_fr.mu), ql = ph * c_fr.mu;
+  uint64_t q = (qh << 1) | (ql >> 63);
+  // r = P - q * p  (mod 2^256; the true value is < 3p < 2^256)
+  const uint64_t P0 = c_fr.p[0], P1 = c_fr.p[1], P2 = c_fr.p[2], P3 = c_fr.p[3];
+  uint64_t m0 = q * P0, m1, m2, m3;
+  {
+    uint64_t l1 = q * P1, l2 = q * P2, l3 = q * P3;
+    uint64_t h0 = __umul64hi(q, P0), h1 = __umul64hi(q, P1), h2 = __umul64hi(q, P2);
+    asm("add.cc.u64 %0, %3, %4;\n\t"
+        "addc.cc.u64 %1, %5, %6;\n\t"
+        "addc.u64 %2, %7, %8;"
+        : "=l"(m1), "=l"(m2), "=l"(m3)
+        : "l"(l1), "l"(h0), "l"(l2), "l"(h1), "l"(l3), "l"(h2));
+  }
+  uint64_t r0, r1, r2, r3;
+  asm("sub.cc.u64 %0, %4, %8;\n\t"
+      "subc.cc.u64 %1, %5, %9;\n\t"
+      "subc.cc.u64 %2, %6, %10;\n\t"
+      "subc.u64 %3, %7, %11;"
+      : "=l"(r0), "=l"(r1), "=l"(r2), "=l"(r3)
+      : "l"(p0), "l"(p1), "l"(p2), "l"(p3), "l"(m0), "l"(m1), "l"(m2), "l"(m3));
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    uint64_t s0, s1, s2, s3, borrow;
+    asm("sub.cc.u64 %0, %5, %9;\n\t"
+        "subc.cc.u64 %1, %6, %10;\n\t"
+        "subc.cc.u64 %2, %7, %11;\n\t"
+        "subc.cc.u64 %3, %8, %12;\n\t"
+        "subc.u64 %4, 0, 0;"
+        : "=l"(s0), "=l"(s1), "=l"(s2), "=l"(s3), "=l"(borrow)
+        : "l"(r0), "l"(r1), "l"(r2), "l"(r3), "l"(P0), "l"(P1), "l"(P2), "l"(P3));
+    if (borrow == 0) { r0 = s0; r1 = s1; r2 = s2; r3 = s3; }
+  }
+  r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3;
+}
+// p - r (r != 0), 0 for r == 0
+__device__ __forceinline__ void fr_negate(uint64_t r[4]) {
+  if ((r[0] | r[1] | r[2] | r[3]) == 0) return;
+  uint64_t s0, s1, s2, s3;
+  asm("sub.cc.u64 %0, %4, %8;\n\t"
+      "subc.cc.u64 %1, %5, %9;\n\t"
+      "subc.cc.u64 %2, %6, %10;\n\t"
+      "subc.u64 %3, %7, %11;"
+      : "=l"(s0), "=l"(s1), "=l"(s2), "=l"(s3)
+      : "l"(c_fr.p[0]), "l"(c_fr.p[1]), "l"(c_fr.p[2]), "l"(c_fr.p[3]), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]));
+  r[0] = s0; r[1] = s1; r[2] = s2; r[3] = s3;
+}
+
+// one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
+__device__ __forceinline__ void store_cell(uint32_t* p, const uint32_t x[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]),
+               "r"(x[5]), "r"(x[6]), "r"(x[7])
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long cell_ck(const uint32_t x[8], uint64_t pos) {
+  uint32_t h = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) h += x[k] * c_CKM[k];
+  return (unsigned long long)h * (unsigned long long)(uint32_t)(2u * (uint32_t)pos + 1u);
+}
+
+// bit i -> bit 2i of the low 32 bits
+__device__ __forceinline__ uint64_t spread32(uint64_t x) {
+  x &= 0xffffffffULL;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFULL;
+  x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+  x = (x | (x << 2)) & 0x3333333333333333ULL;
+  x = (x | (x << 1)) & 0x5555555555555555ULL;
+  return x;
+}
+// even-position bits of a 32-bit value, packed into 16 bits
+__device__ __forceinline__ uint32_t even16(uint32_t x) {
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x | (x >> 4)) & 0x00FF00FFu;
+  x = (x | (x >> 8)) & 0x0000FFFFu;
+  return x;
+}
+__device__ __forceinline__ uint64_t extract(uint64_t s, uint32_t sh, uint32_t w) {
+  uint64_t v = s >> sh;
+  return (w >= 64) ? v : (v & ((1ULL << w) - 1ULL));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_trace
+// ---------------------------------------------------------------------------------------------------
+struct TraceArgs {
+  uint64_t n_msgs;
+  uint32_t n_digests;
+  const uint8_t* msgs;
+  const uint64_t* offsets;
+  const uint32_t* lens;
+  const uint32_t* pre_lens;   // may be null
+  uint32_t* btrace;
+  uint32_t* dtrace;
+  uint8_t* digests;           // may be null
+  const DevDigest* digests_plan;
+  uint32_t blocks_per_inst, dtrace_words_per_inst;
+};
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+// byte `pos` of the padded message (lib.rs:98-117): message | 0x80 | zeros | 64-bit BE bit length | zeros up to max
+__device__ __forceinline__ uint32_t padded_byte(const uint8_t* msg, uint32_t len, uint32_t padded_size, uint32_t pos) {
+  if (pos < len) return msg[pos];
+  if (pos == len) return 0x80u;
+  if (pos >= padded_size - 8 && pos < padded_size) {
+    uint64_t bits = 8ull * len;
+    return (uint32_t)(bits >> (8 * (padded_size - 1 - pos))) & 0xffu;
+  }
+  return 0u;
+}
+
+__global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
+  uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= A.n_msgs) return;
+  const uint32_t d = (uint32_t)(m % A.n_digests);
+  const uint64_t inst = m / A.n_digests;
+  const DevDigest dd = A.digests_plan[d];
+  const uint32_t R = dd.dp.n_blocks;
+  const uint8_t* msg = A.msgs + A.offsets[m];
+  const uint32_t len = A.lens[m];
+  const uint32_t pre = A.pre_lens ? A.pre_lens[m] : 0u;
+  const uint32_t num_round = (len + 9 + 63) / 64;          // lib.rs:80-84
+  const uint32_t padded_size = 64 * num_round;             // lib.rs:85
+  const uint32_t pre_round = pre / 64;                     // lib.rs:93
+  uint32_t st[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) st[i] = c_H0[i];
+  uint32_t* dt = A.dtrace + inst * A.dtrace_words_per_inst + dd.dtrace_off;
+  uint32_t* bt = A.btrace + (inst * A.blocks_per_inst + dd.blk_prefix) * (uint64_t)TR_BLOCK_WORDS;
+  const uint32_t words_base = TD_STATES + 8 * (R + 1);
+  uint32_t hfin[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) hfin[i] = 0;
+  // blocks [0, pre_round): un-constrained prefix (sha2::compress256, lib.rs:153-160); blocks [pre_round, pre_round+R): traced
+  for (uint32_t blk = 0; blk < pre_round + R; blk++) {
+    const bool traced = blk >= pre_round;
+    const uint32_t j = blk - pre_round;
+    uint32_t* tw = bt + (uint64_t)j * TR_BLOCK_WORDS;
+    if (traced) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) dt[TD_STATES + 8 * j + i] = st[i];
+    }
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      uint32_t pos = 64 * blk + 4 * i;
+      uint32_t x = (padded_byte(msg, len, padded_size, pos) << 24) | (padded_byte(msg, len, padded_size, pos + 1) << 16) |
+                   (padded_byte(msg, len, padded_size, pos + 2) << 8) | padded_byte(msg, len, padded_size, pos + 3);
+      w[i] = x;
+      if (traced) { tw[TR_W + i] = x; dt[words_base + 16 * j + i] = x; }
+    }
+    uint32_t a = st[0], b = st[1], c = st[2], dd_ = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    if (traced) {
+      tw[TR_A + 3] = a; tw[TR_A + 2] = b; tw[TR_A + 1] = c; tw[TR_A + 0] = dd_;
+      tw[TR_E + 3] = e; tw[TR_E + 2] = f; tw[TR_E + 1] = g; tw[TR_E + 0] = h;
+    }
+    for (int t0 = 0; t0 < 64; t0 += 16) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int t = t0 + i;
+        uint32_t wt;
+        if (t0 == 0) {
+          wt = w[i];
+        } else {
+          uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+          uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+          uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+          wt = w[i] + s0 + w[(i + 9) & 15] + s1;
+          w[i] = wt;
+          if (traced) tw[TR_W + t] = wt;
+        }
+        uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + c_K[t] + wt;
+        uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = dd_ + t1; dd_ = c; c = b; b = a; a = t1 + t2;
+        if (traced) { tw[TR_A + 4 + t] = a; tw[TR_E + 4 + t] = e; }
+      }
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += dd_; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+    if (blk + 1 == num_round) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) hfin[i] = st[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) dt[TD_STATES + 8 * R + i] = st[i];
+  dt[TD_LEN] = len; dt[TD_NUM_ROUND] = num_round; dt[TD_PRE_ROUND] = pre_round; dt[TD_TARGET] = num_round - pre_round;
+#pragma unroll
+  for (int i = 0; i < 8; i++) dt[TD_H + i] = hfin[i];
+  if (A.digests) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t x = hfin[i];
+      A.digests[m * 32 + 4 * i + 0] = (uint8_t)(x >> 24); A.digests[m * 32 + 4 * i + 1] = (uint8_t)(x >> 16);
+      A.digests[m * 32 + 4 * i + 2] = (uint8_t)(x >> 8);  A.digests[m * 32 + 4 * i + 3] = (uint8_t)x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_expand
+// ---------------------------------------------------------------------------------------------------
+struct Misc {
+  unsigned long long ck[3];
+  uint32_t next_item;
+  uint32_t job_lo, job_hi;
+};
+
+__device__ __forceinline__ uint64_t vm_operand(uint32_t o, const uint64_t* slots, const uint64_t* raw) {
+  if (o & 1u) return raw[o >> 1];
+  return extract(slots[(o >> 1) & 0xfffu], (o >> 13) & 63u, (o >> 19) & 127u);
+}
+
+// phase 1: run the slot program of group `g` for unit instance `u` (one lane)
+__device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitType& ut, uint32_t u, const VmIns* prog, const uint64_t* raw,
+                                                 const uint32_t* trace, uint64_t* slots) {
+  for (uint32_t k = 0; k < ut.n_in; k++) {
+    int32_t base = g.in[k].base;
+    slots[k] = (base < 0) ? (uint64_t)u : (uint64_t)trace[base + g.in[k].stride * (int32_t)u];
+  }
+  const VmIns* ins = prog + ut.prog_off;
+  for (uint32_t pc = 0; pc < ut.prog_len; pc++) {
+    const VmIns I = ins[pc];
+    const uint32_t op = I.op_dst & 0xffu, dst = (I.op_dst >> 8) & 0xffu;
+    uint64_t a = vm_operand(I.a, slots, raw);
+    uint64_t r;
+    switch (op) {
+      case OP_ADD: r = a + vm_operand(I.b, slots, raw); break;
+      case OP_SUB: r = a - vm_operand(I.b, slots, raw); break;
+      case OP_MULADD: r = a * vm_operand(I.b, slots, raw) + vm_operand(I.c, slots, raw); break;
+      case OP_SPREAD: r = spread32(a); break;
+      case OP_COMPRESS2: {
+        uint32_t x = (uint32_t)a, y = (uint32_t)vm_operand(I.b, slots, raw);
+        r = (uint64_t)even16(x) | ((uint64_t)even16(y) << 16) | ((uint64_t)even16(x >> 1) << 32) | ((uint64_t)even16(y >> 1) << 48);
+        break;
+      }
+      case OP_EQ: r = (a == vm_operand(I.b, slots, raw)) ? 1 : 0; break;
+      case OP_GT: r = (a > vm_operand(I.b, slots, raw)) ? 1 : 0; break;
+      case OP_SEL: r = a ? vm_operand(I.b, slots, raw) : vm_operand(I.c, slots, raw); break;
+      default: r = a; break;  // OP_MOV
+    }
+    slots[dst] = r;
+  }
+}
+
+// Fr value of one template entry
+__device__ __forceinline__ void eval_entry(const TmplEntry e, const uint64_t* slots, const uint32_t* table, uint32_t x[8]) {
+  const uint32_t kind = H2SHA_TE_KIND(e);
+  uint64_t s = slots[H2SHA_TE_SLOT(e)];
+  if (kind == KIND_TABLE) {
+    uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
+    const uint4* t = reinterpret_cast<const uint4*>(table + 8 * idx);
+    uint4 lo = t[0], hi = t[1];
+    x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+    return;
+  }
+  bool neg = H2SHA_TE_NEG(e);
+  uint64_t v;
+  if (kind == KIND_SIGNED) {
+    int64_t sv = (int64_t)s;
+    neg = sv < 0;
+    v = neg ? (uint64_t)(-sv) : (uint64_t)sv;
+  } else {
+    v = extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e)) << H2SHA_TE_SHL(e);
+  }
+  uint64_t r[4];
+  mont_from_u64(v, r);
+  if (neg) fr_negate(r);
+  x[0] = (uint32_t)r[0]; x[1] = (uint32_t)(r[0] >> 32); x[2] = (uint32_t)r[1]; x[3] = (uint32_t)(r[1] >> 32);
+  x[4] = (uint32_t)r[2]; x[5] = (uint32_t)(r[2] >> 32); x[6] = (uint32_t)r[3]; x[7] = (uint32_t)(r[3] >> 32);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs A) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  // ---- static plan -> shared memory (once per persistent CTA) ----
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.blob);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = tid; i < P.blob_bytes / 16; i += NT) dst[i] = src[i];
+  }
+  const TmplEntry* s_tmpl = reinterpret_cast<const TmplEntry*>(smem + P.off_tmpl);
+  const uint32_t* s_table = reinterpret_cast<const uint32_t*>(smem + P.off_table);
+  const VmIns* s_prog = reinterpret_cast<const VmIns*>(smem + P.off_prog);
+  const UnitGroup* s_groups = reinterpret_cast<const UnitGroup*>(smem + P.off_groups);
+  const WarpTask* s_tasks = reinterpret_cast<const WarpTask*>(smem + P.off_tasks);
+  const UnitType* s_types = reinterpret_cast<const UnitType*>(smem + P.off_types);
+  const JobClass* s_classes = reinterpret_cast<const JobClass*>(smem + P.off_classes);
+  const uint64_t* s_raw = reinterpret_cast<const uint64_t*>(smem + P.off_raw);
+  const uint32_t* s_breaks = reinterpret_cast<const uint32_t*>(smem + P.off_breaks);
+  const DevDigest* s_digests = reinterpret_cast<const DevDigest*>(smem + P.off_digests);
+  uint32_t* s_trace = reinterpret_cast<uint32_t*>(smem + P.off_trace);
+  uint64_t* s_slots = reinterpret_cast<uint64_t*>(smem + P.off_slots);
+  Misc* s_misc = reinterpret_cast<Misc*>(smem + P.off_misc);
+  for (int i = tid; i < 64; i += NT) s_trace[TR_K + i] = c_K[i];
+
+  const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst;
+  const uint64_t n_jobs = n_block_jobs + A.n_inst * P.n_digests;
+
+  for (;;) {
+    __syncthreads();  // previous job fully done (slots / trace / misc reusable); blob visible on the first pass
+    if (tid == 0) {
+      unsigned long long j = atomicAdd(A.job_counter, 1ULL);
+      s_misc->job_lo = (uint32_t)j; s_misc->job_hi = (uint32_t)(j >> 32);
+      s_misc->next_item = 0; s_misc->ck[0] = 0; s_misc->ck[1] = 0; s_misc->ck[2] = 0;
+    }
+    __syncthreads();
+    const uint64_t job = ((uint64_t)s_misc->job_hi << 32) | s_misc->job_lo;
+    if (job >= n_jobs) break;
+    // ---- decode job ----
+    uint64_t inst; uint32_t cls, gate0, lk0, limb0; const uint32_t* tr_src; uint32_t tr_words;
+    if (job < n_block_jobs) {
+      inst = job / P.blocks_per_inst;
+      uint32_t r = (uint32_t)(job - inst * P.blocks_per_inst);
+      uint32_t d = 0;
+      while (d + 1 < P.n_digests && r >= s_digests[d + 1].blk_prefix) d++;
+      const DevDigest& dd = s_digests[d];
+      uint32_t jb = r - dd.blk_prefix;
+      cls = 0;
+      gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
+      lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
+      limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
+      tr_src = A.btrace + job * (uint64_t)TR_BLOCK_WORDS;
+      tr_words = TR_BLOCK_WORDS;
+    } else {
+      uint64_t k = job - n_block_jobs;
+      inst = k / P.n_digests;
+      uint32_t d = (uint32_t)(k - inst * P.n_digests);
+      const DevDigest& dd = s_digests[d];
+      cls = dd.dp.job_class;
+      gate0 = 0; lk0 = 0; limb0 = 0;
+      tr_src = A.dtrace + inst * P.dtrace_words_per_inst + dd.dtrace_off;
+      tr_words = dd.dp.trace_words;
+    }
+    const JobClass jc = s_classes[cls];
+    for (uint32_t i = tid; i < tr_words; i += NT) s_trace[i] = tr_src[i];
+    __syncthreads();
+    // ---- phase 1: slot programs, lanes = unit instances ----
+    for (uint32_t t = warp; t < jc.n_tasks; t += NW) {
+      const WarpTask wt = s_tasks[jc.task_off + t];
+      const UnitGroup& g = s_groups[jc.group_off + wt.group];
+      const UnitType& ut = s_types[g.type];
+      uint32_t u = wt.first + lane;
+      if (u < g.count) run_unit_program(g, ut, u, s_prog, s_raw, s_trace, s_slots + g.slot_base + u * (ut.n_slots | 1u));
+    }
+    __syncthreads();
+    // ---- phase 2: template expansion, one warp per unit instance (dynamic) ----
+    unsigned long long ck_g = 0, ck_l = 0, ck_s = 0;
+    uint32_t* gate_out = A.gate ? A.gate + inst * P.gate_inst_cells * 8 : nullptr;
+    uint32_t* lk_out = A.lookup ? A.lookup + inst * P.lookup_inst_cells * 8 : nullptr;
+    uint32_t* sp_out = A.spread ? A.spread + inst * P.spread_inst_cells * 8 : nullptr;
+    // items are enumerated group-major; total = sum of counts
+    uint32_t n_items = 0;
+    for (uint32_t gi = 0; gi < jc.n_groups; gi++) n_items += s_groups[jc.group_off + gi].count;
+    for (;;) {
+      uint32_t item = 0;
+      if (lane == 0) item = atomicAdd(&s_misc->next_item, 1u);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= n_items) break;
+      // heavy groups (ROUND, SCHED) are not first in stream order; walk the groups from the largest unit downwards
+      uint32_t gi = 0, u = item;
+      {
+        // group order by decreasing template length is precomputed by the planner in the task list; here: linear scan
+        // over groups in task order (tasks are sorted longest-program-first and cover every group)
+        uint32_t rem = item; bool found = false;
+        for (uint32_t t = 0; t < jc.n_tasks && !found; t++) {
+          const WarpTask wt = s_tasks[jc.task_off + t];
+          uint32_t cnt = min(32u, s_groups[jc.group_off + wt.group].count - wt.first);
+          if (rem < cnt) { gi = wt.group; u = wt.first + rem; found = true; } else rem -= cnt;
+        }
+      }
+      const UnitGroup& g = s_groups[jc.group_off + gi];
+      const UnitType& ut = s_types[g.type];
+      const uint64_t* slots = s_slots + g.slot_base + u * (ut.n_slots | 1u);
+      // gate cells
+      {
+        const uint32_t g_lo = gate0 + g.gate_base + u * g.gate_stride;   // instance-relative gate-stream index of the unit's first cell
+        uint32_t c0 = 0;
+        while (c0 + 1 < P.n_breaks && s_breaks[c0 + 1] <= g_lo) c0++;
+        const uint32_t next_brk = (c0 + 1 < P.n_breaks) ? s_breaks[c0 + 1] : 0xffffffffu;
+        const uint32_t brk0 = s_breaks[c0];
+        const TmplEntry* tm = s_tmpl + ut.gate_off;
+        for (uint32_t i = lane; i < ut.gate_len; i += 32) {
+          const TmplEntry e = tm[i];
+          uint32_t x[8];
+          eval_entry(e, slots, s_table, x);
+          uint32_t gidx = g_lo + H2SHA_TE_DST(e);
+          uint64_t pos = (gidx >= next_brk) ? (uint64_t)(c0 + 1) * P.gate_col_rows + (gidx - next_brk) : (uint64_t)c0 * P.gate_col_rows + (gidx - brk0);
+          if (gate_out) store_cell(gate_out + pos * 8, x);
+          ck_g += cell_ck(x, pos);
+        }
+      }
+      // lookup-column cells (range.finalize copies cells_to_lookup in push order, wrapping at max_rows)
+      if (ut.lk_len) {
+        const uint32_t l_lo = lk0 + g.lk_base + u * g.lk_stride;
+        const TmplEntry* tm = s_tmpl + ut.lk_off;
+        for (uint32_t i = lane; i < ut.lk_len; i += 32) {
+          const TmplEntry e = tm[i];
+          uint32_t x[8];
+          eval_entry(e, slots, s_table, x);
+          uint32_t li = l_lo + H2SHA_TE_DST(e);
+          uint32_t col = li / P.max_rows, row = li - col * P.max_rows;
+          uint64_t pos = (uint64_t)col * P.lookup_col_rows + row;
+          if (lk_out) store_cell(lk_out + pos * 8, x);
+          ck_l += cell_ck(x, pos);
+        }
+      }
+      // spread-table columns: limb n -> column n % cols, row n / cols (spread.rs:202,228-231); dense then spread
+      if (ut.limb_len) {
+        const uint32_t m_lo = limb0 + g.limb_base + u * g.limb_stride;
+        const TmplEntry* tm = s_tmpl + ut.limb_off;
+        for (uint32_t i = lane; i < ut.limb_len; i += 32) {
+          const TmplEntry e = tm[i];
+          uint32_t x[8];
+          eval_entry(e, slots, s_table, x);
+          uint32_t n = m_lo + (H2SHA_TE_DST(e) >> 1), which = H2SHA_TE_DST(e) & 1u;
+          uint32_t row = n / P.spread_cols, col = n - row * P.spread_cols;
+          uint64_t pos = (uint64_t)(which * P.spread_cols + col) * P.spread_rows + row;
+          if (sp_out) store_cell(sp_out + pos * 8, x);
+          ck_s += cell_ck(x, pos);
+        }
+      }
+    }
+    // ---- checksums: warp reduce, CTA reduce in shared memory, one global atomic per kind ----
+    if (A.cks) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ck_g += __shfl_xor_sync(0xffffffffu, ck_g, o);
+        ck_l += __shfl_xor_sync(0xffffffffu, ck_l, o);
+        ck_s += __shfl_xor_sync(0xffffffffu, ck_s, o);
+      }
+      if (lane == 0) { atomicAdd(&s_misc->ck[0], ck_g); atomicAdd(&s_misc->ck[1], ck_l); atomicAdd(&s_misc->ck[2], ck_s); }
+      __syncthreads();
+      if (tid < 3) {
+        unsigned long long v = s_misc->ck[tid];
+        atomicAdd(&A.cks[inst * 4 + tid], v);
+        atomicAdd(&A.cks[inst * 4 + 3], v);
+      }
+    }
+  }
+}
+
+__global__ void k_mont_debug(const uint64_t* vals, uint64_t* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t r[4];
+  mont_from_u64(vals[i], r);
+  out[4 * i] = r[0]; out[4 * i + 1] = r[1]; out[4 * i + 2] = r[2]; out[4 * i + 3] = r[3];
+}
+
+__global__ void k_zero_ranges(uint4* buf, uint64_t inst_cells, uint64_t n_inst, const uint32_t* ranges /*pos,count pairs*/, uint32_t n_ranges) {
+  // grid.y = instance, grid.x strides over the cells of all ranges
+  uint64_t inst = blockIdx.y;
+  if (inst >= n_inst) return;
+  for (uint32_t r = 0; r < n_ranges; r++) {
+    uint64_t pos = ranges[2 * r], cnt = ranges[2 * r + 1];
+    uint4* p = buf + (inst * inst_cells + pos) * 2;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt * 2; i += (uint64_t)gridDim.x * blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+constexpr int EXPAND_THREADS = 256;
+uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// host engine
+// ---------------------------------------------------------------------------------------------------
+struct h2sha_engine {
+  Plan plan;
+  int device = 0;
+  int n_sms = 0;
+  DevPlan dplan{};
+  uint8_t* d_blob = nullptr;
+  DevDigest* d_digests = nullptr;
+  uint32_t* d_zero_ranges[3] = {nullptr, nullptr, nullptr};
+  uint32_t n_zero_ranges[3] = {0, 0, 0};
+  // workspace (grown on demand)
+  uint64_t ws_msgs = 0, ws_bytes = 0;
+  uint8_t* d_msgs = nullptr;
+  uint64_t* d_offsets = nullptr;
+  uint32_t* d_lens = nullptr;
+  uint32_t* d_pre = nullptr;
+  uint32_t* d_btrace = nullptr;
+  uint32_t* d_dtrace = nullptr;
+  unsigned long long* d_counter = nullptr;
+  uint8_t* d_digests_out = nullptr;
+  unsigned long long* d_cks = nullptr;
+  uint32_t blocks_per_inst = 0, dtrace_words_per_inst = 0;
+  int last_launches = 0;
+  int expand_ctas = 0;
+};
+
+namespace {
+
+int ensure_workspace(h2sha_engine* e, uint64_t n_inst, uint64_t msg_bytes) {
+  uint64_t n_msgs = n_inst * e->plan.digests.size();
+  if (n_msgs > e->ws_msgs) {
+    cudaFree(e->d_offsets); cudaFree(e->d_lens); cudaFree(e->d_pre); cudaFree(e->d_btrace); cudaFree(e->d_dtrace);
+    cudaFree(e->d_digests_out); cudaFree(e->d_cks);
+    e->ws_msgs = 0;
+    CUDA_TRY(cudaMalloc(&e->d_offsets, n_msgs * 8));
+    CUDA_TRY(cudaMalloc(&e->d_lens, n_msgs * 4));
+    CUDA_TRY(cudaMalloc(&e->d_pre, n_msgs * 4));
+    CUDA_TRY(cudaMalloc(&e->d_btrace, n_inst * e->blocks_per_inst * (uint64_t)TR_BLOCK_WORDS * 4));
+    CUDA_TRY(cudaMalloc(&e->d_dtrace, n_inst * (uint64_t)e->dtrace_words_per_inst * 4));
+    CUDA_TRY(cudaMalloc(&e->d_digests_out, n_msgs * 32));
+    CUDA_TRY(cudaMalloc(&e->d_cks, n_inst * 32));
+    e->ws_msgs = n_msgs;
+  }
+  if (msg_bytes + 16 > e->ws_bytes) {
+    cudaFree(e->d_msgs);
+    e->ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&e->d_msgs, msg_bytes + 16));
+    e->ws_bytes = msg_bytes + 16;
+  }
+  return H2SHA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* h2sha_last_error(void) { return g_err.c_str(); }
+
+int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
+  if (!cfg || !out) return set_err(H2SHA_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->n_digests == 0 || !cfg->max_variable_byte_sizes) return set_err(H2SHA_EINVAL, "max_variable_byte_sizes is empty");
+  // device == -1: plan-only engine (layout / shape / handle queries on the host); it can never generate a witness
+  const bool plan_only = cfg->device == -1;
+  cudaDeviceProp prop{};
+  if (!plan_only) {
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev == 0)
+      return set_err(H2SHA_ECUDA, std::string("no usable CUDA device (this engine has no CPU path): ") + cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= n_dev) return set_err(H2SHA_EINVAL, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return set_err(H2SHA_ECUDA, "this engine is built for sm_100a (B200) only");
+  }
+
+  Config pc;
+  pc.max_variable_byte_sizes.assign(cfg->max_variable_byte_sizes, cfg->max_variable_byte_sizes + cfg->n_digests);
+  if (cfg->max_rows) pc.max_rows = cfg->max_rows;
+  if (cfg->lookup_bits) pc.lookup_bits = cfg->lookup_bits;
+  if (cfg->num_bits_lookup) pc.limb_bits = cfg->num_bits_lookup;
+  if (cfg->num_advice_columns) pc.spread_cols = cfg->num_advice_columns;
+  pc.is_input_range_check = cfg->is_input_range_check ? 1 : 0;
+  pc.record_shape = cfg->build_shape ? 1 : 0;
+  h2sha_engine* e = new h2sha_engine();
+  std::string err;
+  if (!build_plan(pc, &e->plan, &err)) { delete e; return set_err(H2SHA_EINVAL, err); }
+  Plan& P = e->plan;
+  if (cfg->gate_col_rows) { if (cfg->gate_col_rows < P.gate_col_rows) { delete e; return set_err(H2SHA_EINVAL, "gate_col_rows too small"); } P.gate_col_rows = cfg->gate_col_rows; }
+  if (cfg->lookup_col_rows) { if (cfg->lookup_col_rows < P.lookup_col_rows) { delete e; return set_err(H2SHA_EINVAL, "lookup_col_rows too small"); } P.lookup_col_rows = cfg->lookup_col_rows; }
+  if (cfg->spread_rows) { if (cfg->spread_rows < P.spread_rows) { delete e; return set_err(H2SHA_EINVAL, "spread_rows too small"); } P.spread_rows = cfg->spread_rows; }
+  if ((P.gate_col_rows | P.lookup_col_rows | P.spread_rows) & 1u) { delete e; return set_err(H2SHA_EINVAL, "column row strides must be even"); }
+  e->device = cfg->device;
+  e->n_sms = prop.multiProcessorCount;
+  {
+    uint32_t bp0 = 0, dw0 = 0;
+    for (auto& dgp : P.digests) { bp0 += dgp.n_blocks; dw0 += dgp.trace_words; }
+    e->blocks_per_inst = bp0; e->dtrace_words_per_inst = dw0;
+  }
+  compute_zero_ranges(&P);  // against the final (possibly widened) strides
+  if (plan_only) { *out = e; return H2SHA_OK; }
+
+  // ---- field constants ----
+  FrConsts fc;
+  memcpy(fc.p, fr::P, 32);
+  U256 r1 = fr::mont_r();
+  memcpy(fc.r1, r1.l, 32);
+  fc.mu = fr::floor_pow2_div_p(317);
+  CUDA_TRY(cudaMemcpyToSymbol(c_fr, &fc, sizeof fc));
+
+  // ---- per-digest device info ----
+  std::vector<DevDigest> dds(P.digests.size());
+  uint32_t bp = 0, dw = 0;
+  for (size_t d = 0; d < P.digests.size(); d++) {
+    dds[d].dp = P.digests[d];
+    dds[d].blk_prefix = bp; dds[d].dtrace_off = dw;
+    bp += P.digests[d].n_blocks; dw += P.digests[d].trace_words;
+  }
+  e->blocks_per_inst = bp; e->dtrace_words_per_inst = dw;
+
+  // ---- blob ----
+  DevPlan& D = e->dplan;
+  std::vector<uint8_t> blob;
+  auto put = [&](const void* p, size_t bytes) {
+    uint32_t off = (uint32_t)blob.size();
+    blob.resize(align_up((uint32_t)(off + bytes), 16), 0);
+    if (bytes) memcpy(blob.data() + off, p, bytes);
+    return off;
+  };
+  D.off_tmpl = put(P.tmpl.data(), P.tmpl.size() * sizeof(TmplEntry));
+  D.off_table = put(P.mont_table.data(), P.mont_table.size() * 32);
+  D.off_prog = put(P.prog.data(), P.prog.size() * sizeof(VmIns));
+  D.off_groups = put(P.groups.data(), P.groups.size() * sizeof(UnitGroup));
+  D.off_tasks = put(P.tasks.data(), P.tasks.size() * sizeof(WarpTask));
+  D.off_types = put(P.types.data(), P.types.size() * sizeof(UnitType));
+  D.off_classes = put(P.classes.data(), P.classes.size() * sizeof(JobClass));
+  D.off_raw = put(P.raw_consts.data(), P.raw_consts.size() * 8);
+  D.off_breaks = put(P.breaks.data(), P.breaks.size() * 4);
+  D.off_digests = put(dds.data(), dds.size() * sizeof(DevDigest));
+  D.blob_bytes = (uint32_t)blob.size();
+  D.n_breaks = (uint32_t)P.breaks.size();
+  D.n_digests = (uint32_t)P.digests.size();
+  D.off_trace = D.blob_bytes;
+  D.off_slots = align_up(D.off_trace + 4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
+  D.off_misc = align_up(D.off_slots + 8 * P.max_slots, 16);
+  D.smem_bytes = D.off_misc + (uint32_t)sizeof(Misc);
+  if (D.smem_bytes > 227 * 1024) { delete e; return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory"); }
+  D.max_rows = pc.max_rows; D.spread_cols = pc.spread_cols;
+  D.n_gate_cols = P.n_gate_cols; D.gate_col_rows = P.gate_col_rows;
+  D.n_lookup_cols = P.n_lookup_cols; D.lookup_col_rows = P.lookup_col_rows; D.spread_rows = P.spread_rows;
+  D.blocks_per_inst = bp; D.dtrace_words_per_inst = dw;
+  D.gate_inst_cells = (uint64_t)P.n_gate_cols * P.gate_col_rows;
+  D.lookup_inst_cells = (uint64_t)P.n_lookup_cols * P.lookup_col_rows;
+  D.spread_inst_cells = (uint64_t)2 * pc.spread_cols * P.spread_rows;
+  CUDA_TRY(cudaMalloc(&e->d_blob, blob.size()));
+  CUDA_TRY(cudaMemcpy(e->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  D.blob = e->d_blob;
+  CUDA_TRY(cudaMalloc(&e->d_digests, dds.size() * sizeof(DevDigest)));
+  CUDA_TRY(cudaMemcpy(e->d_digests, dds.data(), dds.size() * sizeof(DevDigest), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&e->d_counter, 8));
+  for (int b = 0; b < 3; b++) {
+    std::vector<uint32_t> rr;
+    for (auto& z : P.zero_ranges) if ((int)z.buf == b) { rr.push_back(z.pos); rr.push_back(z.count); }
+    e->n_zero_ranges[b] = (uint32_t)rr.size() / 2;
+    if (!rr.empty()) {
+      CUDA_TRY(cudaMalloc(&e->d_zero_ranges[b], rr.size() * 4));
+      CUDA_TRY(cudaMemcpy(e->d_zero_ranges[b], rr.data(), rr.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  CUDA_TRY(cudaFuncSetAttribute(k_expand<EXPAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand<EXPAND_THREADS>, EXPAND_THREADS, D.smem_bytes));
+  if (occ < 1) { delete e; return set_err(H2SHA_ECUDA, "expand kernel does not fit on an SM"); }
+  e->expand_ctas = occ * e->n_sms;
+  *out = e;
+  return H2SHA_OK;
+}
+
+void h2sha_destroy(h2sha_engine_t* e) {
+  if (!e) return;
+  if (e->device < 0) { delete e; return; }
+  cudaSetDevice(e->device);
+  cudaFree(e->d_blob); cudaFree(e->d_digests); cudaFree(e->d_counter);
+  for (int b = 0; b < 3; b++) cudaFree(e->d_zero_ranges[b]);
+  cudaFree(e->d_msgs); cudaFree(e->d_offsets); cudaFree(e->d_lens); cudaFree(e->d_pre); cudaFree(e->d_btrace); cudaFree(e->d_dtrace);
+  cudaFree(e->d_digests_out); cudaFree(e->d_cks);
+  delete e;
+}
+
+int h2sha_get_layout(const h2sha_engine_t* e, h2sha_layout_t* L) {
+  if (!e || !L) return set_err(H2SHA_EINVAL, "null argument");
+  const Plan& P = e->plan;
+  memset(L, 0, sizeof *L);
+  L->n_digests = (uint32_t)P.digests.size();
+  L->n_gate_cells = P.n_gate; L->n_lookup_cells = P.n_lookup; L->n_spread_limbs = P.n_limb;
+  L->n_gate_cols = P.n_gate_cols; L->gate_col_rows = P.gate_col_rows;
+  L->n_lookup_cols = P.n_lookup_cols; L->lookup_col_rows = P.lookup_col_rows;
+  L->n_spread_cols = 2 * P.cfg.spread_cols; L->spread_rows = P.spread_rows;
+  L->n_blocks = e->blocks_per_inst;
+  L->n_fixed = (uint32_t)P.fixed_consts.size(); L->n_copies = (uint32_t)P.copies.size();
+  uint32_t on = 0; for (uint8_t s : P.selectors) on += s;
+  L->n_selectors_on = on;
+  L->cells_per_instance = P.cells_per_instance();
+  L->gate_bytes = (uint64_t)P.n_gate_cols * P.gate_col_rows * 32;
+  L->lookup_bytes = (uint64_t)P.n_lookup_cols * P.lookup_col_rows * 32;
+  L->spread_bytes = (uint64_t)2 * P.cfg.spread_cols * P.spread_rows * 32;
+  return H2SHA_OK;
+}
+
+int h2sha_get_breaks(const h2sha_engine_t* e, uint32_t* breaks) {
+  if (!e || !breaks) return set_err(H2SHA_EINVAL, "null argument");
+  memcpy(breaks, e->plan.breaks.data(), e->plan.breaks.size() * 4);
+  return H2SHA_OK;
+}
+
+int h2sha_get_handles(const h2sha_engine_t* e, uint32_t d, uint32_t* input_len_idx, uint32_t* input_bytes_idx, uint32_t* output_bytes_idx) {
+  if (!e || d >= e->plan.handles.size()) return set_err(H2SHA_EINVAL, "bad digest index");
+  const DigestHandles& h = e->plan.handles[d];
+  if (input_len_idx) *input_len_idx = h.input_len_idx;
+  if (input_bytes_idx) memcpy(input_bytes_idx, h.input_bytes_idx.data(), h.input_bytes_idx.size() * 4);
+  if (output_bytes_idx) memcpy(output_bytes_idx, h.output_bytes_idx, 32 * 4);
+  return H2SHA_OK;
+}
+
+int h2sha_get_shape(const h2sha_engine_t* e, uint8_t* selectors, uint32_t* copies, uint64_t* fixed, uint32_t* lookup_src,
+                    uint32_t* limb_dense_src, uint32_t* limb_spread_src) {
+  if (!e) return set_err(H2SHA_EINVAL, "null argument");
+  const Plan& P = e->plan;
+  if (!P.cfg.record_shape) return set_err(H2SHA_EINVAL, "engine was created without build_shape");
+  if (selectors) memcpy(selectors, P.selectors.data(), P.selectors.size());
+  if (copies) memcpy(copies, P.copies.data(), P.copies.size() * sizeof(CopyPair));
+  if (fixed) memcpy(fixed, P.fixed_consts.data(), P.fixed_consts.size() * 32);
+  if (lookup_src) memcpy(lookup_src, P.lookup_cells.data(), P.lookup_cells.size() * 4);
+  if (limb_dense_src) memcpy(limb_dense_src, P.limb_gate_dense.data(), P.limb_gate_dense.size() * 4);
+  if (limb_spread_src) memcpy(limb_spread_src, P.limb_gate_spread.data(), P.limb_gate_spread.size() * 4);
+  return H2SHA_OK;
+}
+
+int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
+  if (!e || !b) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine (device = -1): witness generation needs a CUDA device; there is no CPU path");
+  if (b->n_instances == 0) return H2SHA_OK;
+  if (!b->msgs && b->msgs_bytes) return set_err(H2SHA_EINVAL, "msgs is null");
+  if (!b->offsets || !b->lens) return set_err(H2SHA_EINVAL, "offsets / lens are null");
+  const Plan& P = e->plan;
+  const uint32_t D = (uint32_t)P.digests.size();
+  const uint64_t n_msgs = b->n_instances * D;
+  if (n_msgs * (uint64_t)1 > 0xffffffffull) return set_err(H2SHA_EINVAL, "batch too large");
+  // the reference's panics (lib.rs:89-90) become error returns
+  for (uint64_t m = 0; m < n_msgs; m++) {
+    const uint32_t maxb = P.digests[m % D].max_bytes;
+    const uint64_t len = b->lens[m], pre = b->precomputed_lens ? b->precomputed_lens[m] : 0;
+    if (pre % 64 != 0) return set_err(H2SHA_EPANIC, "precomputed_input_len is not a multiple of 64 (lib.rs:89), message " + std::to_string(m));
+    const uint64_t padded = (len + 9 + 63) / 64 * 64;
+    if (padded < pre || padded - pre > maxb)
+      return set_err(H2SHA_EPANIC, "padded input does not fit max_variable_byte_size (lib.rs:90), message " + std::to_string(m));
+    if (b->offsets[m] + len > b->msgs_bytes) return set_err(H2SHA_EINVAL, "message " + std::to_string(m) + " exceeds msgs_bytes");
+  }
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)b->stream;
+  int rc = ensure_workspace(e, b->n_instances, b->msgs_on_device ? 0 : b->msgs_bytes);
+  if (rc) return rc;
+  const uint8_t* d_msgs = b->msgs;
+  if (!b->msgs_on_device) {
+    if (b->msgs_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_msgs, b->msgs, b->msgs_bytes, cudaMemcpyHostToDevice, st));
+    d_msgs = e->d_msgs;
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->d_offsets, b->offsets, n_msgs * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(e->d_lens, b->lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
+  if (b->precomputed_lens) CUDA_TRY(cudaMemcpyAsync(e->d_pre, b->precomputed_lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
+  // host arrays must be consumed before we return (pageable memory is staged synchronously by the runtime;
+  // for pinned memory we wait for the copies explicitly)
+  cudaEvent_t copied;
+  CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(copied, st));
+
+  uint8_t* dig_dev = b->digests_dev ? b->digests_dev : (b->digests_host ? e->d_digests_out : nullptr);
+  unsigned long long* cks_dev = b->checksums_dev ? (unsigned long long*)b->checksums_dev : (b->checksums_host ? e->d_cks : nullptr);
+  int launches = 0;
+  TraceArgs ta{};
+  ta.n_msgs = n_msgs; ta.n_digests = D; ta.msgs = d_msgs; ta.offsets = e->d_offsets; ta.lens = e->d_lens;
+  ta.pre_lens = b->precomputed_lens ? e->d_pre : nullptr;
+  ta.btrace = e->d_btrace; ta.dtrace = e->d_dtrace; ta.digests = dig_dev; ta.digests_plan = e->d_digests;
+  ta.blocks_per_inst = e->blocks_per_inst; ta.dtrace_words_per_inst = e->dtrace_words_per_inst;
+  k_trace<<<(unsigned)((n_msgs + 127) / 128), 128, 0, st>>>(ta);
+  launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (b->gate || b->lookup || b->spread || cks_dev) {
+    CUDA_TRY(cudaMemsetAsync(e->d_counter, 0, 8, st));
+    if (cks_dev) CUDA_TRY(cudaMemsetAsync(cks_dev, 0, b->n_instances * 32, st));
+    JobArgs ja{};
+    ja.n_inst = b->n_instances; ja.btrace = e->d_btrace; ja.dtrace = e->d_dtrace;
+    ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
+    ja.cks = cks_dev; ja.job_counter = e->d_counter;
+    uint64_t n_jobs = b->n_instances * (uint64_t)(e->blocks_per_inst + D);
+    unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
+    k_expand<EXPAND_THREADS><<<grid, EXPAND_THREADS, e->dplan.smem_bytes, st>>>(e->dplan, ja);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (b->digests_host) CUDA_TRY(cudaMemcpyAsync(b->digests_host, dig_dev, n_msgs * 32, cudaMemcpyDeviceToHost, st));
+  if (b->checksums_host) CUDA_TRY(cudaMemcpyAsync(b->checksums_host, cks_dev, b->n_instances * 32, cudaMemcpyDeviceToHost, st));
+  e->last_launches = launches;
+  CUDA_TRY(cudaEventSynchronize(copied));
+  cudaEventDestroy(copied);
+  return H2SHA_OK;
+}
+
+int h2sha_zero_outputs(h2sha_engine_t* e, uint64_t n_inst, void* gate, void* lookup, void* spread, int only_unassigned, void* stream) {
+  if (!e) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  void* bufs[3] = {gate, lookup, spread};
+  uint64_t cells[3] = {e->dplan.gate_inst_cells, e->dplan.lookup_inst_cells, e->dplan.spread_inst_cells};
+  for (int b = 0; b < 3; b++) {
+    if (!bufs[b]) continue;
+    if (!only_unassigned) { CUDA_TRY(cudaMemsetAsync(bufs[b], 0, n_inst * cells[b] * 32, st)); continue; }
+    if (e->n_zero_ranges[b] == 0) continue;
+    dim3 grid(64, (unsigned)n_inst);
+    k_zero_ranges<<<grid, 256, 0, st>>>((uint4*)bufs[b], cells[b], n_inst, e->d_zero_ranges[b], e->n_zero_ranges[b]);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return H2SHA_OK;
+}
+
+int h2sha_debug_mont_from_u64(h2sha_engine_t* e, const uint64_t* vals_dev, uint64_t* out_dev, uint64_t n, void* stream) {
+  if (!e) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (n == 0) return H2SHA_OK;
+  k_mont_debug<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals_dev, out_dev, n);
+  CUDA_TRY(cudaGetLastError());
+  return H2SHA_OK;
+}
+
+int h2sha_last_launch_count(const h2sha_engine_t* e) { return e ? e->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// h2sha_defs.h -- data structures shared by the host planner and the sm_100a kernels.
+//
+// The engine is a two-phase, template-driven expander:
+//   phase 1 ("slots"):  per unit instance (one SHA-256 round, one schedule step, ...) a tiny
+//                       straight-line VM program turns a few u32 trace words into <= 255 raw u64 "slots";
+//   phase 2 ("cells"):  a static per-unit-type template maps every advice / lookup / spread-column cell to
+//                       (slot, shift, width) or a constant; the kernel converts to BN254 Fr Montgomery form
+//                       and stores the cell at its final (column,row).
+// Both the VM programs and the templates are produced once per configuration by the host planner
+// (planner.cc), which walks the reference's call order (lib.rs:71-349 -> compression.rs:19-213 ->
+// spread.rs:76-233) symbolically.
+#pragma once
+#include <stdint.h>
+
+namespace h2sha {
+
+// ---------------------------------------------------------------------------------------------
+// Template entry: one output cell.  8 bytes.
+//   lo: dst (16)  | tbl (16)
+//   hi: slot (8) | sh (6) | w (7) | shl (5) | kind (2) | neg (1)
+// value(raw)  = ((slots[slot] >> sh) & mask(w)) << shl          (w == 0 -> 0, w == 64 -> all bits)
+// KIND_TABLE  : cell = mont_table[tbl + value(raw)]             (constants: w == 0)
+// KIND_GENERIC: cell = Mont(value(raw)), negated mod p if neg
+// KIND_SIGNED : slots[slot] is an int64; cell = Mont(|v|), negated if v < 0
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { KIND_TABLE = 0, KIND_GENERIC = 1, KIND_SIGNED = 2 };
+
+struct TmplEntry {
+  uint32_t lo, hi;
+};
+static inline TmplEntry tmpl_pack(uint32_t dst, uint32_t tbl, uint32_t slot, uint32_t sh, uint32_t w, uint32_t shl, uint32_t kind,
+                                  uint32_t neg) {
+  TmplEntry e;
+  e.lo = (dst & 0xffffu) | (tbl << 16);
+  e.hi = (slot & 0xffu) | ((sh & 63u) << 8) | ((w & 127u) << 14) | ((shl & 31u) << 21) | ((kind & 3u) << 26) | ((neg & 1u) << 28);
+  return e;
+}
+#define H2SHA_TE_DST(e) ((e).lo & 0xffffu)
+#define H2SHA_TE_TBL(e) ((e).lo >> 16)
+#define H2SHA_TE_SLOT(e) ((e).hi & 0xffu)
+#define H2SHA_TE_SH(e) (((e).hi >> 8) & 63u)
+#define H2SHA_TE_W(e) (((e).hi >> 14) & 127u)
+#define H2SHA_TE_SHL(e) (((e).hi >> 21) & 31u)
+#define H2SHA_TE_KIND(e) (((e).hi >> 26) & 3u)
+#define H2SHA_TE_NEG(e) (((e).hi >> 28) & 1u)
+
+// ---------------------------------------------------------------------------------------------
+// Slot VM.  Operand (32 bit): is_const (1) | slot-or-const-index (12) | sh (6) | w (7)
+//   is_const: value = raw_consts[index]   else: value = (slots[slot] >> sh) & mask(w)
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t {
+  OP_ADD = 0,        // dst = A + B
+  OP_SUB = 1,        // dst = A - B            (wrapping; read back as int64 by KIND_SIGNED)
+  OP_MULADD = 2,     // dst = A * B + C
+  OP_SPREAD = 3,     // dst = bit-interleave of the low 32 bits of A with zeros (bit i -> bit 2i)
+  OP_COMPRESS2 = 4,  // dst = even16(A) | even16(B)<<16 | odd16(A)<<32 | odd16(B)<<48   (A,B 32-bit)
+  OP_EQ = 5,         // dst = (A == B)
+  OP_GT = 6,         // dst = (A > B), unsigned
+  OP_SEL = 7,        // dst = A ? B : C
+  OP_MOV = 8,        // dst = A
+};
+struct VmIns {
+  uint32_t op_dst;  // op (8) | dst slot (8)
+  uint32_t a, b, c;
+};
+static inline uint32_t vm_operand_slot(uint32_t slot, uint32_t sh, uint32_t w) { return (slot << 1) | ((sh & 63u) << 13) | ((w & 127u) << 19); }
+static inline uint32_t vm_operand_const(uint32_t idx) { return 1u | (idx << 1); }
+
+// ---------------------------------------------------------------------------------------------
+// Unit type: program + templates (offsets into the plan's flat arrays).
+// ---------------------------------------------------------------------------------------------
+struct UnitType {
+  uint32_t n_in, n_slots;        // input slots, total slots (slot stride is n_slots | 1)
+  uint32_t prog_off, prog_len;   // VmIns
+  uint32_t gate_off, gate_len;   // TmplEntry, table-kind entries first
+  uint32_t gate_n_table;         // number of leading KIND_TABLE entries in the gate template
+  uint32_t lk_off, lk_len;       // lookup-column template (dst = index in the unit's lookup span)
+  uint32_t limb_off, limb_len;   // spread-column template: 2 entries per limb (dense, spread); dst = limb index in unit
+};
+
+// Input source of slot k of a unit instance u: trace[in_base + in_stride * u]; or the instance index u itself.
+struct InputMap {
+  int32_t base;    // index into the job's trace array (u32 words); -1: value = u
+  int32_t stride;
+};
+enum { MAX_UNIT_INPUTS = 20 };
+
+// A group = `count` consecutive instances of one unit type inside a job.
+struct UnitGroup {
+  uint32_t type;
+  uint32_t count;
+  uint32_t slot_base;            // offset (in u64) of instance 0's slots in the job's slot area
+  uint32_t gate_base, gate_stride;   // gate-stream index of instance 0 relative to the job's gate base, and per-instance stride
+  uint32_t lk_base, lk_stride;       // same for the lookup stream
+  uint32_t limb_base, limb_stride;   // same for spread limbs
+  InputMap in[MAX_UNIT_INPUTS];
+};
+
+// Warp task of phase 1: lanes = instances [first, first+32) of a group.
+struct WarpTask {
+  uint32_t group, first;
+};
+
+// A job class: the block job (one sha256_compression) or the per-digest prologue/epilogue job.
+struct JobClass {
+  uint32_t group_off, n_groups;  // UnitGroup
+  uint32_t task_off, n_tasks;    // WarpTask
+  uint32_t n_slots_total;        // u64 slots needed in shared memory
+  uint32_t n_trace_words;        // u32 words of trace the job loads
+};
+
+// Trace layout of a block job (u32 words), written by the trace kernel:
+//   W[64] | A[68] | E[68]          A[k+4] / E[k+4] = working variables a / e after round k;
+//                                  A[3..0] = a,b,c,d and E[3..0] = e,f,g,h of the input state
+enum { TR_W = 0, TR_A = 64, TR_E = 132, TR_K = 200, TR_BLOCK_WORDS = 200, TR_BLOCK_WORDS_WITH_K = 264 };
+// Trace layout of a digest job: scalars | H[8] | states[(R+1)][8] | msg words [R][16]
+enum { TD_LEN = 0, TD_NUM_ROUND = 1, TD_PRE_ROUND = 2, TD_TARGET = 3, TD_H = 4, TD_STATES = 12 };
+
+// Per-digest placement inside one instance (all stream indices are instance-relative).
+struct DigestPlace {
+  uint32_t max_bytes, n_blocks;
+  uint32_t gate_base, lk_base, limb_base;   // start of this digest's prologue
+  uint32_t blk_gate_base, blk_lk_base, blk_limb_base;   // block 0 of this digest (after the one-time zero cell, if any)
+  uint32_t blk_gate_stride, blk_lk_stride, blk_limb_stride;
+  uint32_t job_class;            // digest-job class index (block jobs all share class 0)
+  uint32_t trace_words;          // digest-job trace words
+};
+
+}  // namespace h2sha

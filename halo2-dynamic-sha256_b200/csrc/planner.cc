@@ -1,0 +1,1020 @@
+// planner.cc -- symbolic walk of the reference program -> static plan.  See planner.h.
+//
+// Every function below that mirrors a reference function cites it.  The "symbolic value" of a cell
+// (struct Sym) says how the kernel derives the cell from the unit's raw u64 slots; the gate/range op
+// patterns are those of halo2-base v0.2.x.
+#include "planner.h"
+
+#include <algorithm>
+#include <array>
+#include <map>
+#include <stdexcept>
+
+namespace h2sha {
+namespace {
+
+enum : uint8_t { T_CONST = 0, T_BYTE = 1, T_SBYTE = 2, T_INV = 3 };
+
+struct Sym {
+  uint8_t kind = KIND_GENERIC;
+  uint8_t neg = 0;
+  uint8_t slot = 0, sh = 0, w = 0, shl = 0;
+  uint8_t table = T_CONST;
+  uint16_t tbl_off = 0;
+  bool operator==(const Sym& o) const {
+    return kind == o.kind && neg == o.neg && slot == o.slot && sh == o.sh && w == o.w && shl == o.shl && table == o.table && tbl_off == o.tbl_off;
+  }
+};
+
+struct AV {  // AssignedValue: global gate-stream index + symbolic value valid inside unit `serial`
+  uint32_t idx = 0;
+  Sym s;
+  uint32_t serial = 0;  // 0: valid everywhere (constants)
+};
+enum { QC_EXISTING, QC_CONSTANT, QC_WITNESS };
+struct QC {
+  int kind;
+  AV ex;
+  U256 cval;  // QC_CONSTANT: canonical value
+  Sym s;
+  bool has_raw = false;  // QC_CONSTANT: fits a u64 -> usable as VM operand
+  uint64_t raw = 0;
+  bool dyn = false;      // QC_CONSTANT whose value differs per unit instance (cell comes from a slot)
+};
+
+struct UnitRec {
+  std::vector<Sym> gate, lk, limb;
+  std::vector<VmIns> prog;
+  std::vector<InputMap> in;
+  uint32_t n_slots = 0;
+  bool same_as(const UnitRec& o) const {
+    if (!(gate == o.gate && lk == o.lk && limb == o.limb) || n_slots != o.n_slots || prog.size() != o.prog.size()) return false;
+    for (size_t i = 0; i < prog.size(); i++)
+      if (prog[i].op_dst != o.prog[i].op_dst || prog[i].a != o.prog[i].a || prog[i].b != o.prog[i].b || prog[i].c != o.prog[i].c) return false;
+    return true;
+  }
+};
+
+struct GroupRec {
+  std::string type;
+  uint32_t count = 0, seen = 0;
+  uint32_t gate_base = 0, gate_stride = 0, lk_base = 0, lk_stride = 0, limb_base = 0, limb_stride = 0;
+  std::vector<InputMap> in;
+  bool same_as(const GroupRec& o) const {
+    if (type != o.type || count != o.count || gate_base != o.gate_base || gate_stride != o.gate_stride || lk_base != o.lk_base ||
+        lk_stride != o.lk_stride || limb_base != o.limb_base || limb_stride != o.limb_stride || in.size() != o.in.size())
+      return false;
+    for (size_t i = 0; i < in.size(); i++)
+      if (in[i].base != o.in[i].base || in[i].stride != o.in[i].stride) return false;
+    return true;
+  }
+};
+struct ClassRec {
+  uint32_t gate_origin = 0, lk_origin = 0, limb_origin = 0;
+  std::vector<GroupRec> groups;
+};
+
+[[noreturn]] void fail(const std::string& m) { throw std::runtime_error(m); }
+
+U256 pow2(uint32_t n) {
+  if (n >= 254) fail("pow2 too large");
+  U256 r = {{0, 0, 0, 0}};
+  r.l[n / 64] = 1ULL << (n % 64);
+  return r;
+}
+
+class Builder {
+ public:
+  Builder(const Config& cfg, Plan* plan) : cfg_(cfg), P_(plan) {}
+
+  void run() {
+    if (cfg_.max_variable_byte_sizes.empty()) fail("max_variable_byte_sizes is empty");
+    if (cfg_.limb_bits == 0 || 16 % cfg_.limb_bits != 0) fail("num_bits_lookup must divide 16 (spread.rs:37)");
+    if (cfg_.limb_bits > 8) fail("num_bits_lookup > 8 is not supported by this engine (shared-memory spread table)");
+    if (cfg_.spread_cols == 0) fail("num_advice_columns must be >= 1");
+    if (cfg_.lookup_bits < 8 || cfg_.lookup_bits > 32) fail("lookup_bits must be in [8, 32]");
+    if (cfg_.max_rows < 64) fail("max_rows too small");
+    uint32_t max_r = 0;
+    for (uint32_t m : cfg_.max_variable_byte_sizes) {
+      if (m == 0 || m % 64 != 0) fail("max_variable_byte_size must be a positive multiple of 64 (lib.rs:57-59)");
+      max_r = std::max(max_r, m / 64);
+    }
+    inv_bias_ = max_r + 2;
+    if (2 * inv_bias_ + 1 > 250) fail("max_variable_byte_size too large for the inverse table");
+    const_id(U256{{0, 0, 0, 0}});  // table entry 0 is the zero constant
+    for (uint32_t d = 0; d < cfg_.max_variable_byte_sizes.size(); d++) digest(d);
+    finalize();
+  }
+
+ private:
+  const Config& cfg_;
+  Plan* P_;
+  // ---- global stream state (Context) ----
+  uint32_t n_gate_ = 0, col_ = 0, row_ = 0;
+  uint32_t n_lk_ = 0, n_limb_ = 0;
+  bool has_zero_ = false;
+  AV zero_;
+  std::vector<U256> consts_;  // Montgomery table consts (superset of fixed cells; same order for fixed ones)
+  std::map<std::pair<std::pair<uint64_t, uint64_t>, std::pair<uint64_t, uint64_t>>, uint32_t> const_map_;
+  std::map<uint64_t, uint32_t> raw_map_;
+  uint32_t inv_bias_ = 0;
+  // ---- unit / group / class recording ----
+  std::map<std::string, uint32_t> type_idx_;
+  std::vector<UnitRec> type_recs_;
+  UnitRec cur_;
+  bool in_unit_ = false;
+  uint32_t serial_ = 0;
+  uint32_t unit_gate0_ = 0, unit_lk0_ = 0, unit_limb0_ = 0;
+  ClassRec* cls_ = nullptr;
+  GroupRec* grp_ = nullptr;
+  std::vector<ClassRec> class_recs_;  // index = class id
+  std::vector<bool> class_set_;
+
+  // ======================================================================================
+  // symbolic values
+  // ======================================================================================
+  static Sym ext(uint32_t slot, uint32_t sh, uint32_t w) {
+    Sym s;
+    s.kind = KIND_GENERIC;
+    s.slot = (uint8_t)slot; s.sh = (uint8_t)sh; s.w = (uint8_t)w;
+    if (slot > 255 || sh > 63 || w > 64 || sh + w > 64) fail("bad extract");
+    return s;
+  }
+  static bool plain(const Sym& s) { return s.kind == KIND_GENERIC && !s.neg && s.shl == 0; }
+  // bits [sh2, sh2+w2) of an extract
+  static Sym sub(const Sym& s, uint32_t sh2, uint32_t w2) {
+    if (!plain(s)) fail("sub-extract of a non-plain value");
+    uint32_t w = sh2 >= s.w ? 0 : std::min<uint32_t>(w2, s.w - sh2);
+    return ext(s.slot, w ? s.sh + sh2 : 0, w);
+  }
+  static Sym shl(const Sym& s, uint32_t n) {
+    if (!plain(s) || n > 31) fail("bad shl");
+    Sym r = s; r.shl = (uint8_t)n; return r;
+  }
+  static Sym negated(const Sym& s) {
+    if (!plain(s)) fail("bad neg");
+    Sym r = s; r.neg = 1; return r;
+  }
+  static Sym table(uint8_t t, const Sym& idx, uint32_t off = 0) {
+    if (!plain(idx)) fail("table index must be a plain extract");
+    Sym r = idx; r.kind = KIND_TABLE; r.table = t; r.tbl_off = (uint16_t)off; return r;
+  }
+  static Sym signed_slot(uint32_t slot) {
+    Sym r; r.kind = KIND_SIGNED; r.slot = (uint8_t)slot; r.w = 64; return r;
+  }
+
+  // index of a constant in the Montgomery table
+  uint32_t const_id(const U256& v) {
+    auto key = std::make_pair(std::make_pair(v.l[0], v.l[1]), std::make_pair(v.l[2], v.l[3]));
+    auto it = const_map_.find(key);
+    if (it != const_map_.end()) return it->second;
+    uint32_t id = (uint32_t)consts_.size();
+    consts_.push_back(v);
+    fixed_of_const_.push_back(~0u);
+    const_map_[key] = id;
+    return id;
+  }
+  // Context::assign_fixed: the fixed-column cell of a constant, de-duplicated, in first-use order
+  uint32_t fixed_id(uint32_t cid) {
+    if (fixed_of_const_[cid] == ~0u) {
+      fixed_of_const_[cid] = n_fixed_++;
+      if (cfg_.record_shape) P_->fixed_consts.push_back(consts_[cid]);
+    }
+    return fixed_of_const_[cid];
+  }
+  std::vector<uint32_t> fixed_of_const_;
+  uint32_t n_fixed_ = 0;
+
+  uint32_t raw_const(uint64_t v) {
+    auto it = raw_map_.find(v);
+    if (it != raw_map_.end()) return it->second;
+    uint32_t id = (uint32_t)P_->raw_consts.size();
+    P_->raw_consts.push_back(v);
+    raw_map_[v] = id;
+    return id;
+  }
+
+  // ---- QuantumCell constructors ----
+  QC EX(const AV& a) { QC q; q.kind = QC_EXISTING; q.ex = a; q.s = a.s; return q; }
+  QC CU(const U256& v) {  // Constant(F)
+    QC q; q.kind = QC_CONSTANT; q.cval = v;
+    uint32_t id = const_id(v);
+    q.s = Sym(); q.s.kind = KIND_TABLE; q.s.table = T_CONST; q.s.tbl_off = (uint16_t)id; q.s.w = 0;
+    q.has_raw = (v.l[1] | v.l[2] | v.l[3]) == 0; q.raw = v.l[0];
+    return q;
+  }
+  QC C(uint64_t v) { return CU(fr::from_u64(v)); }
+  // Constant whose value differs per unit instance (round constant K[t], loop counter n): the cell is
+  // produced from an input slot; the fixed-column bookkeeping uses this instance's concrete value.
+  QC Cdyn(const Sym& s, const U256& this_instance_value) {
+    QC q; q.kind = QC_CONSTANT; q.s = s; q.has_raw = false; q.dyn = true; q.cval = this_instance_value; return q;
+  }
+  QC W(const Sym& s) { QC q; q.kind = QC_WITNESS; q.s = s; return q; }
+
+  uint32_t operand(const QC& q) {
+    if (q.kind == QC_CONSTANT && !q.dyn) {
+      if (!q.has_raw) fail("constant does not fit a VM operand");
+      return vm_operand_const(raw_const(q.raw));
+    }
+    return operand(q.s);
+  }
+  uint32_t operand(const Sym& s) {
+    if (!plain(s)) fail("VM operand must be a plain extract");
+    return vm_operand_slot(s.slot, s.sh, s.w);
+  }
+
+  // ======================================================================================
+  // unit / group / class bookkeeping
+  // ======================================================================================
+  void use_class(ClassRec* c) { cls_ = c; }
+  void begin_group(const std::string& type, uint32_t count) {
+    if (grp_) fail("nested group");
+    cls_->groups.emplace_back();
+    grp_ = &cls_->groups.back();
+    grp_->type = type; grp_->count = count;
+  }
+  void end_group() {
+    if (!grp_ || grp_->seen != grp_->count) fail("group instance count mismatch: " + (grp_ ? grp_->type : std::string("?")));
+    grp_ = nullptr;
+  }
+  void begin_unit() {
+    if (in_unit_ || !grp_) fail("begin_unit outside group");
+    in_unit_ = true; serial_++;
+    cur_ = UnitRec();
+    unit_gate0_ = n_gate_; unit_lk0_ = n_lk_; unit_limb0_ = n_limb_;
+  }
+  // declares input slot k = trace[base + stride * u]  (base < 0: the instance index u)
+  Sym input(uint32_t k, int32_t base, int32_t stride, uint32_t w = 32) {
+    if (k != cur_.in.size() || k >= MAX_UNIT_INPUTS) fail("inputs must be declared in order");
+    cur_.in.push_back(InputMap{base, stride});
+    cur_.n_slots = k + 1;
+    return ext(k, 0, w);
+  }
+  uint32_t new_slot() {
+    if (cur_.n_slots >= 255) fail("too many slots in unit " + grp_->type);
+    return cur_.n_slots++;
+  }
+  Sym emit(uint32_t op, uint32_t a, uint32_t b, uint32_t c, uint32_t width) {
+    uint32_t dst = new_slot();
+    cur_.prog.push_back(VmIns{op | (dst << 8), a, b, c});
+    return ext(dst, 0, width);
+  }
+  void end_unit() {
+    if (!in_unit_) fail("end_unit");
+    in_unit_ = false;
+    uint32_t u = grp_->seen++;
+    // per-instance input base: the declared base is that of instance u -> normalise to instance 0
+    std::vector<InputMap> in0 = cur_.in;
+    for (auto& m : in0)
+      if (m.base >= 0) m.base -= m.stride * (int32_t)u;
+    cur_.in = in0;
+    auto it = type_idx_.find(grp_->type);
+    if (it == type_idx_.end()) {
+      type_idx_[grp_->type] = (uint32_t)type_recs_.size();
+      type_recs_.push_back(cur_);
+    } else if (!type_recs_[it->second].same_as(cur_)) {
+      fail("unit instances of type " + grp_->type + " differ");
+    }
+    uint32_t g = unit_gate0_ - cls_->gate_origin, l = unit_lk0_ - cls_->lk_origin, m = unit_limb0_ - cls_->limb_origin;
+    if (u == 0) {
+      grp_->gate_base = g; grp_->lk_base = l; grp_->limb_base = m; grp_->in = in0;
+    } else {
+      if (u == 1) { grp_->gate_stride = g - grp_->gate_base; grp_->lk_stride = l - grp_->lk_base; grp_->limb_stride = m - grp_->limb_base; }
+      if (g != grp_->gate_base + u * grp_->gate_stride || l != grp_->lk_base + u * grp_->lk_stride || m != grp_->limb_base + u * grp_->limb_stride)
+        fail("non-uniform unit stride in " + grp_->type);
+      for (size_t i = 0; i < in0.size(); i++)
+        if (in0[i].base != grp_->in[i].base || in0[i].stride != grp_->in[i].stride) fail("non-affine input map in " + grp_->type);
+    }
+  }
+  AV rebind(const AV& a, const Sym& s) { AV r = a; r.s = s; r.serial = serial_; return r; }
+
+  // ======================================================================================
+  // halo2-base Context / FlexGate / Range (symbolic)
+  // ======================================================================================
+  void add_copy(uint32_t ak, uint32_t ai, uint32_t bk, uint32_t bi) {
+    if (cfg_.record_shape) P_->copies.push_back(CopyPair{ak, ai, bk, bi});
+  }
+  // FlexGateConfig::assign_region_in: break to the next column when `row + len >= max_rows`
+  void assign_region(const std::vector<QC>& cells, std::initializer_list<int> gate_offs, std::vector<AV>* out) {
+    if (!in_unit_) fail("assign_region outside a unit");
+    uint32_t n = (uint32_t)cells.size();
+    if (P_->breaks.empty()) P_->breaks.push_back(0);
+    if (row_ + n >= cfg_.max_rows) {
+      if (row_ == 0) fail("max_rows too small for one op");
+      row_ = 0; col_++;
+      P_->breaks.push_back(n_gate_);
+    }
+    uint32_t base = n_gate_;
+    if (out) out->resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+      const QC& q = cells[i];
+      if (q.kind == QC_EXISTING && q.ex.serial != 0 && q.ex.serial != serial_) fail("cell from another unit used without rebind in " + grp_->type);
+      cur_.gate.push_back(q.s);
+      if (cfg_.record_shape) {
+        P_->selectors.push_back(0);
+        if (q.kind == QC_EXISTING) add_copy(CP_GATE, base + i, CP_GATE, q.ex.idx);
+      }
+      if (q.kind == QC_CONSTANT) {
+        uint32_t fid = fixed_id(q.dyn ? const_id(q.cval) : q.s.tbl_off);
+        add_copy(CP_GATE, base + i, CP_FIXED, fid);
+      }
+      if (out) { (*out)[i].idx = base + i; (*out)[i].s = q.s; (*out)[i].serial = (q.s.kind == KIND_TABLE && q.s.w == 0) ? 0 : serial_; }
+    }
+    if (cfg_.record_shape)
+      for (int o : gate_offs) P_->selectors[base + o] = 1;
+    n_gate_ += n; row_ += n;
+  }
+
+  AV load_witness(const Sym& s) { std::vector<AV> o; assign_region({W(s)}, {}, &o); return o[0]; }
+  AV load_zero() {
+    if (has_zero_) return zero_;
+    std::vector<AV> o; assign_region({C(0)}, {}, &o);
+    has_zero_ = true; zero_ = o[0]; zero_.serial = 0;
+    return zero_;
+  }
+  AV add(const QC& a, const QC& b, const Sym& out) { std::vector<AV> o; assign_region({a, b, C(1), W(out)}, {0}, &o); return o[3]; }
+  AV sub(const QC& a, const QC& b, const Sym& out) { std::vector<AV> o; assign_region({W(out), b, C(1), a}, {0}, &o); return o[0]; }
+  AV neg(const QC& a, const Sym& out) { std::vector<AV> o; assign_region({a, W(out), C(1), C(0)}, {0}, &o); return o[1]; }
+  AV mul(const QC& a, const QC& b, const Sym& out) { std::vector<AV> o; assign_region({C(0), a, b, W(out)}, {0}, &o); return o[3]; }
+  AV mul_add(const QC& a, const QC& b, const QC& c, const Sym& out) { std::vector<AV> o; assign_region({c, a, b, W(out)}, {0}, &o); return o[3]; }
+  AV select(const QC& a, const QC& b, const QC& sel, const Sym& diff, const Sym& out) {
+    std::vector<AV> o;
+    assign_region({W(diff), C(1), b, a, b, sel, W(diff), W(out)}, {0, 4}, &o);
+    add_copy(CP_GATE, o[0].idx, CP_GATE, o[6].idx);
+    return o[7];
+  }
+  AV is_zero(const AV& a, const Sym& z, const Sym& inv) {
+    std::vector<AV> o;
+    assign_region({W(z), EX(a), W(inv), C(1), C(0), EX(a), W(z), C(0)}, {0, 4}, &o);
+    add_copy(CP_GATE, o[0].idx, CP_GATE, o[6].idx);
+    return o[0];
+  }
+  void assert_equal(const AV& a, const AV& b) { add_copy(CP_GATE, a.idx, CP_GATE, b.idx); }
+  void assert_is_const(const AV& a, const U256& v) {
+    add_copy(CP_GATE, a.idx, CP_FIXED, fixed_id(const_id(v)));
+  }
+  // new-slot flavours
+  AV add_new(const QC& a, const QC& b, uint32_t width) { return add(a, b, emit(OP_ADD, operand(a), operand(b), 0, width)); }
+
+  void lk_push(const AV& a) {
+    cur_.lk.push_back(a.s);
+    if (a.serial != 0 && a.serial != serial_) fail("lookup of a cell from another unit");
+    if (cfg_.record_shape) P_->lookup_cells.push_back(a.idx);
+    n_lk_++;
+  }
+  // RangeConfig::range_check (Vertical)
+  AV range_check(const AV& a, uint32_t range_bits) {
+    uint32_t lb = cfg_.lookup_bits;
+    uint32_t k = (range_bits + lb - 1) / lb, rem = range_bits % lb;
+    AV last = a;
+    if (k == 1) {
+      lk_push(a);
+    } else {
+      std::vector<QC> cells;
+      std::vector<int> limb_pos;
+      std::vector<int> offs;
+      for (uint32_t i = 0; i < k; i++) {
+        Sym limb = sub(a.s, lb * i, lb);
+        if (i == 0) { limb_pos.push_back(0); cells.push_back(W(limb)); }
+        else {
+          offs.push_back((int)cells.size() - 1);
+          limb_pos.push_back((int)cells.size());
+          cells.push_back(W(limb));
+          cells.push_back(CU(pow2(lb * i)));
+          cells.push_back(W(sub(a.s, 0, lb * (i + 1))));
+        }
+      }
+      std::vector<AV> o;
+      assign_region_offs(cells, offs, &o);
+      for (uint32_t i = 0; i < k; i++) lk_push(o[limb_pos[i]]);
+      last = o[limb_pos[k - 1]];
+      add_copy(CP_GATE, a.idx, CP_GATE, o.back().idx);
+    }
+    if (rem == 1) fail("range_check with rem_bits == 1 (assert_bit) is not used by the reference");
+    if (rem > 1) {
+      std::vector<AV> o;
+      assign_region({C(0), EX(last), CU(pow2(lb - rem)), W(shl(last.s, lb - rem))}, {0}, &o);
+      lk_push(o[3]);
+      last = o[3];
+    }
+    return last;  // the most recently looked-up cell (ctx.cells_to_lookup.last())
+  }
+  void assign_region_offs(const std::vector<QC>& cells, const std::vector<int>& offs, std::vector<AV>* out) {
+    assign_region(cells, {}, out);
+    if (cfg_.record_shape)
+      for (int o : offs) P_->selectors[(*out)[0].idx + o] = 1;
+  }
+
+  // ======================================================================================
+  // src/spread.rs
+  // ======================================================================================
+  // spread.rs:196-233
+  AV spread_limb(const AV& limb) {
+    Sym sp = table(T_SBYTE, limb.s);
+    cur_.limb.push_back(limb.s);  // dense column cell (:203-208)
+    cur_.limb.push_back(sp);      // spread column cell (:219-224)
+    AV as = load_witness(sp);     // :225
+    if (cfg_.record_shape) { P_->limb_gate_dense.push_back(limb.idx); P_->limb_gate_spread.push_back(as.idx); }
+    n_limb_++;
+    return as;
+  }
+  // spread.rs:76-123; `out` = symbolic 32-bit spread of `dense` (the caller owns the slot)
+  AV spread(const AV& dense, const Sym& out) {
+    uint32_t lb = cfg_.limb_bits, nl = 16 / lb;
+    if (!plain(dense.s) || dense.s.w != 16) fail("spread() of a value that is not a 16-bit extract");
+    std::vector<AV> limbs;
+    for (uint32_t i = 0; i < nl; i++) limbs.push_back(load_witness(sub(dense.s, lb * i, lb)));           // :85-88
+    AV sum = load_zero();                                                                                 // :90
+    for (uint32_t i = 0; i < nl; i++) sum = mul_add(EX(limbs[i]), C(1ULL << (lb * i)), EX(sum), sub(dense.s, 0, lb * (i + 1)));  // :91-98
+    assert_equal(sum, dense);                                                                             // :104-108
+    AV acc = load_zero();                                                                                 // :110
+    for (uint32_t i = 0; i < nl; i++) {                                                                   // :112-121
+      AV sl = spread_limb(limbs[i]);
+      Sym partial = (i == 0) ? table(T_SBYTE, limbs[0].s) : sub(out, 0, 2 * lb * (i + 1));
+      acc = mul_add(EX(sl), C(1ULL << (2 * lb * i)), EX(acc), partial);
+    }
+    return acc;
+  }
+  // spread.rs:139-163
+  void decompose_even_and_odd_unchecked(const Sym& even, const Sym& odd, AV* e, AV* o) {
+    *e = load_witness(even);   // :158
+    *o = load_witness(odd);    // :159
+    range_check(*e, 16);       // :160
+    range_check(*o, 16);       // :161
+  }
+
+  // ======================================================================================
+  // src/compression.rs
+  // ======================================================================================
+  struct SpreadU32 { AV lo, hi; };  // compression.rs:17
+
+  // compression.rs:215-246; x must be a 32-bit plain extract.  Allocates the slot S = spread32(x).
+  SpreadU32 state_to_spread_u32(const AV& x) {
+    Sym S = emit(OP_SPREAD, operand(sub(x.s, 0, 32)), 0, 0, 64);
+    AV lo = load_witness(sub(x.s, 0, 16));                                   // :222-230
+    AV hi = load_witness(sub(x.s, 16, 16));                                  // :226-231
+    AV composed = mul_add(EX(hi), C(1ULL << 16), EX(lo), sub(x.s, 0, 32));   // :232-237
+    assert_equal(x, composed);                                               // :238-242
+    SpreadU32 r;
+    r.lo = spread(lo, sub(S, 0, 32));                                        // :243
+    r.hi = spread(hi, sub(S, 32, 32));                                       // :244
+    return r;
+  }
+  // compression.rs:266-295; x is a plain extract of a slot holding the (< 2^64) sum
+  AV mod_u32(const AV& x) {
+    AV lo = load_witness(sub(x.s, 0, 32));                                   // :272-280
+    AV hi = load_witness(sub(x.s, 32, 32));                                  // :276-281
+    range_check(lo, 32);                                                     // :282
+    AV composed = mul_add(EX(hi), C(1ULL << 32), EX(lo), x.s);               // :283-288
+    assert_equal(x, composed);                                               // :289-293
+    return lo;
+  }
+  // shared tail of ch / maj / sigma_generic (compression.rs:344-354 etc.)
+  void check_even_odd(const AV& even, const AV& odd, const AV& v, const Sym& even_spread, const Sym& odd_spread) {
+    AV es = spread(even, even_spread);
+    AV os = spread(odd, odd_spread);
+    AV sum = mul_add(C(2), EX(os), EX(es), v.s);
+    assert_equal(sum, v);
+  }
+  // even/odd decomposition of two 32-bit values packed by OP_COMPRESS2, plus their re-spreads
+  struct EvenOdd { Sym lo_e, lo_o, hi_e, hi_o, se_lo, so_lo, se_hi, so_hi, evens32, odds32; };
+  EvenOdd compress_pair(const Sym& lo32, const Sym& hi32) {
+    Sym Cx = emit(OP_COMPRESS2, operand(lo32), operand(hi32), 0, 64);
+    Sym SE = emit(OP_SPREAD, operand(sub(Cx, 0, 32)), 0, 0, 64);
+    Sym SO = emit(OP_SPREAD, operand(sub(Cx, 32, 32)), 0, 0, 64);
+    EvenOdd r;
+    r.lo_e = sub(Cx, 0, 16); r.hi_e = sub(Cx, 16, 16); r.lo_o = sub(Cx, 32, 16); r.hi_o = sub(Cx, 48, 16);
+    r.se_lo = sub(SE, 0, 32); r.se_hi = sub(SE, 32, 32); r.so_lo = sub(SO, 0, 32); r.so_hi = sub(SO, 32, 32);
+    r.evens32 = sub(Cx, 0, 32); r.odds32 = sub(Cx, 32, 32);
+    return r;
+  }
+  // compression.rs:297-405
+  AV ch(const SpreadU32& x, const SpreadU32& y, const SpreadU32& z) {
+    AV p_lo = add_new(EX(x.lo), EX(y.lo), 32);                               // :309-313
+    AV p_hi = add_new(EX(x.hi), EX(y.hi), 32);                               // :314-318
+    const uint64_t MASK_EVEN_32 = 0x55555555ULL;                             // :319
+    AV x_neg_lo = neg(EX(x.lo), negated(x.lo.s));                            // :320
+    AV x_neg_hi = neg(EX(x.hi), negated(x.hi.s));                            // :321
+    // three_add(mask, -x, z) (:322-335, :521-530): add1 = mask - x, add2 = add1 + z
+    QC mask = C(MASK_EVEN_32);
+    AV q1_lo = add(mask, EX(x_neg_lo), emit(OP_SUB, operand(mask), operand(x.lo.s), 0, 32));
+    AV q_lo = add_new(EX(q1_lo), EX(z.lo), 32);
+    AV q1_hi = add(mask, EX(x_neg_hi), emit(OP_SUB, operand(mask), operand(x.hi.s), 0, 32));
+    AV q_hi = add_new(EX(q1_hi), EX(z.hi), 32);
+    EvenOdd p = compress_pair(p_lo.s, p_hi.s), q = compress_pair(q_lo.s, q_hi.s);
+    AV p_lo_e, p_lo_o, p_hi_e, p_hi_o, q_lo_e, q_lo_o, q_hi_e, q_hi_o;
+    decompose_even_and_odd_unchecked(p.lo_e, p.lo_o, &p_lo_e, &p_lo_o);      // :336-343
+    decompose_even_and_odd_unchecked(p.hi_e, p.hi_o, &p_hi_e, &p_hi_o);
+    decompose_even_and_odd_unchecked(q.lo_e, q.lo_o, &q_lo_e, &q_lo_o);
+    decompose_even_and_odd_unchecked(q.hi_e, q.hi_o, &q_hi_e, &q_hi_o);
+    check_even_odd(p_lo_e, p_lo_o, p_lo, p.se_lo, p.so_lo);                  // :344-354
+    check_even_odd(p_hi_e, p_hi_o, p_hi, p.se_hi, p.so_hi);                  // :355-365
+    check_even_odd(q_lo_e, q_lo_o, q_lo, q.se_lo, q.so_lo);                  // :366-376
+    check_even_odd(q_hi_e, q_hi_o, q_hi, q.se_hi, q.so_hi);                  // :377-387
+    // odd(P) and odd(Q) have disjoint bits, so both 16-bit halves add without carry: one packed slot
+    Sym OUT = emit(OP_ADD, operand(p.odds32), operand(q.odds32), 0, 32);
+    AV out_lo = add(EX(p_lo_o), EX(q_lo_o), sub(OUT, 0, 16));                // :388-392
+    AV out_hi = add(EX(p_hi_o), EX(q_hi_o), sub(OUT, 16, 16));               // :393-397
+    return mul_add(EX(out_hi), C(1ULL << 16), EX(out_lo), OUT);              // :398-403
+  }
+  // compression.rs:460-519
+  AV maj(const SpreadU32& x, const SpreadU32& y, const SpreadU32& z) {
+    AV m1_lo = add_new(EX(x.lo), EX(y.lo), 32);                              // :472-478 (three_add)
+    AV m_lo = add_new(EX(m1_lo), EX(z.lo), 32);
+    AV m1_hi = add_new(EX(x.hi), EX(y.hi), 32);                              // :479-485
+    AV m_hi = add_new(EX(m1_hi), EX(z.hi), 32);
+    EvenOdd m = compress_pair(m_lo.s, m_hi.s);
+    AV lo_e, lo_o, hi_e, hi_o;
+    decompose_even_and_odd_unchecked(m.lo_e, m.lo_o, &lo_e, &lo_o);          // :486-489
+    decompose_even_and_odd_unchecked(m.hi_e, m.hi_o, &hi_e, &hi_o);
+    check_even_odd(lo_e, lo_o, m_lo, m.se_lo, m.so_lo);                      // :490-500
+    check_even_odd(hi_e, hi_o, m_hi, m.se_hi, m.so_hi);                      // :501-511
+    return mul_add(EX(hi_o), C(1ULL << 16), EX(lo_o), m.odds32);             // :512-517
+  }
+  // compression.rs:702-882.  xs.lo / xs.hi must be extracts [0,32) / [32,64) of one slot S = spread32(x).
+  AV sigma_generic(const SpreadU32& xs, const int starts[4], const int ends[4], const uint64_t coeffs[4]) {
+    const Sym& lo = xs.lo.s;
+    if (!plain(lo) || !plain(xs.hi.s) || lo.slot != xs.hi.s.slot || lo.sh != 0 || lo.w != 32 || xs.hi.s.sh != 32 || xs.hi.s.w != 32)
+      fail("sigma_generic: x_spread must be the two halves of one spread slot");
+    Sym S = ext(lo.slot, 0, 64);
+    AV piece[4];
+    for (int k = 0; k < 4; k++) piece[k] = load_witness(sub(S, 2 * starts[k], 2 * (ends[k] - starts[k])));   // :719-734
+    {                                                                        // :735-766
+      AV sum = piece[0];
+      for (int k = 1; k < 4; k++) sum = mul_add(EX(piece[k]), C(1ULL << (2 * starts[k])), EX(sum), sub(S, 0, 2 * ends[k]));
+      AV x_composed = mul_add(EX(xs.hi), C(1ULL << 32), EX(xs.lo), S);
+      assert_equal(x_composed, sum);
+    }
+    AV r_spread = load_zero();                                               // :775-810
+    for (int k = 0; k < 4; k++) {
+      QC coeff = C(coeffs[k]);
+      uint32_t prev = (k == 0) ? vm_operand_const(raw_const(0)) : operand(r_spread.s);
+      Sym acc = emit(OP_MULADD, operand(coeff), operand(piece[k].s), prev, 64);
+      r_spread = mul_add(coeff, EX(piece[k]), EX(r_spread), acc);
+    }
+    Sym Rr = r_spread.s;
+    AV r_lo = load_witness(sub(Rr, 0, 32));                                  // :811-821
+    AV r_hi = load_witness(sub(Rr, 32, 32));
+    range_check(r_lo, 32);                                                   // :822
+    range_check(r_hi, 32);                                                   // :823
+    AV composed = mul_add(EX(r_hi), C(1ULL << 32), EX(r_lo), Rr);            // :824-829
+    assert_equal(r_spread, composed);                                        // :830-834
+    EvenOdd eo = compress_pair(r_lo.s, r_hi.s);
+    AV lo_e, lo_o, hi_e, hi_o;
+    decompose_even_and_odd_unchecked(eo.lo_e, eo.lo_o, &lo_e, &lo_o);        // :843-846
+    decompose_even_and_odd_unchecked(eo.hi_e, eo.hi_o, &hi_e, &hi_o);
+    check_even_odd(lo_e, lo_o, r_lo, eo.se_lo, eo.so_lo);                    // :852-862
+    check_even_odd(hi_e, hi_o, r_hi, eo.se_hi, eo.so_hi);                    // :863-873
+    return mul_add(EX(hi_e), C(1ULL << 16), EX(lo_e), eo.evens32);           // :874-879
+  }
+#define B_(n) (1ULL << (n))
+  AV sigma_upper0(const SpreadU32& x) {  // compression.rs:594-619
+    static const int S[4] = {0, 2, 13, 22}, E[4] = {2, 13, 22, 32};
+    static const uint64_t K[4] = {B_(60) + B_(38) + B_(20), B_(0) + B_(42) + B_(24), B_(22) + B_(0) + B_(46), B_(40) + B_(18) + B_(0)};
+    return sigma_generic(x, S, E, K);
+  }
+  AV sigma_upper1(const SpreadU32& x) {  // compression.rs:621-646
+    static const int S[4] = {0, 6, 11, 25}, E[4] = {6, 11, 25, 32};
+    static const uint64_t K[4] = {B_(52) + B_(42) + B_(14), B_(0) + B_(54) + B_(26), B_(10) + B_(0) + B_(36), B_(38) + B_(28) + B_(0)};
+    return sigma_generic(x, S, E, K);
+  }
+  AV sigma_lower0(const SpreadU32& x) {  // compression.rs:648-673
+    static const int S[4] = {0, 3, 7, 18}, E[4] = {3, 7, 18, 32};
+    static const uint64_t K[4] = {B_(50) + B_(28), B_(0) + B_(56) + B_(34), B_(8) + B_(0) + B_(42), B_(30) + B_(22) + B_(0)};
+    return sigma_generic(x, S, E, K);
+  }
+  AV sigma_lower1(const SpreadU32& x) {  // compression.rs:675-700
+    static const int S[4] = {0, 10, 17, 19}, E[4] = {10, 17, 19, 32};
+    static const uint64_t K[4] = {B_(30) + B_(26), B_(0) + B_(50) + B_(46), B_(14) + B_(0) + B_(60), B_(18) + B_(4) + B_(0)};
+    return sigma_generic(x, S, E, K);
+  }
+#undef B_
+  // a SpreadU32 living in another unit, re-derived in this unit from the u32 input `x`
+  SpreadU32 rebind_spread(const SpreadU32& src, const Sym& x) {
+    Sym S = emit(OP_SPREAD, operand(sub(x, 0, 32)), 0, 0, 64);
+    SpreadU32 r;
+    r.lo = rebind(src.lo, sub(S, 0, 32));
+    r.hi = rebind(src.hi, sub(S, 32, 32));
+    return r;
+  }
+
+  static const uint32_t* round_constants() {
+    static const uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+        0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+        0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+        0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+        0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+        0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    return K;
+  }
+
+  // compression.rs:19-213, split into units.  `blk` is the block-class recorder, `dig` the enclosing digest's.
+  void sha256_compression(ClassRec* blk, ClassRec* dig, const std::vector<AV>& in_bytes /*64*/, const AV pre[8], AV next[8]) {
+    if (!has_zero_) {  // the one-time `C 0` cell of the first load_zero in the Context (:34) belongs to the digest job
+      use_class(dig);
+      begin_group("ZERO", 1); begin_unit(); load_zero(); end_unit(); end_group();
+    }
+    use_class(blk);
+    blk->gate_origin = n_gate_; blk->lk_origin = n_lk_; blk->limb_origin = n_limb_;
+    blk->groups.clear();
+    AV w[64]; SpreadU32 ws[64];
+    begin_group("WORD", 16);                                                 // :31-47
+    for (int i = 0; i < 16; i++) {
+      begin_unit();
+      Sym Wi = input(0, TR_W + i, 1);
+      AV sum = load_zero();
+      for (int idx = 0; idx < 4; idx++) {
+        AV byte = rebind(in_bytes[4 * i + 3 - idx], sub(Wi, 8 * idx, 8));
+        sum = mul_add(EX(byte), C(1ULL << (8 * idx)), EX(sum), sub(Wi, 0, 8 * (idx + 1)));
+      }
+      w[i] = sum;
+      end_unit();
+    }
+    end_group();
+    begin_group("STSW", 16);                                                 // :53-56
+    for (int i = 0; i < 16; i++) {
+      begin_unit();
+      Sym Wi = input(0, TR_W + i, 1);
+      ws[i] = state_to_spread_u32(rebind(w[i], Wi));
+      end_unit();
+    }
+    end_group();
+    begin_group("SCHED", 48);                                                // :57-96
+    for (int idx = 16; idx < 64; idx++) {
+      begin_unit();
+      Sym w2 = input(0, TR_W + idx - 2, 1), w15 = input(1, TR_W + idx - 15, 1), w7 = input(2, TR_W + idx - 7, 1), w16 = input(3, TR_W + idx - 16, 1);
+      AV term1 = sigma_lower1(rebind_spread(ws[idx - 2], w2));
+      AV term3 = sigma_lower0(rebind_spread(ws[idx - 15], w15));
+      AV sum = add_new(EX(term1), EX(rebind(w[idx - 7], w7)), 33);
+      sum = add_new(EX(sum), EX(term3), 34);
+      sum = add_new(EX(sum), EX(rebind(w[idx - 16], w16)), 35);
+      w[idx] = mod_u32(sum);
+      ws[idx] = state_to_spread_u32(w[idx]);
+      end_unit();
+    }
+    end_group();
+    AV a = pre[0], b = pre[1], c = pre[2], d = pre[3], e = pre[4], f = pre[5], g = pre[6], h = pre[7];   // :99-108
+    SpreadU32 a_s, b_s, c_s, e_s, f_s, g_s;
+    begin_group("STSA", 3);                                                  // :109-111
+    { AV* src[3] = {&a, &b, &c}; SpreadU32* dst[3] = {&a_s, &b_s, &c_s};
+      for (int i = 0; i < 3; i++) { begin_unit(); Sym x = input(0, TR_A + 3 - i, -1); *dst[i] = state_to_spread_u32(rebind(*src[i], x)); end_unit(); } }
+    end_group();
+    begin_group("STSE", 3);                                                  // :113-115
+    { AV* src[3] = {&e, &f, &g}; SpreadU32* dst[3] = {&e_s, &f_s, &g_s};
+      for (int i = 0; i < 3; i++) { begin_unit(); Sym x = input(0, TR_E + 3 - i, -1); *dst[i] = state_to_spread_u32(rebind(*src[i], x)); end_unit(); } }
+    end_group();
+    // :123-124 two load_zero calls: cached, no cells
+    begin_group("ROUND", 64);                                                // :125-196
+    for (int idx = 0; idx < 64; idx++) {
+      begin_unit();
+      Sym ia = input(0, TR_A + idx + 3, 1), ib = input(1, TR_A + idx + 2, 1), ic = input(2, TR_A + idx + 1, 1), id = input(3, TR_A + idx, 1);
+      Sym ie = input(4, TR_E + idx + 3, 1), if_ = input(5, TR_E + idx + 2, 1), ig = input(6, TR_E + idx + 1, 1), ih = input(7, TR_E + idx, 1);
+      Sym iw = input(8, TR_W + idx, 1), ik = input(9, TR_K + idx, 1);
+      SpreadU32 es = rebind_spread(e_s, ie), fs = rebind_spread(f_s, if_), gs = rebind_spread(g_s, ig);
+      AV sigma_term = sigma_upper1(es);                                      // :130
+      AV ch_term = ch(es, fs, gs);                                           // :131
+      AV add1 = add_new(EX(rebind(h, ih)), EX(sigma_term), 33);              // :138-142
+      AV add2 = add_new(EX(add1), EX(ch_term), 34);                          // :143-147
+      QC kc = Cdyn(ik, fr::from_u64(round_constants()[idx]));
+      AV add3 = add(EX(add2), kc, emit(OP_ADD, operand(add2.s), operand(ik), 0, 35));   // :148-152
+      AV add4 = add_new(EX(add3), EX(rebind(w[idx], iw)), 36);               // :153-157
+      AV t1 = mod_u32(add4);                                                 // :158
+      SpreadU32 as = rebind_spread(a_s, ia), bs = rebind_spread(b_s, ib), cs = rebind_spread(c_s, ic);
+      AV sigma0 = sigma_upper0(as);                                          // :164
+      AV maj_term = maj(as, bs, cs);                                         // :165
+      AV addt2 = add_new(EX(sigma0), EX(maj_term), 33);                      // :166-170
+      AV t2 = mod_u32(addt2);                                                // :171
+      h = g; g = f; g_s = f_s; f = e; f_s = e_s;                             // :174-179
+      AV adde = add_new(EX(rebind(d, id)), EX(t1), 33);                      // :181
+      e = mod_u32(adde);                                                     // :182
+      e_s = state_to_spread_u32(e);                                          // :184
+      d = c; c = b; c_s = b_s; b = a; b_s = a_s;                             // :185-190
+      AV adda = add_new(EX(t1), EX(t2), 33);                                 // :192
+      a = mod_u32(adda);                                                     // :193
+      a_s = state_to_spread_u32(a);                                          // :195
+      end_unit();
+    }
+    end_group();
+    AV ns[8] = {a, b, c, d, e, f, g, h};                                     // :197-212
+    begin_group("FFA", 4);
+    for (int i = 0; i < 4; i++) {
+      begin_unit();
+      Sym x = input(0, TR_A + 67 - i, -1), y = input(1, TR_A + 3 - i, -1);
+      next[i] = mod_u32(add_new(EX(rebind(ns[i], x)), EX(rebind(pre[i], y)), 33));
+      end_unit();
+    }
+    end_group();
+    begin_group("FFE", 4);
+    for (int i = 0; i < 4; i++) {
+      begin_unit();
+      Sym x = input(0, TR_E + 67 - i, -1), y = input(1, TR_E + 3 - i, -1);
+      next[4 + i] = mod_u32(add_new(EX(rebind(ns[4 + i], x)), EX(rebind(pre[4 + i], y)), 33));
+      end_unit();
+    }
+    end_group();
+    commit_class(0, *blk);
+  }
+
+  void commit_class(uint32_t id, const ClassRec& c) {
+    if (class_recs_.size() <= id) { class_recs_.resize(id + 1); class_set_.resize(id + 1, false); }
+    if (!class_set_[id]) { class_recs_[id] = c; class_set_[id] = true; return; }
+    const ClassRec& o = class_recs_[id];
+    if (o.groups.size() != c.groups.size()) fail("job class shape differs between instances");
+    for (size_t i = 0; i < c.groups.size(); i++)
+      if (!o.groups[i].same_as(c.groups[i])) fail("job class group differs between instances: " + c.groups[i].type);
+  }
+
+  // ======================================================================================
+  // src/lib.rs:71-349  Sha256DynamicConfig::digest
+  // ======================================================================================
+  void digest(uint32_t d) {
+    const uint32_t M = cfg_.max_variable_byte_sizes[d], Rn = M / 64;
+    const uint32_t lb = cfg_.lookup_bits;
+    ClassRec dig, blk;
+    use_class(&dig);
+    DigestPlace dp{};
+    dp.max_bytes = M; dp.n_blocks = Rn; dp.gate_base = n_gate_; dp.lk_base = n_lk_; dp.limb_base = n_limb_;
+    dp.job_class = 1 + d;
+    const int32_t words_base = TD_STATES + 8 * (int32_t)(Rn + 1);
+    dp.trace_words = (uint32_t)words_base + 16 * Rn;
+    DigestHandles hd;
+    AV a_target, st0[8];
+    // ---- prologue: length check (:122-151) + precomputed state words (:162-165) ----
+    begin_group("PRO", 1); begin_unit();
+    {
+      Sym len = input(0, TD_LEN, 0), nr = input(1, TD_NUM_ROUND, 0), pr = input(2, TD_PRE_ROUND, 0), tg = input(3, TD_TARGET, 0);
+      Sym s0[8]; for (int i = 0; i < 8; i++) s0[i] = input(4 + i, TD_STATES + i, 0);
+      AV a_len = load_witness(len);                                          // :124-125
+      AV a_nr = load_witness(nr);                                            // :126
+      QC c64 = C(64);
+      AV a_padded = mul(EX(a_nr), c64, emit(OP_MULADD, operand(nr), operand(c64), vm_operand_const(raw_const(0)), 40));   // :127-131
+      QC c9 = C(9);
+      AV a_with9 = add(EX(a_len), c9, emit(OP_ADD, operand(len), operand(c9), 0, 33));                                   // :132-136
+      AV padding = sub(EX(a_padded), EX(a_with9), emit(OP_SUB, operand(a_padded.s), operand(a_with9.s), 0, 32));         // :137-141
+      // range.is_less_than_safe(padding, 64) (:142-143)
+      uint32_t range_bits = (7 + lb - 1) / lb * lb;  // bit_length(64) == 7
+      range_check(padding, range_bits);
+      uint32_t k = (range_bits + lb - 1) / lb, padded_bits = k * lb;
+      if (padded_bits + lb > 62) fail("lookup_bits too large for is_less_than");
+      U256 pw = pow2(padded_bits);
+      Sym shift_a = emit(OP_ADD, operand(padding.s), vm_operand_const(raw_const(1ULL << padded_bits)), 0, padded_bits + 1);
+      Sym shifted = emit(OP_SUB, operand(shift_a), operand(c64), 0, padded_bits + 1);
+      std::vector<AV> o;
+      assign_region({W(shifted), c64, C(1), W(shift_a), CU(fr::neg(pw)), C(1), EX(padding)}, {0, 3}, &o);
+      AV last = range_check(o[0], padded_bits + lb);
+      // is_zero(last limb): in a valid witness the limb is 0 (padding < 64), but stay general (limb in {0,1})
+      Sym z = emit(OP_EQ, operand(last.s), vm_operand_const(raw_const(0)), 0, 1);
+      Sym ib = emit(OP_ADD, operand(last.s), vm_operand_const(raw_const(inv_bias_)), 0, 8);
+      AV lt = is_zero(last, z, table(T_INV, ib));
+      assert_is_const(lt, fr::from_u64(1));                                  // :144
+      AV a_pre = load_witness(pr);                                           // :145-146
+      a_target = sub(EX(a_nr), EX(a_pre), tg);                               // :147-151
+      for (int i = 0; i < 8; i++) st0[i] = load_witness(s0[i]);              // :162-165
+      hd.input_len_idx = a_len.idx;
+    }
+    end_unit(); end_group();
+    // ---- input bytes (:170-173) ----
+    std::vector<AV> in_bytes(M);
+    begin_group("INB", Rn);
+    for (uint32_t j = 0; j < Rn; j++) {
+      begin_unit();
+      Sym wj[16]; for (int i = 0; i < 16; i++) wj[i] = input(i, words_base + 16 * (int32_t)j + i, 16);
+      for (int b = 0; b < 64; b++) in_bytes[64 * j + b] = load_witness(sub(wj[b / 4], 24 - 8 * (b % 4), 8));
+      end_unit();
+    }
+    end_group();
+    for (uint32_t i = 0; i < M; i++) hd.input_bytes_idx.push_back(in_bytes[i].idx);
+    if (cfg_.is_input_range_check) {                                         // :174-178
+      begin_group("INRC", Rn);
+      for (uint32_t j = 0; j < Rn; j++) {
+        begin_unit();
+        Sym wj[16]; for (int i = 0; i < 16; i++) wj[i] = input(i, words_base + 16 * (int32_t)j + i, 16);
+        for (int b = 0; b < 64; b++) range_check(rebind(in_bytes[64 * j + b], sub(wj[b / 4], 24 - 8 * (b % 4), 8)), 8);
+        end_unit();
+      }
+      end_group();
+    }
+    // ---- the block loop (:179-238) ----
+    std::vector<std::array<AV, 8>> states(Rn + 1);
+    for (int i = 0; i < 8; i++) states[0][i] = st0[i];
+    for (uint32_t j = 0; j < Rn; j++) {
+      std::vector<AV> bytes(in_bytes.begin() + 64 * j, in_bytes.begin() + 64 * (j + 1));
+      uint32_t g0 = n_gate_, l0 = n_lk_, m0 = n_limb_;
+      bool had_zero = has_zero_;
+      sha256_compression(&blk, &dig, bytes, states[j].data(), states[j + 1].data());
+      if (!had_zero) g0 += 1;
+      if (j == 0) { dp.blk_gate_base = g0; dp.blk_lk_base = l0; dp.blk_limb_base = m0; }
+      if (j == 1) { dp.blk_gate_stride = g0 - dp.blk_gate_base; dp.blk_lk_stride = l0 - dp.blk_lk_base; dp.blk_limb_stride = m0 - dp.blk_limb_base; }
+      if (j >= 1 && (g0 != dp.blk_gate_base + j * dp.blk_gate_stride || l0 != dp.blk_lk_base + j * dp.blk_lk_stride ||
+                     m0 != dp.blk_limb_base + j * dp.blk_limb_stride))
+        fail("non-uniform block stride");
+    }
+    use_class(&dig);
+    // ---- round selection (:294-310) ----
+    AV zero = load_zero();  // cached by now
+    AV out_h[8]; for (int i = 0; i < 8; i++) out_h[i] = zero;
+    begin_group("SEL", Rn + 1);
+    for (uint32_t n = 0; n <= Rn; n++) {
+      begin_unit();
+      Sym in_n = input(0, -1, 0), tg = input(1, TD_TARGET, 0);
+      Sym st[8], H[8];
+      for (int i = 0; i < 8; i++) st[i] = input(2 + i, TD_STATES + 8 * (int32_t)n + i, 8);
+      for (int i = 0; i < 8; i++) H[i] = input(10 + i, TD_H + i, 0);
+      // is_equal(Constant(n), target) = is_zero(sub(n, target))
+      Sym Dn = emit(OP_SUB, operand(in_n), operand(tg), 0, 64);
+      std::vector<AV> o;
+      assign_region({W(signed_slot(Dn.slot)), EX(rebind(a_target, tg)), C(1), Cdyn(in_n, fr::from_u64(n))}, {0}, &o);
+      Sym z = emit(OP_EQ, operand(in_n), operand(tg), 0, 1);
+      Sym ib = emit(OP_ADD, operand(Dn), vm_operand_const(raw_const(inv_bias_)), 0, 8);
+      AV selector = is_zero(o[0], z, table(T_INV, ib));
+      Sym gt = emit(OP_GT, operand(in_n), operand(tg), 0, 1);
+      for (int i = 0; i < 8; i++) {
+        // output_h_out[i] before this step: state[target] once n > target, else the zero cell
+        Sym bprev = emit(OP_MULADD, operand(gt), operand(H[i]), vm_operand_const(raw_const(0)), 32);
+        Sym df = emit(OP_SUB, operand(st[i]), operand(bprev), 0, 64);
+        Sym ov = emit(OP_SEL, operand(z), operand(st[i]), operand(bprev), 32);
+        // every instance uses the same template symbol for b (for n == 0 b is the cached zero cell and bprev == 0)
+        QC bq = EX((n == 0) ? out_h[i] : rebind(out_h[i], bprev));
+        bq.s = bprev;
+        out_h[i] = select(EX(rebind(states[n][i], st[i])), bq, EX(selector), signed_slot(df.slot), ov);
+      }
+      end_unit();
+    }
+    end_group();
+    // ---- digest bytes (:311-341) ----
+    begin_group("DIG", 1); begin_unit();
+    {
+      Sym H[8]; for (int i = 0; i < 8; i++) H[i] = input(i, TD_H + i, 0);
+      for (int wi = 0; wi < 8; wi++) {
+        AV bytes[4];
+        for (int idx = 0; idx < 4; idx++) {
+          bytes[idx] = load_witness(sub(H[wi], 24 - 8 * idx, 8));            // :319-320
+          range_check(bytes[idx], 8);                                        // :321
+          hd.output_bytes_idx[4 * wi + idx] = bytes[idx].idx;
+        }
+        AV sum = load_zero();                                                // :325
+        for (int idx = 0; idx < 4; idx++)                                    // :326-333
+          sum = mul_add(EX(bytes[idx]), C(1ULL << (24 - 8 * idx)), EX(sum), shl(sub(H[wi], 24 - 8 * idx, 8 * (idx + 1)), 24 - 8 * idx));
+        assert_equal(rebind(out_h[wi], H[wi]), sum);                         // :334-338
+      }
+    }
+    end_unit(); end_group();
+    commit_class(1 + d, dig);
+    P_->digests.push_back(dp);
+    P_->handles.push_back(hd);
+  }
+
+  // ======================================================================================
+  // finalize: pack templates, build tables, layout
+  // ======================================================================================
+  TmplEntry pack(const Sym& s0, uint32_t dst) {
+    Sym s = s0;
+    // small plain values come from the byte table instead of a Barrett reduction
+    if (s.kind == KIND_GENERIC && !s.neg && s.shl == 0 && s.w <= 8) { s.kind = KIND_TABLE; s.table = T_BYTE; s.tbl_off = 0; }
+    uint32_t tbl = 0;
+    if (s.kind == KIND_TABLE) {
+      switch (s.table) {
+        case T_CONST: tbl = s.tbl_off; break;
+        case T_BYTE: tbl = P_->tb_byte + s.tbl_off; break;
+        case T_SBYTE: tbl = P_->tb_sbyte + s.tbl_off; break;
+        case T_INV: tbl = P_->tb_inv + s.tbl_off; break;
+      }
+      if (s.table == T_SBYTE && s.w > cfg_.limb_bits) fail("spread-table index wider than a limb");
+      if (tbl > 0xffff) fail("table too large");
+    }
+    return tmpl_pack(dst, tbl, s.slot, s.sh, s.w, s.shl, s.kind, s.neg);
+  }
+
+  void finalize() {
+    Plan& P = *P_;
+    P.cfg = cfg_;
+    P.n_gate = n_gate_; P.n_lookup = n_lk_; P.n_limb = n_limb_;
+    // ---- Montgomery table ----
+    P.tb_byte = (uint32_t)consts_.size();
+    P.tb_sbyte = P.tb_byte + 256;
+    P.tb_inv = P.tb_sbyte + (1u << cfg_.limb_bits);
+    P.inv_bias = inv_bias_;
+    for (auto& c : consts_) P.mont_table.push_back(fr::to_mont(c));
+    for (uint32_t i = 0; i < 256; i++) P.mont_table.push_back(fr::to_mont(fr::from_u64(i)));
+    for (uint32_t i = 0; i < (1u << cfg_.limb_bits); i++) {
+      uint64_t sp = 0;
+      for (int b = 0; b < 8; b++) sp |= (uint64_t)((i >> b) & 1) << (2 * b);
+      P.mont_table.push_back(fr::to_mont(fr::from_u64(sp)));
+    }
+    for (int64_t dv = -(int64_t)inv_bias_; dv <= (int64_t)inv_bias_; dv++) {
+      U256 v = fr::from_i64(dv);
+      P.mont_table.push_back(fr::to_mont(dv == 0 ? fr::from_u64(1) : fr::inv(v)));
+    }
+    // ---- unit types ----
+    for (auto& kv : type_idx_) { if (P.type_names.size() <= kv.second) P.type_names.resize(kv.second + 1); P.type_names[kv.second] = kv.first; }
+    for (size_t t = 0; t < type_recs_.size(); t++) {
+      const UnitRec& u = type_recs_[t];
+      UnitType ut{};
+      ut.n_in = (uint32_t)u.in.size(); ut.n_slots = u.n_slots;
+      ut.prog_off = (uint32_t)P.prog.size(); ut.prog_len = (uint32_t)u.prog.size();
+      P.prog.insert(P.prog.end(), u.prog.begin(), u.prog.end());
+      // gate template: table-kind entries first (stable), then generic/signed
+      ut.gate_off = (uint32_t)P.tmpl.size(); ut.gate_len = (uint32_t)u.gate.size();
+      if (u.gate.size() > 0xffff) fail("unit too large");
+      std::vector<TmplEntry> tab, gen;
+      for (size_t i = 0; i < u.gate.size(); i++) {
+        TmplEntry e = pack(u.gate[i], (uint32_t)i);
+        (H2SHA_TE_KIND(e) == KIND_TABLE ? tab : gen).push_back(e);
+      }
+      ut.gate_n_table = (uint32_t)tab.size();
+      P.tmpl.insert(P.tmpl.end(), tab.begin(), tab.end());
+      P.tmpl.insert(P.tmpl.end(), gen.begin(), gen.end());
+      ut.lk_off = (uint32_t)P.tmpl.size(); ut.lk_len = (uint32_t)u.lk.size();
+      for (size_t i = 0; i < u.lk.size(); i++) P.tmpl.push_back(pack(u.lk[i], (uint32_t)i));
+      ut.limb_off = (uint32_t)P.tmpl.size(); ut.limb_len = (uint32_t)u.limb.size();
+      for (size_t i = 0; i < u.limb.size(); i++) P.tmpl.push_back(pack(u.limb[i], (uint32_t)i));
+      P.types.push_back(ut);
+      P.max_slots = std::max(P.max_slots, ut.n_slots);
+    }
+    // ---- job classes ----
+    P.max_slots = 0;
+    for (size_t ci = 0; ci < class_recs_.size(); ci++) {
+      const ClassRec& c = class_recs_[ci];
+      JobClass jc{};
+      jc.group_off = (uint32_t)P.groups.size(); jc.n_groups = (uint32_t)c.groups.size();
+      uint32_t slot_base = 0;
+      for (const GroupRec& g : c.groups) {
+        UnitGroup ug{};
+        ug.type = type_idx_.at(g.type); ug.count = g.count; ug.slot_base = slot_base;
+        ug.gate_base = g.gate_base; ug.gate_stride = g.gate_stride; ug.lk_base = g.lk_base; ug.lk_stride = g.lk_stride;
+        ug.limb_base = g.limb_base; ug.limb_stride = g.limb_stride;
+        for (size_t i = 0; i < g.in.size(); i++) ug.in[i] = g.in[i];
+        slot_base += g.count * (P.types[ug.type].n_slots | 1u);
+        P.groups.push_back(ug);
+      }
+      jc.n_slots_total = slot_base;
+      P.max_slots = std::max(P.max_slots, slot_base);
+      // warp tasks, longest program first
+      jc.task_off = (uint32_t)P.tasks.size();
+      std::vector<std::pair<uint32_t, WarpTask>> ts;
+      for (uint32_t gi = 0; gi < c.groups.size(); gi++) {
+        const UnitGroup& ug = P.groups[jc.group_off + gi];
+        for (uint32_t first = 0; first < ug.count; first += 32) ts.push_back({P.types[ug.type].prog_len, WarpTask{gi, first}});
+      }
+      std::stable_sort(ts.begin(), ts.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+      for (auto& t : ts) P.tasks.push_back(t.second);
+      jc.n_tasks = (uint32_t)ts.size();
+      jc.n_trace_words = (ci == 0) ? (uint32_t)TR_BLOCK_WORDS_WITH_K : P.digests[ci - 1].trace_words;
+      P.max_trace_words = std::max(P.max_trace_words, jc.n_trace_words);
+      P.classes.push_back(jc);
+    }
+    // ---- layout ----
+    auto up4 = [](uint32_t x) { return (x + 3u) & ~3u; };
+    P.n_gate_cols = (uint32_t)P.breaks.size();
+    uint32_t rows = 0;
+    for (size_t c = 0; c < P.breaks.size(); c++) {
+      uint32_t e = (c + 1 < P.breaks.size()) ? P.breaks[c + 1] : n_gate_;
+      rows = std::max(rows, e - P.breaks[c]);
+    }
+    P.gate_col_rows = up4(rows);
+    P.n_lookup_cols = std::max(1u, (n_lk_ + cfg_.max_rows - 1) / cfg_.max_rows);
+    P.lookup_col_rows = up4(std::min(n_lk_, cfg_.max_rows));
+    P.spread_rows = up4((n_limb_ + cfg_.spread_cols - 1) / cfg_.spread_cols);
+    compute_zero_ranges(P_);
+  }
+};
+
+}  // namespace
+
+
+void compute_zero_ranges(Plan* plan) {
+  Plan& P = *plan;
+  const Config& cfg_ = P.cfg;
+  const uint32_t n_gate_ = P.n_gate, n_lk_ = P.n_lookup, n_limb_ = P.n_limb;
+  P.zero_ranges.clear();
+  // cells of the column-major buffers nobody assigns (column tails, stride padding)
+    for (size_t c = 0; c < P.breaks.size(); c++) {
+      uint32_t e = (c + 1 < P.breaks.size()) ? P.breaks[c + 1] : n_gate_;
+      uint32_t used = e - P.breaks[c];
+      if (used < P.gate_col_rows) P.zero_ranges.push_back(ZeroRange{BUF_GATE, (uint32_t)c * P.gate_col_rows + used, P.gate_col_rows - used});
+    }
+    for (uint32_t c = 0; c < P.n_lookup_cols; c++) {
+      uint32_t used = std::min(cfg_.max_rows, n_lk_ - std::min(n_lk_, c * cfg_.max_rows));
+      if (used < P.lookup_col_rows) P.zero_ranges.push_back(ZeroRange{BUF_LOOKUP, c * P.lookup_col_rows + used, P.lookup_col_rows - used});
+    }
+    for (uint32_t c = 0; c < 2 * cfg_.spread_cols; c++) {
+      uint32_t cc = c % cfg_.spread_cols;
+      uint32_t used = (n_limb_ + cfg_.spread_cols - 1 - cc) / cfg_.spread_cols;  // limbs n with n % cols == cc
+      if (used < P.spread_rows) P.zero_ranges.push_back(ZeroRange{BUF_SPREAD, c * P.spread_rows + used, P.spread_rows - used});
+    }
+}
+
+bool build_plan(const Config& cfg, Plan* out, std::string* err) {
+  *out = Plan();
+  try {
+    Builder b(cfg, out);
+    b.run();
+  } catch (const std::exception& e) {
+    if (err) *err = e.what();
+    return false;
+  }
+  return true;
+}
+
+}  // namespace h2sha

@@ -1,0 +1,138 @@
+/*
+ * h2sha_b200.h -- C ABI of the B200-native SHA-256 witness-generation engine.
+ *
+ * Drop-in boundary for ONE path of zhmolly/halo2-dynamic-sha256: the value-producing half of
+ * `Sha256DynamicConfig::digest` (reference src/lib.rs:71-349) together with `sha256_compression`
+ * (src/compression.rs:19-213) and `SpreadConfig::{spread,spread_limb,decompose_even_and_odd_unchecked}`
+ * (src/spread.rs:76-233).  The reference has no FFI of its own: its boundary is the Rust API
+ *   configure(meta, max_variable_byte_sizes, range, num_bits_lookup, num_advice_columns, is_input_range_check)  lib.rs:49-56
+ *   digest(&mut self, ctx, input: &[u8], precomputed_input_len: Option<usize>) -> AssignedHashResult           lib.rs:71-76
+ *   new_context / range / load                                                                                  lib.rs:351-368
+ * Each entry point below names the reference item it replaces.  INTEGRATION.md shows the Rust binding.
+ *
+ * Model: one *instance* = one halo2 region / `Context` in which `n_digests` digest() calls are made in
+ * order (the reference's tests use 2, its bench 1).  For a given configuration every instance has the
+ * same shape; the engine produces, for a batch of instances, every advice cell as BN254 Fr in
+ * Montgomery form (4 x u64 little-endian limbs = halo2curves bn256::Fr memory layout), column-major:
+ *
+ *   gate   [instance][n_gate_cols  ][gate_col_rows  ]  FlexGate advice columns (halo2-base, Vertical)
+ *   lookup [instance][n_lookup_cols][lookup_col_rows]  range-lookup advice column(s) filled by range.finalize
+ *   spread [instance][2*num_advice_columns][spread_rows]  SpreadConfig denses[0..], then spreads[0..]
+ *
+ * Cells the reference never assigns are NOT written (zero the buffers once; the shape is static, so they
+ * stay zero across reuse).  All pointers are plain C; no C++ or torch types cross this boundary.
+ * Every call returns 0 on success or a negative H2SHA_E* code; h2sha_last_error() gives the message
+ * (thread-local).  The engine never falls back to the CPU: without a CUDA device every call fails.
+ */
+#ifndef H2SHA_B200_H
+#define H2SHA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2SHA_OK 0
+#define H2SHA_EINVAL (-1)      /* bad argument / configuration the reference would reject (lib.rs:57-59, spread.rs:37) */
+#define H2SHA_EPANIC (-2)      /* input the reference would panic on (lib.rs:89-90: bad precomputed length, message too long) */
+#define H2SHA_ECUDA (-3)       /* CUDA runtime error (no device, launch failure, out of memory) */
+#define H2SHA_ENOMEM (-4)
+
+typedef struct h2sha_engine h2sha_engine_t;
+
+/* Replaces the arguments of Sha256DynamicConfig::configure (lib.rs:49-56), RangeConfig::configure
+ * (lib.rs:409-418: lookup_bits, k) and ContextParams.max_rows (lib.rs:354-358). */
+typedef struct {
+  uint32_t n_digests;                       /* max_variable_byte_sizes.len()                                   */
+  const uint32_t* max_variable_byte_sizes;  /* each a positive multiple of 64 (lib.rs:57-59)                    */
+  uint32_t max_rows;                        /* range.gate.max_rows = 2^k - minimum_rows; 0 -> 2^17 - 9          */
+  uint32_t lookup_bits;                     /* RangeConfig lookup_bits; 0 -> 16                                 */
+  uint32_t num_bits_lookup;                 /* SpreadConfig limb bits, divides 16, <= 8; 0 -> 8                 */
+  uint32_t num_advice_columns;              /* SpreadConfig column pairs; 0 -> 2                                */
+  uint32_t is_input_range_check;            /* lib.rs:55,174-178                                                */
+  uint32_t gate_col_rows;                   /* row stride of a gate column in the output; 0 -> tight            */
+  uint32_t lookup_col_rows;                 /* 0 -> tight                                                       */
+  uint32_t spread_rows;                     /* 0 -> tight                                                       */
+  int32_t device;                           /* CUDA device ordinal; -1 = plan-only (host queries, no witness)   */
+  uint32_t build_shape;                     /* also build selectors / copy constraints / fixed column (host)    */
+} h2sha_config_t;
+
+typedef struct {
+  uint32_t n_digests;
+  uint32_t n_gate_cells, n_lookup_cells, n_spread_limbs;   /* stream lengths per instance                    */
+  uint32_t n_gate_cols, gate_col_rows;
+  uint32_t n_lookup_cols, lookup_col_rows;
+  uint32_t n_spread_cols, spread_rows;                     /* n_spread_cols = 2 * num_advice_columns          */
+  uint32_t n_blocks;                                       /* sha256_compression calls per instance           */
+  uint32_t n_fixed, n_copies, n_selectors_on;              /* shape sizes (0 unless build_shape)              */
+  uint64_t cells_per_instance;                             /* assigned Fr per instance over all three buffers */
+  uint64_t gate_bytes, lookup_bytes, spread_bytes;         /* buffer bytes per instance                       */
+} h2sha_layout_t;
+
+/* Sha256DynamicConfig::configure + new_context (lib.rs:49-69, 351-360): builds the static plan and uploads it. */
+int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out);
+void h2sha_destroy(h2sha_engine_t* e);
+const char* h2sha_last_error(void);
+int h2sha_get_layout(const h2sha_engine_t* e, h2sha_layout_t* out);
+
+/* Gate-stream index -> (column,row): column c holds stream indices [breaks[c], breaks[c+1]).  `breaks` gets n_gate_cols entries. */
+int h2sha_get_breaks(const h2sha_engine_t* e, uint32_t* breaks);
+/* AssignedHashResult (lib.rs:31-36, 342-346) of digest d as gate-stream indices:
+ * input_len (1), input_bytes (max_variable_byte_sizes[d]), output_bytes (32). */
+int h2sha_get_handles(const h2sha_engine_t* e, uint32_t d, uint32_t* input_len_idx, uint32_t* input_bytes_idx, uint32_t* output_bytes_idx);
+
+/* Shape (needs build_shape): what keygen needs and what MockProver checks.
+ *   selectors  [n_gate_cells] u8        gate selector per gate-stream index (q * (a + b*c - d) = 0 over 4 rows)
+ *   copies     [n_copies][4] u32        (a_kind,a_idx,b_kind,b_idx); kind 0 = gate stream, 1 = fixed column cell
+ *   fixed      [n_fixed][4] u64         canonical (non-Montgomery) constants, first-use order (Context::assign_fixed)
+ *   lookup_src [n_lookup_cells] u32     gate-stream index each lookup-column cell copies (range.finalize, lib.rs:469)
+ *   limb_dense_src / limb_spread_src [n_spread_limbs] u32   gate cells the spread-column cells are copy-constrained to (spread.rs:209-227)
+ * Any pointer may be NULL. */
+int h2sha_get_shape(const h2sha_engine_t* e, uint8_t* selectors, uint32_t* copies, uint64_t* fixed, uint32_t* lookup_src,
+                    uint32_t* limb_dense_src, uint32_t* limb_spread_src);
+
+/* One batch = n_instances instances; message m = instance * n_digests + d. */
+typedef struct {
+  uint64_t n_instances;
+  const uint8_t* msgs;               /* packed message bytes                                                     */
+  int32_t msgs_on_device;            /* 0: `msgs` is host memory (copied H2D on `stream`), 1: device memory       */
+  uint64_t msgs_bytes;               /* total bytes in `msgs`                                                     */
+  const uint64_t* offsets;           /* host, [n_msgs]: byte offset of message m in `msgs`                        */
+  const uint32_t* lens;              /* host, [n_msgs]: input.len()                                               */
+  const uint32_t* precomputed_lens;  /* host, [n_msgs] or NULL (= None): precomputed_input_len (lib.rs:75,88)     */
+  void* gate;                        /* device, n_instances * gate_bytes, or NULL to skip                         */
+  void* lookup;                      /* device, n_instances * lookup_bytes, or NULL                               */
+  void* spread;                      /* device, n_instances * spread_bytes, or NULL                               */
+  uint8_t* digests_dev;              /* device [n_msgs][32] or NULL                                               */
+  uint64_t* checksums_dev;           /* device [n_instances][4] or NULL: gate, lookup, spread, total              */
+  uint8_t* digests_host;             /* host [n_msgs][32] or NULL: copied D2H on `stream`                         */
+  uint64_t* checksums_host;          /* host [n_instances][4] or NULL                                             */
+  void* stream;                      /* cudaStream_t (NULL = default stream); the call only enqueues              */
+} h2sha_batch_t;
+
+/* Replaces `digest` (lib.rs:71-349) for a whole batch: padding and length selection, the precomputed
+ * prefix state (sha2::compress256, lib.rs:153-160), every compression and every cell.  Asynchronous on
+ * batch->stream; host arrays `offsets/lens/precomputed_lens` are consumed before the call returns. */
+int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* batch);
+
+/* Zero-fill output buffers (or just the never-assigned ranges when only_unassigned != 0). */
+int h2sha_zero_outputs(h2sha_engine_t* e, uint64_t n_instances, void* gate, void* lookup, void* spread, int only_unassigned, void* stream);
+
+/* Checksum definition (so a consumer can re-verify): for every assigned cell at position `pos` (Fr index inside the
+ * instance's buffer of that kind) with 32-bit limbs x[0..8):  h = sum_k x[k] * H2SHA_CK_M[k] mod 2^32;
+ * checksum += (u64)h * (u32)(2*pos+1)  mod 2^64. */
+extern const uint32_t H2SHA_CK_M[8];
+
+/* Test hook: Montgomery form of n raw u64 values (device pointers), through the same device function the
+ * expansion kernel uses.  out: [n][4] u64. */
+int h2sha_debug_mont_from_u64(h2sha_engine_t* e, const uint64_t* vals_dev, uint64_t* out_dev, uint64_t n, void* stream);
+
+/* Kernel launch statistics of the last h2sha_digest_batch (for bench.py's gpu_launches). */
+int h2sha_last_launch_count(const h2sha_engine_t* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2SHA_B200_H */
