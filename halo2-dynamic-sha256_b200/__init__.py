@@ -29,7 +29,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape",
-    "h2sha_digest_batch", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_last_launch_count", "H2SHA_CK_M",
+    "h2sha_digest_batch", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
 
@@ -62,7 +62,7 @@ class _Batch(C.Structure):
     _fields_ = [("n_instances", C.c_uint64), ("msgs", C.c_void_p), ("msgs_on_device", C.c_int32), ("msgs_bytes", C.c_uint64),
                 ("offsets", C.c_void_p), ("lens", C.c_void_p), ("precomputed_lens", C.c_void_p), ("gate", C.c_void_p), ("lookup", C.c_void_p),
                 ("spread", C.c_void_p), ("digests_dev", C.c_void_p), ("checksums_dev", C.c_void_p), ("digests_host", C.c_void_p),
-                ("checksums_host", C.c_void_p), ("stream", C.c_void_p)]
+                ("checksums_host", C.c_void_p), ("stream", C.c_void_p), ("reuse_inputs", C.c_int32), ("time_kernels", C.c_int32)]
 
 
 _lib = None
@@ -88,6 +88,7 @@ def load_library():
     L.h2sha_zero_outputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.h2sha_debug_mont_from_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.h2sha_last_launch_count.argtypes = [C.c_void_p]
+    L.h2sha_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -250,20 +251,32 @@ class Sha256DynamicConfig:
     def digest_batch_raw(self, n_instances: int, msgs_ptr: int, msgs_on_device: bool, msgs_bytes: int, offsets: np.ndarray, lens: np.ndarray,
                          precomputed_lens: Optional[np.ndarray], *, gate_ptr: int = 0, lookup_ptr: int = 0, spread_ptr: int = 0,
                          digests_dev_ptr: int = 0, checksums_dev_ptr: int = 0, digests_host_ptr: int = 0, checksums_host_ptr: int = 0,
-                         stream: int = 0):
+                         stream: int = 0, reuse_inputs: bool = False, time_kernels: bool = False):
         """Thin wrapper over h2sha_digest_batch (all pointers are integers)."""
-        assert offsets.dtype == np.uint64 and lens.dtype == np.uint32
-        b = _Batch(n_instances, msgs_ptr, 1 if msgs_on_device else 0, msgs_bytes, offsets.ctypes.data, lens.ctypes.data,
-                   precomputed_lens.ctypes.data if precomputed_lens is not None else None, gate_ptr or None, lookup_ptr or None,
-                   spread_ptr or None, digests_dev_ptr or None, checksums_dev_ptr or None, digests_host_ptr or None,
-                   checksums_host_ptr or None, stream or None)
+        if reuse_inputs:
+            off_p = len_p = pre_p = None
+        else:
+            assert offsets.dtype == np.uint64 and lens.dtype == np.uint32
+            off_p, len_p = offsets.ctypes.data, lens.ctypes.data
+            pre_p = precomputed_lens.ctypes.data if precomputed_lens is not None else None
+        b = _Batch(n_instances, msgs_ptr or None, 1 if msgs_on_device else 0, msgs_bytes, off_p, len_p, pre_p, gate_ptr or None,
+                   lookup_ptr or None, spread_ptr or None, digests_dev_ptr or None, checksums_dev_ptr or None, digests_host_ptr or None,
+                   checksums_host_ptr or None, stream or None, 1 if reuse_inputs else 0, 1 if time_kernels else 0)
         _check(load_library().h2sha_digest_batch(self._h, C.byref(b)))
+
+    def last_kernel_ms(self) -> Tuple[float, float]:
+        """(k_trace ms, k_expand ms) of the last batch run with time_kernels=True."""
+        a, b = C.c_float(), C.c_float()
+        _check(load_library().h2sha_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     def digest_batch(self, instances: Sequence[Sequence[bytes]], precomputed_input_lens: Optional[Sequence[Sequence[int]]] = None, *,
                      want_cells: bool = True, outputs=None) -> BatchResult:
         """digest() (lib.rs:71-349) for every message of every instance.  instances[i][d] is the input of the d-th
         digest call of instance i; precomputed_input_lens[i][d] its `precomputed_input_len` (None = no prefix)."""
         import torch
+        if self.device < 0:
+            raise EngineError(H2SHA_ECUDA, "plan-only engine (device=-1): witness generation needs a CUDA device; there is no CPU path")
         D = len(self.max_variable_byte_sizes)
         n = len(instances)
         for inst in instances:

@@ -608,6 +608,11 @@ struct h2sha_engine {
   uint32_t blocks_per_inst = 0, dtrace_words_per_inst = 0;
   int last_launches = 0;
   int expand_ctas = 0;
+  uint64_t resident_instances = 0;   // instances whose inputs are in the workspace (reuse_inputs)
+  bool resident_has_pre = false;
+  const uint8_t* resident_msgs = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // trace start/stop, expand start/stop
+  bool timed = false;
 };
 
 namespace {
@@ -826,51 +831,65 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   if (!e || !b) return set_err(H2SHA_EINVAL, "null argument");
   if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine (device = -1): witness generation needs a CUDA device; there is no CPU path");
   if (b->n_instances == 0) return H2SHA_OK;
-  if (!b->msgs && b->msgs_bytes) return set_err(H2SHA_EINVAL, "msgs is null");
-  if (!b->offsets || !b->lens) return set_err(H2SHA_EINVAL, "offsets / lens are null");
   const Plan& P = e->plan;
   const uint32_t D = (uint32_t)P.digests.size();
   const uint64_t n_msgs = b->n_instances * D;
   if (n_msgs * (uint64_t)1 > 0xffffffffull) return set_err(H2SHA_EINVAL, "batch too large");
-  // the reference's panics (lib.rs:89-90) become error returns
-  for (uint64_t m = 0; m < n_msgs; m++) {
-    const uint32_t maxb = P.digests[m % D].max_bytes;
-    const uint64_t len = b->lens[m], pre = b->precomputed_lens ? b->precomputed_lens[m] : 0;
-    if (pre % 64 != 0) return set_err(H2SHA_EPANIC, "precomputed_input_len is not a multiple of 64 (lib.rs:89), message " + std::to_string(m));
-    const uint64_t padded = (len + 9 + 63) / 64 * 64;
-    if (padded < pre || padded - pre > maxb)
-      return set_err(H2SHA_EPANIC, "padded input does not fit max_variable_byte_size (lib.rs:90), message " + std::to_string(m));
-    if (b->offsets[m] + len > b->msgs_bytes) return set_err(H2SHA_EINVAL, "message " + std::to_string(m) + " exceeds msgs_bytes");
-  }
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)b->stream;
-  int rc = ensure_workspace(e, b->n_instances, b->msgs_on_device ? 0 : b->msgs_bytes);
-  if (rc) return rc;
-  const uint8_t* d_msgs = b->msgs;
-  if (!b->msgs_on_device) {
-    if (b->msgs_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_msgs, b->msgs, b->msgs_bytes, cudaMemcpyHostToDevice, st));
-    d_msgs = e->d_msgs;
+  const uint8_t* d_msgs = nullptr;
+  bool has_pre = false;
+  cudaEvent_t copied = nullptr;
+  if (b->reuse_inputs) {
+    if (b->n_instances > e->resident_instances) return set_err(H2SHA_EINVAL, "reuse_inputs: no resident inputs for that many instances");
+    d_msgs = e->resident_msgs; has_pre = e->resident_has_pre;
+  } else {
+    if (!b->msgs && b->msgs_bytes) return set_err(H2SHA_EINVAL, "msgs is null");
+    if (!b->offsets || !b->lens) return set_err(H2SHA_EINVAL, "offsets / lens are null");
+    // the reference's panics (lib.rs:89-90) become error returns
+    for (uint64_t m = 0; m < n_msgs; m++) {
+      const uint32_t maxb = P.digests[m % D].max_bytes;
+      const uint64_t len = b->lens[m], pre = b->precomputed_lens ? b->precomputed_lens[m] : 0;
+      if (pre % 64 != 0) return set_err(H2SHA_EPANIC, "precomputed_input_len is not a multiple of 64 (lib.rs:89), message " + std::to_string(m));
+      const uint64_t padded = (len + 9 + 63) / 64 * 64;
+      if (padded < pre || padded - pre > maxb)
+        return set_err(H2SHA_EPANIC, "padded input does not fit max_variable_byte_size (lib.rs:90), message " + std::to_string(m));
+      if (b->offsets[m] + len > b->msgs_bytes) return set_err(H2SHA_EINVAL, "message " + std::to_string(m) + " exceeds msgs_bytes");
+    }
+    e->resident_instances = 0;
+    int rc = ensure_workspace(e, b->n_instances, b->msgs_on_device ? 0 : b->msgs_bytes);
+    if (rc) return rc;
+    d_msgs = b->msgs;
+    if (!b->msgs_on_device) {
+      if (b->msgs_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_msgs, b->msgs, b->msgs_bytes, cudaMemcpyHostToDevice, st));
+      d_msgs = e->d_msgs;
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->d_offsets, b->offsets, n_msgs * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_lens, b->lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
+    if (b->precomputed_lens) CUDA_TRY(cudaMemcpyAsync(e->d_pre, b->precomputed_lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
+    has_pre = b->precomputed_lens != nullptr;
+    // host arrays must be consumed before we return: wait for the copies (not for the kernels) below
+    CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(copied, st));
+    e->resident_instances = b->n_instances; e->resident_has_pre = has_pre; e->resident_msgs = d_msgs;
   }
-  CUDA_TRY(cudaMemcpyAsync(e->d_offsets, b->offsets, n_msgs * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(e->d_lens, b->lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
-  if (b->precomputed_lens) CUDA_TRY(cudaMemcpyAsync(e->d_pre, b->precomputed_lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
-  // host arrays must be consumed before we return (pageable memory is staged synchronously by the runtime;
-  // for pinned memory we wait for the copies explicitly)
-  cudaEvent_t copied;
-  CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventRecord(copied, st));
+  e->timed = b->time_kernels != 0;
+  if (e->timed && !e->ev[0])
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&e->ev[i]));
 
   uint8_t* dig_dev = b->digests_dev ? b->digests_dev : (b->digests_host ? e->d_digests_out : nullptr);
   unsigned long long* cks_dev = b->checksums_dev ? (unsigned long long*)b->checksums_dev : (b->checksums_host ? e->d_cks : nullptr);
   int launches = 0;
   TraceArgs ta{};
   ta.n_msgs = n_msgs; ta.n_digests = D; ta.msgs = d_msgs; ta.offsets = e->d_offsets; ta.lens = e->d_lens;
-  ta.pre_lens = b->precomputed_lens ? e->d_pre : nullptr;
+  ta.pre_lens = has_pre ? e->d_pre : nullptr;
   ta.btrace = e->d_btrace; ta.dtrace = e->d_dtrace; ta.digests = dig_dev; ta.digests_plan = e->d_digests;
   ta.blocks_per_inst = e->blocks_per_inst; ta.dtrace_words_per_inst = e->dtrace_words_per_inst;
+  if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[0], st));
   k_trace<<<(unsigned)((n_msgs + 127) / 128), 128, 0, st>>>(ta);
   launches++;
   CUDA_TRY(cudaGetLastError());
+  if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[1], st));
   if (b->gate || b->lookup || b->spread || cks_dev) {
     CUDA_TRY(cudaMemsetAsync(e->d_counter, 0, 8, st));
     if (cks_dev) CUDA_TRY(cudaMemsetAsync(cks_dev, 0, b->n_instances * 32, st));
@@ -880,15 +899,19 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     ja.cks = cks_dev; ja.job_counter = e->d_counter;
     uint64_t n_jobs = b->n_instances * (uint64_t)(e->blocks_per_inst + D);
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
+    if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     k_expand<EXPAND_THREADS><<<grid, EXPAND_THREADS, e->dplan.smem_bytes, st>>>(e->dplan, ja);
     launches++;
     CUDA_TRY(cudaGetLastError());
+    if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[3], st));
   }
   if (b->digests_host) CUDA_TRY(cudaMemcpyAsync(b->digests_host, dig_dev, n_msgs * 32, cudaMemcpyDeviceToHost, st));
   if (b->checksums_host) CUDA_TRY(cudaMemcpyAsync(b->checksums_host, cks_dev, b->n_instances * 32, cudaMemcpyDeviceToHost, st));
   e->last_launches = launches;
-  CUDA_TRY(cudaEventSynchronize(copied));
-  cudaEventDestroy(copied);
+  if (copied) {
+    CUDA_TRY(cudaEventSynchronize(copied));
+    cudaEventDestroy(copied);
+  }
   return H2SHA_OK;
 }
 
@@ -921,5 +944,13 @@ int h2sha_debug_mont_from_u64(h2sha_engine_t* e, const uint64_t* vals_dev, uint6
 }
 
 int h2sha_last_launch_count(const h2sha_engine_t* e) { return e ? e->last_launches : 0; }
+
+int h2sha_last_kernel_ms(h2sha_engine_t* e, float* trace_ms, float* expand_ms) {
+  if (!e || !e->timed || !e->ev[0]) return set_err(H2SHA_EINVAL, "last batch was not run with time_kernels");
+  CUDA_TRY(cudaEventSynchronize(e->ev[3]));
+  if (trace_ms) CUDA_TRY(cudaEventElapsedTime(trace_ms, e->ev[0], e->ev[1]));
+  if (expand_ms) CUDA_TRY(cudaEventElapsedTime(expand_ms, e->ev[2], e->ev[3]));
+  return H2SHA_OK;
+}
 
 }  // extern "C"

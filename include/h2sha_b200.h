@@ -110,6 +110,10 @@ typedef struct {
   uint8_t* digests_host;             /* host [n_msgs][32] or NULL: copied D2H on `stream`                         */
   uint64_t* checksums_host;          /* host [n_instances][4] or NULL                                             */
   void* stream;                      /* cudaStream_t (NULL = default stream); the call only enqueues              */
+  int32_t reuse_inputs;              /* 1: messages / offsets / lens uploaded by the previous call on this engine are
+                                        still resident in HBM and are reused (no validation, no H2D); n_instances
+                                        must not exceed that call's                                                */
+  int32_t time_kernels;              /* 1: bracket each kernel with CUDA events on `stream` (h2sha_last_kernel_ms) */
 } h2sha_batch_t;
 
 /* Replaces `digest` (lib.rs:71-349) for a whole batch: padding and length selection, the precomputed
@@ -131,6 +135,8 @@ int h2sha_debug_mont_from_u64(h2sha_engine_t* e, const uint64_t* vals_dev, uint6
 
 /* Kernel launch statistics of the last h2sha_digest_batch (for bench.py's gpu_launches). */
 int h2sha_last_launch_count(const h2sha_engine_t* e);
+/* Device time of the two kernels of the last batch run with time_kernels = 1; synchronises on the recorded events. */
+int h2sha_last_kernel_ms(h2sha_engine_t* e, float* trace_ms, float* expand_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,227 @@
+"""Parity tests proper (need a B200): the CUDA path, called through the C-ABI, against the oracle on the same inputs --
+bit-exact for every advice, lookup and spread-column cell, the digests and the checksums -- plus a MockProver-style
+pass over the GPU output using the product's own shape plan, and size-independent properties at BASELINE sizes."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mock_prover as MP
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+P = O.P
+NCPU = os.cpu_count() or 1
+
+
+def _u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def _oracle_cfg(kw):
+    return O.OracleConfig(**kw)
+
+
+def _engine(pkg, kw, **extra):
+    return pkg.Sha256DynamicConfig.configure(list(kw["max_variable_byte_sizes"]), max_rows=kw.get("max_rows", (1 << 17) - 9),
+                                             lookup_bits=kw.get("lookup_bits", 16), num_bits_lookup=kw.get("limb_bits", 8),
+                                             num_advice_columns=kw.get("spread_cols", 2),
+                                             is_input_range_check=kw.get("is_input_range_check", True), device=0, **extra)
+
+
+def _compare(pkg, kw, instances, pre=None, threads=NCPU):
+    cfg = _engine(pkg, kw)
+    lay = cfg.layout
+    res = cfg.digest_batch(instances, pre)
+    olay = O.Layout(lay.n_gate_cols, lay.gate_col_rows, lay.n_lookup_cols, lay.lookup_col_rows, lay.spread_rows)
+    ref = O.batch(_oracle_cfg(kw), olay, instances, pre, want_cells=True, n_threads=min(threads, len(instances)))
+    assert (res.digests == ref["digests"]).all(), "digests differ"
+    for name in ("gate", "lookup", "spread"):
+        got = _u64(getattr(res, name))
+        bad = np.argwhere((got != ref[name]).any(axis=-1))
+        assert bad.size == 0, f"{name}: {len(bad)} cells differ, first at (instance, column, row) = {bad[0]}"
+    assert (res.checksums == ref["checksums"]).all(), "checksums differ"
+    cfg.close()
+    return res, ref
+
+
+def test_montgomery_conversion_matches_python_ints(pkg):
+    """Device Barrett conversion v -> v * 2^256 mod p, against Python big ints: edge values and 2^20 random ones."""
+    cfg = _engine(pkg, dict(max_variable_byte_sizes=(64,)))
+    rng = np.random.default_rng(1)
+    edge = [0, 1, 2, 255, 256, 0xFFFF, 0x10000, 0x55555555, 0xAAAAAAAA, 0xFFFFFFFF, 1 << 32, (1 << 35) - 1, 0x5555555555555555,
+            0xAAAAAAAAAAAAAAAA, (1 << 63) - 1, 1 << 63, (1 << 64) - 1, (1 << 64) - 2]
+    edge += [(1 << k) for k in range(64)] + [(1 << k) - 1 for k in range(1, 65)]
+    vals = np.concatenate([np.array(edge, dtype=np.uint64), rng.integers(0, 1 << 63, size=1 << 20, dtype=np.uint64) * np.uint64(2) + np.uint64(1),
+                           rng.integers(0, 1 << 32, size=1 << 16, dtype=np.uint64), rng.integers(0, 1 << 16, size=1 << 12, dtype=np.uint64)])
+    out = cfg.mont_from_u64(vals)
+    R = (1 << 256) % P
+    idx = list(range(len(edge))) + list(rng.integers(0, len(vals), size=20000))
+    for i in idx:
+        got = sum(int(out[i, k]) << (64 * k) for k in range(4))
+        assert got == int(vals[i]) * R % P, f"value {int(vals[i]):#x}"
+    # all results are canonical (< p): compare the top limb cheaply for the whole batch
+    assert (out[:, 3] <= np.uint64(P >> 192)).all()
+    cfg.close()
+
+
+def test_reference_test_vectors_two_digests_per_context(pkg):
+    """The reference's TestCircuit (lib.rs:400-494): two digest() calls in one Context, max 128 each, k = 17."""
+    kw = dict(max_variable_byte_sizes=(128, 128))
+    instances = [[b"abc", b""], [b"\x00", b""], [b"\x01" * 56, b"\x00\x00\x00"]]
+    res, _ = _compare(pkg, kw, instances)
+    exp = ["ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad", "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855",
+           "6e340b9cffb37a989ca544e6bb780a2c78901d3fb33738768511a30617afa01d", "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855",
+           "51e14a913680f24c85fe3b0e2e5b57f7202f117bb214f8ffdd4ea0f4e921fd52", "709e80c88487a2411e1ee4dfb9f22a861492d20c4765150c0c794abd70f8147c"]
+    assert [bytes(d).hex() for d in res.digests] == exp
+
+
+def test_mock_prover_on_gpu_output(pkg):
+    """MockProver pass on sampled instances: the GPU cells satisfy every gate, copy and lookup constraint of the
+    product's own shape plan and the output-byte cells equal the digests (lib.rs:480-482, 525-526)."""
+    kw = dict(max_variable_byte_sizes=(128, 128))
+    cfg = _engine(pkg, kw, build_shape=True)
+    rng = np.random.default_rng(5)
+    instances = [[b"abc", b""], [bytes(rng.integers(0, 256, 119, dtype=np.uint8)), bytes(rng.integers(0, 256, 64, dtype=np.uint8))]]
+    res = cfg.digest_batch(instances)
+    lay, sh, brk = cfg.layout, cfg.shape(), cfg.breaks()
+    gate = _u64(res.gate); lookup = _u64(res.lookup); spread = _u64(res.spread)
+    ends = list(brk[1:]) + [lay.n_gate_cells]
+    for i, inst in enumerate(instances):
+        stream = np.concatenate([gate[i, c, : int(e) - int(s)] for c, (s, e) in enumerate(zip(brk, ends))])
+        # the lookup column must hold copies of the looked-up gate cells, in push order (range.finalize)
+        lk = np.concatenate([lookup[i, c] for c in range(lay.n_lookup_cols)])[: lay.n_lookup_cells]
+        assert (lk == stream[sh.lookup_src]).all()
+        nc = lay.n_spread_cols // 2
+        n = np.arange(lay.n_spread_limbs)
+        dense = spread[i, n % nc, n // nc]
+        spr = spread[i, nc + n % nc, n // nc]
+        consts_mont = np.array([O.int_to_mont(int(a) | int(b) << 64 | int(c) << 128 | int(d) << 192) for a, b, c, d in sh.fixed], dtype=np.uint64)
+        stats = MP.verify(gate=stream, selectors=sh.selectors, breaks=brk, lookup_idx=sh.lookup_src, dense=dense, spread=spr,
+                          limb_gate_dense=sh.limb_dense_src, limb_gate_spread=sh.limb_spread_src, copies=sh.copies, consts=consts_mont,
+                          lookup_bits=16, limb_bits=8, max_rows=(1 << 17) - 9,
+                          output_bytes_idx=[cfg.handles(d).output_bytes for d in range(2)],
+                          expected_digests=[hashlib.sha256(m).digest() for m in inst])
+        assert stats["gates"] == lay.n_selectors_on
+    cfg.close()
+
+
+def test_config2_1024_one_block_messages_bit_exact(pkg):
+    """BASELINE configs[1]: 1024 random 55-byte messages, one block each, every cell compared with the oracle."""
+    import __graft_entry__ as ge
+    S = ge.load_package_module("synthetic")
+    w = S.WORKLOADS["cfg2"]
+    blob, offs, lens = S.generate(w, 0, w.n_instances)
+    instances = [[bytes(blob[int(o):int(o) + int(l)])] for o, l in zip(offs, lens)]
+    _compare(pkg, dict(max_variable_byte_sizes=w.max_variable_byte_sizes), instances)
+
+
+def test_config1_single_message(pkg):
+    """BASELINE configs[0]: one 64-byte message, max input 128 bytes; plus the bench's own [0x01;56] with max 1024."""
+    _compare(pkg, dict(max_variable_byte_sizes=(128,)), [[bytes(range(64))]])
+    res, _ = _compare(pkg, dict(max_variable_byte_sizes=(1024,)), [[b"\x01" * 56]])
+    assert bytes(res.digests[0]).hex() == "51e14a913680f24c85fe3b0e2e5b57f7202f117bb214f8ffdd4ea0f4e921fd52"
+
+
+def test_config3_dynamic_lengths_with_edges(pkg):
+    """BASELINE configs[2] shape (max 1088 = 17 blocks): edge lengths 0, 55, 56, 63, 64, 119, 120, max-9 and random ones."""
+    rng = np.random.default_rng(3)
+    lens = [0, 1, 55, 56, 63, 64, 119, 120, 1023, 1024, 1079] + [int(x) for x in rng.integers(0, 1025, size=13)]
+    instances = [[bytes(rng.integers(0, 256, n, dtype=np.uint8))] for n in lens]
+    res, _ = _compare(pkg, dict(max_variable_byte_sizes=(1088,)), instances)
+    for inst, d in zip(instances, res.digests):
+        assert hashlib.sha256(inst[0]).digest() == bytes(d)
+
+
+def test_precomputed_prefix(pkg):
+    """test_sha256_correct4 (lib.rs:587-611): 192 bytes with precomputed_input_len = 128, and a target_round == 0 corner."""
+    rng = np.random.default_rng(9)
+    kw = dict(max_variable_byte_sizes=(128, 128))
+    instances = [[bytes(rng.integers(0, 256, 192, dtype=np.uint8)) for _ in range(2)] for _ in range(3)]
+    pre = [[128, 128], [128, 64], [64, 128]]
+    res, _ = _compare(pkg, kw, instances, pre)
+    for inst, ds in zip(instances, res.digests.reshape(3, 2, 32)):
+        assert [hashlib.sha256(m).digest() for m in inst] == [bytes(x) for x in ds]
+    # everything inside the prefix: padded size == precomputed length, so the selected round is 0
+    _compare(pkg, dict(max_variable_byte_sizes=(64,)), [[b"q" * 50]], [[64]])
+
+
+@pytest.mark.parametrize("kw", [dict(max_variable_byte_sizes=(128,), max_rows=4099), dict(max_variable_byte_sizes=(64,), lookup_bits=8),
+                                dict(max_variable_byte_sizes=(64,), lookup_bits=12), dict(max_variable_byte_sizes=(64,), limb_bits=4),
+                                dict(max_variable_byte_sizes=(64,), limb_bits=2, spread_cols=3), dict(max_variable_byte_sizes=(128,), spread_cols=1),
+                                dict(max_variable_byte_sizes=(128,), is_input_range_check=False), dict(max_variable_byte_sizes=(64, 192, 128))],
+                         ids=lambda kw: "-".join(f"{k}={v}" for k, v in kw.items() if k != "max_variable_byte_sizes") or "multi")
+def test_alternative_configurations(pkg, kw):
+    rng = np.random.default_rng(11)
+    D = len(kw["max_variable_byte_sizes"])
+    instances = [[bytes(rng.integers(0, 256, int(rng.integers(0, m - 8)), dtype=np.uint8)) for m in kw["max_variable_byte_sizes"]] for _ in range(3)]
+    assert all(len(i) == D for i in instances)
+    _compare(pkg, kw, instances)
+
+
+def test_wider_strides_leave_unassigned_cells_untouched(pkg):
+    import torch
+    kw = dict(max_variable_byte_sizes=(64,))
+    cfg = _engine(pkg, kw, gate_col_rows=1 << 17, lookup_col_rows=4096, spread_rows=2100)
+    lay = cfg.layout
+    sentinel = -0x0123456789ABCDEF
+    outs = cfg.alloc_outputs(2, zero=False)
+    for t in outs:
+        t.fill_(sentinel)
+    res = cfg.digest_batch([[b"abc"], [b"abcd" * 13]], outputs=outs)
+    olay = O.Layout(lay.n_gate_cols, lay.gate_col_rows, lay.n_lookup_cols, lay.lookup_col_rows, lay.spread_rows)
+    ref = O.batch(_oracle_cfg(kw), olay, [[b"abc"], [b"abcd" * 13]], None, want_cells=True)
+    g = _u64(res.gate)
+    assert (g[:, :, : lay.n_gate_cells] == ref["gate"][:, :, : lay.n_gate_cells]).all()
+    assert (res.gate[:, :, lay.n_gate_cells:] == sentinel).all(), "cells beyond the assigned rows must not be written"
+    assert (res.lookup[:, :, lay.n_lookup_cells:] == sentinel).all()
+    assert (res.spread[:, :, lay.n_spread_limbs // 2:] == sentinel).all()
+    # zero-fill of just the never-assigned ranges
+    lib = pkg.load_library()
+    rc = lib.h2sha_zero_outputs(cfg._h, 2, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), 1, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert (_u64(res.gate) == ref["gate"]).all() and (_u64(res.lookup) == ref["lookup"]).all() and (_u64(res.spread) == ref["spread"]).all()
+    cfg.close()
+
+
+def test_reference_panics_are_errors(pkg):
+    cfg = _engine(pkg, dict(max_variable_byte_sizes=(128,)))
+    with pytest.raises(pkg.ReferencePanic):   # lib.rs:89
+        cfg.digest_batch([[b"abc"]], [[32]])
+    with pytest.raises(pkg.ReferencePanic):   # lib.rs:90
+        cfg.digest_batch([[b"a" * 120]])
+    cfg.digest_batch([[b"a" * 119]])
+    with pytest.raises(pkg.EngineError):
+        cfg.digest_batch([[b"a", b"b"]])
+    cfg.close()
+
+
+def test_config4_sample_properties_at_full_shape(pkg):
+    """BASELINE configs[3] shape (256-byte messages, max 320, 5 blocks): 512 instances from the synthetic stream --
+    all digests against hashlib, checksum-of-checksums against the oracle on a 32-instance sample, idempotence."""
+    import __graft_entry__ as ge
+    S = ge.load_package_module("synthetic")
+    w = S.WORKLOADS["cfg4"]
+    n = 512
+    blob, offs, lens = S.generate(w, 4096, n)
+    instances = [[bytes(blob[int(o):int(o) + int(l)])] for o, l in zip(offs, lens)]
+    cfg = _engine(pkg, dict(max_variable_byte_sizes=w.max_variable_byte_sizes))
+    lay = cfg.layout
+    assert lay.n_gate_cols == 3 and lay.cells_per_instance == 406958
+    outs = cfg.alloc_outputs(n)
+    res = cfg.digest_batch(instances, outputs=outs)
+    for inst, d in zip(instances, res.digests):
+        assert hashlib.sha256(inst[0]).digest() == bytes(d)
+    first = res.checksums.copy()
+    res2 = cfg.digest_batch(instances, outputs=outs)  # same buffers, same inputs: nothing may change
+    assert (res2.checksums == first).all()
+    olay = O.Layout(lay.n_gate_cols, lay.gate_col_rows, lay.n_lookup_cols, lay.lookup_col_rows, lay.spread_rows)
+    sample = list(range(0, n, 16))
+    ref = O.batch(_oracle_cfg(dict(max_variable_byte_sizes=w.max_variable_byte_sizes)), olay, [instances[i] for i in sample], None,
+                  want_cells=False, n_threads=NCPU)
+    assert (first[sample] == ref["checksums"]).all()
+    assert int(first[sample, 3].sum()) == int(ref["checksums"][:, 3].sum())
+    cfg.close()
