@@ -224,7 +224,9 @@ def main():
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     # per-kernel durations, measured live with CUDA events on the launching stream over the same step
-    for _ in range(args.steps):
+    # (the loop continues for >= 1 s so that the clock sampler sees the GPU under this same load)
+    t_loop = time.perf_counter()
+    while len(kernel_ms) < args.steps or time.perf_counter() - t_loop < 1.0:
         step_resident(timed=True)
         kernel_ms.append(cfg.last_kernel_ms())
     clocks = sampler.stop()

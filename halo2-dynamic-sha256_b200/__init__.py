@@ -47,7 +47,7 @@ class _Config(C.Structure):
     _fields_ = [("n_digests", C.c_uint32), ("max_variable_byte_sizes", C.POINTER(C.c_uint32)), ("max_rows", C.c_uint32),
                 ("lookup_bits", C.c_uint32), ("num_bits_lookup", C.c_uint32), ("num_advice_columns", C.c_uint32),
                 ("is_input_range_check", C.c_uint32), ("gate_col_rows", C.c_uint32), ("lookup_col_rows", C.c_uint32),
-                ("spread_rows", C.c_uint32), ("device", C.c_int32), ("build_shape", C.c_uint32)]
+                ("spread_rows", C.c_uint32), ("device", C.c_int32), ("build_shape", C.c_uint32), ("block_parts", C.c_uint32)]
 
 
 class _Layout(C.Structure):
@@ -178,11 +178,12 @@ class Sha256DynamicConfig:
     @classmethod
     def configure(cls, max_variable_byte_sizes: Sequence[int], *, max_rows: int = (1 << 17) - 9, lookup_bits: int = 16,
                   num_bits_lookup: int = 8, num_advice_columns: int = 2, is_input_range_check: bool = True, device: int = 0,
-                  build_shape: bool = False, gate_col_rows: int = 0, lookup_col_rows: int = 0, spread_rows: int = 0) -> "Sha256DynamicConfig":
+                  build_shape: bool = False, gate_col_rows: int = 0, lookup_col_rows: int = 0, spread_rows: int = 0,
+                  block_parts: int = 0) -> "Sha256DynamicConfig":
         L = load_library()
         sizes = (C.c_uint32 * len(max_variable_byte_sizes))(*max_variable_byte_sizes)
         cfg = _Config(len(max_variable_byte_sizes), sizes, max_rows, lookup_bits, num_bits_lookup, num_advice_columns,
-                      1 if is_input_range_check else 0, gate_col_rows, lookup_col_rows, spread_rows, device, 1 if build_shape else 0)
+                      1 if is_input_range_check else 0, gate_col_rows, lookup_col_rows, spread_rows, device, 1 if build_shape else 0, block_parts)
         h = C.c_void_p()
         _check(L.h2sha_create(C.byref(cfg), C.byref(h)))
         return cls(h, max_variable_byte_sizes, device)

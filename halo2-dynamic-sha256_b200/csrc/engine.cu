@@ -51,10 +51,11 @@ struct DevPlan {
   const uint8_t* blob;
   uint32_t blob_bytes;
   // byte offsets inside the blob (all 16-byte aligned)
-  uint32_t off_tmpl, off_table, off_prog, off_groups, off_tasks, off_types, off_classes, off_raw, off_breaks, off_digests;
-  uint32_t n_breaks, n_digests;
+  uint32_t off_fill, off_cells, off_chunks, off_items, off_table, off_table_h, off_prog, off_groups, off_tasks, off_types, off_classes,
+      off_raw, off_breaks, off_digests;
+  uint32_t n_breaks, n_digests, n_block_parts;
   // dynamic shared memory layout after the blob
-  uint32_t off_trace, off_slots, off_misc, smem_bytes;
+  uint32_t off_trace, off_slots, off_scratch, off_misc, smem_bytes;
   // layout
   uint32_t max_rows, spread_cols, n_gate_cols, gate_col_rows, n_lookup_cols, lookup_col_rows, spread_rows;
   uint32_t blocks_per_inst, dtrace_words_per_inst;
@@ -318,8 +319,12 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
 // ---------------------------------------------------------------------------------------------------
 struct Misc {
   unsigned long long ck[3];
-  uint32_t next_item;
   uint32_t job_lo, job_hi;
+};
+// per-warp scratch of phase 2: Montgomery values of the chunk's distinct non-constant cells + their checksum hashes
+struct WarpScratch {
+  uint32_t val[H2SHA_MAX_FILL][8];
+  uint32_t h[H2SHA_MAX_FILL];
 };
 
 __device__ __forceinline__ uint64_t vm_operand(uint32_t o, const uint64_t* slots, const uint64_t* raw) {
@@ -332,7 +337,7 @@ __device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitT
                                                  const uint32_t* trace, uint64_t* slots) {
   for (uint32_t k = 0; k < ut.n_in; k++) {
     int32_t base = g.in[k].base;
-    slots[k] = (base < 0) ? (uint64_t)u : (uint64_t)trace[base + g.in[k].stride * (int32_t)u];
+    slots[k] = (base < 0) ? (uint64_t)(g.in[k].stride + (int32_t)u) : (uint64_t)trace[base + g.in[k].stride * (int32_t)u];
   }
   const VmIns* ins = prog + ut.prog_off;
   for (uint32_t pc = 0; pc < ut.prog_len; pc++) {
@@ -359,15 +364,25 @@ __device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitT
   }
 }
 
-// Fr value of one template entry
-__device__ __forceinline__ void eval_entry(const TmplEntry e, const uint64_t* slots, const uint32_t* table, uint32_t x[8]) {
+// checksum hash of a cell: sum_k x[k] * M[k] mod 2^32
+__device__ __forceinline__ uint32_t cell_hash(const uint32_t x[8]) {
+  uint32_t h = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) h += x[k] * c_CKM[k];
+  return h;
+}
+
+// fill phase: Fr value (+ hash) of one distinct value of the chunk -> warp scratch
+__device__ __forceinline__ void fill_entry(const TmplEntry e, const uint64_t* slots, const uint32_t* table, const uint32_t* table_h,
+                                           uint32_t* out_val, uint32_t* out_h) {
   const uint32_t kind = H2SHA_TE_KIND(e);
-  uint64_t s = slots[H2SHA_TE_SLOT(e)];
+  const uint64_t s = slots[H2SHA_TE_SLOT(e)];
   if (kind == KIND_TABLE) {
-    uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
+    const uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
     const uint4* t = reinterpret_cast<const uint4*>(table + 8 * idx);
-    uint4 lo = t[0], hi = t[1];
-    x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+    uint4* o = reinterpret_cast<uint4*>(out_val);
+    o[0] = t[0]; o[1] = t[1];
+    *out_h = table_h[idx];
     return;
   }
   bool neg = H2SHA_TE_NEG(e);
@@ -382,8 +397,21 @@ __device__ __forceinline__ void eval_entry(const TmplEntry e, const uint64_t* sl
   uint64_t r[4];
   mont_from_u64(v, r);
   if (neg) fr_negate(r);
-  x[0] = (uint32_t)r[0]; x[1] = (uint32_t)(r[0] >> 32); x[2] = (uint32_t)r[1]; x[3] = (uint32_t)(r[1] >> 32);
-  x[4] = (uint32_t)r[2]; x[5] = (uint32_t)(r[2] >> 32); x[6] = (uint32_t)r[3]; x[7] = (uint32_t)(r[3] >> 32);
+  uint32_t x[8] = {(uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32),
+                   (uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32)};
+  uint4* o = reinterpret_cast<uint4*>(out_val);
+  o[0] = make_uint4(x[0], x[1], x[2], x[3]); o[1] = make_uint4(x[4], x[5], x[6], x[7]);
+  *out_h = cell_hash(x);
+}
+
+// copy phase: source of a cell (static constant or warp scratch) -> registers + hash
+__device__ __forceinline__ uint32_t load_cell(uint32_t src, const uint32_t* table, const uint32_t* table_h, const WarpScratch* ws, uint32_t x[8]) {
+  const bool dyn = (src & H2SHA_SCRATCH_FLAG) != 0;
+  const uint32_t idx = src & (H2SHA_SCRATCH_FLAG - 1);
+  const uint4* t = reinterpret_cast<const uint4*>(dyn ? &ws->val[idx][0] : table + 8 * idx);
+  uint4 lo = t[0], hi = t[1];
+  x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+  return dyn ? ws->h[idx] : table_h[idx];
 }
 
 template <int NT>
@@ -397,8 +425,12 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (uint32_t i = tid; i < P.blob_bytes / 16; i += NT) dst[i] = src[i];
   }
-  const TmplEntry* s_tmpl = reinterpret_cast<const TmplEntry*>(smem + P.off_tmpl);
+  const TmplEntry* s_fill = reinterpret_cast<const TmplEntry*>(smem + P.off_fill);
+  const CellEntry* s_cells = reinterpret_cast<const CellEntry*>(smem + P.off_cells);
+  const Chunk* s_chunks = reinterpret_cast<const Chunk*>(smem + P.off_chunks);
+  const uint32_t* s_items = reinterpret_cast<const uint32_t*>(smem + P.off_items);
   const uint32_t* s_table = reinterpret_cast<const uint32_t*>(smem + P.off_table);
+  const uint32_t* s_table_h = reinterpret_cast<const uint32_t*>(smem + P.off_table_h);
   const VmIns* s_prog = reinterpret_cast<const VmIns*>(smem + P.off_prog);
   const UnitGroup* s_groups = reinterpret_cast<const UnitGroup*>(smem + P.off_groups);
   const WarpTask* s_tasks = reinterpret_cast<const WarpTask*>(smem + P.off_tasks);
@@ -409,10 +441,11 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
   const DevDigest* s_digests = reinterpret_cast<const DevDigest*>(smem + P.off_digests);
   uint32_t* s_trace = reinterpret_cast<uint32_t*>(smem + P.off_trace);
   uint64_t* s_slots = reinterpret_cast<uint64_t*>(smem + P.off_slots);
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + P.off_scratch) + warp;
   Misc* s_misc = reinterpret_cast<Misc*>(smem + P.off_misc);
   for (int i = tid; i < 64; i += NT) s_trace[TR_K + i] = c_K[i];
 
-  const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst;
+  const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst * P.n_block_parts;
   const uint64_t n_jobs = n_block_jobs + A.n_inst * P.n_digests;
 
   for (;;) {
@@ -420,7 +453,7 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
     if (tid == 0) {
       unsigned long long j = atomicAdd(A.job_counter, 1ULL);
       s_misc->job_lo = (uint32_t)j; s_misc->job_hi = (uint32_t)(j >> 32);
-      s_misc->next_item = 0; s_misc->ck[0] = 0; s_misc->ck[1] = 0; s_misc->ck[2] = 0;
+      s_misc->ck[0] = 0; s_misc->ck[1] = 0; s_misc->ck[2] = 0;
     }
     __syncthreads();
     const uint64_t job = ((uint64_t)s_misc->job_hi << 32) | s_misc->job_lo;
@@ -428,17 +461,18 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
     // ---- decode job ----
     uint64_t inst; uint32_t cls, gate0, lk0, limb0; const uint32_t* tr_src; uint32_t tr_words;
     if (job < n_block_jobs) {
-      inst = job / P.blocks_per_inst;
-      uint32_t r = (uint32_t)(job - inst * P.blocks_per_inst);
+      const uint64_t blk = job / P.n_block_parts;          // global block index = inst * blocks_per_inst + r
+      cls = (uint32_t)(job - blk * P.n_block_parts);        // part of the block job
+      inst = blk / P.blocks_per_inst;
+      uint32_t r = (uint32_t)(blk - inst * P.blocks_per_inst);
       uint32_t d = 0;
       while (d + 1 < P.n_digests && r >= s_digests[d + 1].blk_prefix) d++;
       const DevDigest& dd = s_digests[d];
       uint32_t jb = r - dd.blk_prefix;
-      cls = 0;
       gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
       lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
       limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
-      tr_src = A.btrace + job * (uint64_t)TR_BLOCK_WORDS;
+      tr_src = A.btrace + blk * (uint64_t)TR_BLOCK_WORDS;
       tr_words = TR_BLOCK_WORDS;
     } else {
       uint64_t k = job - n_block_jobs;
@@ -462,82 +496,67 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
       if (u < g.count) run_unit_program(g, ut, u, s_prog, s_raw, s_trace, s_slots + g.slot_base + u * (ut.n_slots | 1u));
     }
     __syncthreads();
-    // ---- phase 2: template expansion, one warp per unit instance (dynamic) ----
+    // ---- phase 2: one warp per (unit instance, chunk); fill the distinct values, then copy the cells out ----
     unsigned long long ck_g = 0, ck_l = 0, ck_s = 0;
     uint32_t* gate_out = A.gate ? A.gate + inst * P.gate_inst_cells * 8 : nullptr;
     uint32_t* lk_out = A.lookup ? A.lookup + inst * P.lookup_inst_cells * 8 : nullptr;
     uint32_t* sp_out = A.spread ? A.spread + inst * P.spread_inst_cells * 8 : nullptr;
-    // items are enumerated group-major; total = sum of counts
-    uint32_t n_items = 0;
-    for (uint32_t gi = 0; gi < jc.n_groups; gi++) n_items += s_groups[jc.group_off + gi].count;
-    for (;;) {
-      uint32_t item = 0;
-      if (lane == 0) item = atomicAdd(&s_misc->next_item, 1u);
-      item = __shfl_sync(0xffffffffu, item, 0);
-      if (item >= n_items) break;
-      // heavy groups (ROUND, SCHED) are not first in stream order; walk the groups from the largest unit downwards
-      uint32_t gi = 0, u = item;
-      {
-        // group order by decreasing template length is precomputed by the planner in the task list; here: linear scan
-        // over groups in task order (tasks are sorted longest-program-first and cover every group)
-        uint32_t rem = item; bool found = false;
-        for (uint32_t t = 0; t < jc.n_tasks && !found; t++) {
-          const WarpTask wt = s_tasks[jc.task_off + t];
-          uint32_t cnt = min(32u, s_groups[jc.group_off + wt.group].count - wt.first);
-          if (rem < cnt) { gi = wt.group; u = wt.first + rem; found = true; } else rem -= cnt;
-        }
-      }
-      const UnitGroup& g = s_groups[jc.group_off + gi];
+    for (uint32_t it = warp; it < jc.n_items; it += NW) {
+      const uint32_t item = s_items[jc.item_off + it];
+      const UnitGroup& g = s_groups[jc.group_off + H2SHA_ITEM_GROUP(item)];
       const UnitType& ut = s_types[g.type];
+      const uint32_t u = H2SHA_ITEM_UNIT(item);
+      const Chunk ch = s_chunks[ut.chunk_off + H2SHA_ITEM_CHUNK(item)];
       const uint64_t* slots = s_slots + g.slot_base + u * (ut.n_slots | 1u);
+      // fill
+      for (uint32_t i = lane; i < ch.n_fill; i += 32) fill_entry(s_fill[ch.fill_off + i], slots, s_table, s_table_h, &ws->val[i][0], &ws->h[i]);
+      __syncwarp();
       // gate cells
-      {
+      if (ch.gate_len) {
         const uint32_t g_lo = gate0 + g.gate_base + u * g.gate_stride;   // instance-relative gate-stream index of the unit's first cell
         uint32_t c0 = 0;
         while (c0 + 1 < P.n_breaks && s_breaks[c0 + 1] <= g_lo) c0++;
         const uint32_t next_brk = (c0 + 1 < P.n_breaks) ? s_breaks[c0 + 1] : 0xffffffffu;
         const uint32_t brk0 = s_breaks[c0];
-        const TmplEntry* tm = s_tmpl + ut.gate_off;
-        for (uint32_t i = lane; i < ut.gate_len; i += 32) {
-          const TmplEntry e = tm[i];
+        for (uint32_t i = lane; i < ch.gate_len; i += 32) {
+          const CellEntry ce = s_cells[ch.gate_off + i];
           uint32_t x[8];
-          eval_entry(e, slots, s_table, x);
-          uint32_t gidx = g_lo + H2SHA_TE_DST(e);
-          uint64_t pos = (gidx >= next_brk) ? (uint64_t)(c0 + 1) * P.gate_col_rows + (gidx - next_brk) : (uint64_t)c0 * P.gate_col_rows + (gidx - brk0);
-          if (gate_out) store_cell(gate_out + pos * 8, x);
-          ck_g += cell_ck(x, pos);
+          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, x);
+          const uint32_t gidx = g_lo + H2SHA_CE_DST(ce);
+          const uint32_t pos = (gidx >= next_brk) ? (c0 + 1) * P.gate_col_rows + (gidx - next_brk) : c0 * P.gate_col_rows + (gidx - brk0);
+          if (gate_out) store_cell(gate_out + (uint64_t)pos * 8, x);
+          ck_g += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
       // lookup-column cells (range.finalize copies cells_to_lookup in push order, wrapping at max_rows)
-      if (ut.lk_len) {
+      if (ch.lk_len) {
         const uint32_t l_lo = lk0 + g.lk_base + u * g.lk_stride;
-        const TmplEntry* tm = s_tmpl + ut.lk_off;
-        for (uint32_t i = lane; i < ut.lk_len; i += 32) {
-          const TmplEntry e = tm[i];
+        for (uint32_t i = lane; i < ch.lk_len; i += 32) {
+          const CellEntry ce = s_cells[ch.lk_off + i];
           uint32_t x[8];
-          eval_entry(e, slots, s_table, x);
-          uint32_t li = l_lo + H2SHA_TE_DST(e);
-          uint32_t col = li / P.max_rows, row = li - col * P.max_rows;
-          uint64_t pos = (uint64_t)col * P.lookup_col_rows + row;
-          if (lk_out) store_cell(lk_out + pos * 8, x);
-          ck_l += cell_ck(x, pos);
+          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, x);
+          const uint32_t li = l_lo + H2SHA_CE_DST(ce);
+          const uint32_t col = li / P.max_rows, row = li - col * P.max_rows;
+          const uint32_t pos = col * P.lookup_col_rows + row;
+          if (lk_out) store_cell(lk_out + (uint64_t)pos * 8, x);
+          ck_l += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
       // spread-table columns: limb n -> column n % cols, row n / cols (spread.rs:202,228-231); dense then spread
-      if (ut.limb_len) {
+      if (ch.limb_len) {
         const uint32_t m_lo = limb0 + g.limb_base + u * g.limb_stride;
-        const TmplEntry* tm = s_tmpl + ut.limb_off;
-        for (uint32_t i = lane; i < ut.limb_len; i += 32) {
-          const TmplEntry e = tm[i];
+        for (uint32_t i = lane; i < ch.limb_len; i += 32) {
+          const CellEntry ce = s_cells[ch.limb_off + i];
           uint32_t x[8];
-          eval_entry(e, slots, s_table, x);
-          uint32_t n = m_lo + (H2SHA_TE_DST(e) >> 1), which = H2SHA_TE_DST(e) & 1u;
-          uint32_t row = n / P.spread_cols, col = n - row * P.spread_cols;
-          uint64_t pos = (uint64_t)(which * P.spread_cols + col) * P.spread_rows + row;
-          if (sp_out) store_cell(sp_out + pos * 8, x);
-          ck_s += cell_ck(x, pos);
+          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, x);
+          const uint32_t n = m_lo + (H2SHA_CE_DST(ce) >> 1), which = H2SHA_CE_DST(ce) & 1u;
+          const uint32_t row = n / P.spread_cols, col = n - row * P.spread_cols;
+          const uint32_t pos = (which * P.spread_cols + col) * P.spread_rows + row;
+          if (sp_out) store_cell(sp_out + (uint64_t)pos * 8, x);
+          ck_s += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
+      __syncwarp();  // scratch is overwritten by the next item's fill
     }
     // ---- checksums: warp reduce, CTA reduce in shared memory, one global atomic per kind ----
     if (A.cks) {
@@ -673,6 +692,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   if (cfg->num_advice_columns) pc.spread_cols = cfg->num_advice_columns;
   pc.is_input_range_check = cfg->is_input_range_check ? 1 : 0;
   pc.record_shape = cfg->build_shape ? 1 : 0;
+  if (cfg->block_parts) pc.block_parts = cfg->block_parts;
   h2sha_engine* e = new h2sha_engine();
   std::string err;
   if (!build_plan(pc, &e->plan, &err)) { delete e; return set_err(H2SHA_EINVAL, err); }
@@ -718,8 +738,21 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
     if (bytes) memcpy(blob.data() + off, p, bytes);
     return off;
   };
-  D.off_tmpl = put(P.tmpl.data(), P.tmpl.size() * sizeof(TmplEntry));
+  D.off_fill = put(P.fill.data(), P.fill.size() * sizeof(TmplEntry));
+  D.off_cells = put(P.cells.data(), P.cells.size() * sizeof(CellEntry));
+  D.off_chunks = put(P.chunks.data(), P.chunks.size() * sizeof(Chunk));
+  D.off_items = put(P.items.data(), P.items.size() * 4);
   D.off_table = put(P.mont_table.data(), P.mont_table.size() * 32);
+  {
+    std::vector<uint32_t> th(P.mont_table.size());
+    for (size_t i = 0; i < th.size(); i++) {
+      const uint32_t* x = reinterpret_cast<const uint32_t*>(P.mont_table[i].l);
+      uint32_t h = 0;
+      for (int k = 0; k < 8; k++) h += x[k] * H2SHA_CK_M[k];
+      th[i] = h;
+    }
+    D.off_table_h = put(th.data(), th.size() * 4);
+  }
   D.off_prog = put(P.prog.data(), P.prog.size() * sizeof(VmIns));
   D.off_groups = put(P.groups.data(), P.groups.size() * sizeof(UnitGroup));
   D.off_tasks = put(P.tasks.data(), P.tasks.size() * sizeof(WarpTask));
@@ -731,9 +764,11 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.blob_bytes = (uint32_t)blob.size();
   D.n_breaks = (uint32_t)P.breaks.size();
   D.n_digests = (uint32_t)P.digests.size();
+  D.n_block_parts = P.n_block_parts;
   D.off_trace = D.blob_bytes;
   D.off_slots = align_up(D.off_trace + 4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
-  D.off_misc = align_up(D.off_slots + 8 * P.max_slots, 16);
+  D.off_scratch = align_up(D.off_slots + 8 * (P.max_slots + 1), 16);
+  D.off_misc = align_up(D.off_scratch + (EXPAND_THREADS / 32) * (uint32_t)sizeof(WarpScratch), 16);
   D.smem_bytes = D.off_misc + (uint32_t)sizeof(Misc);
   if (D.smem_bytes > 227 * 1024) { delete e; return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory"); }
   D.max_rows = pc.max_rows; D.spread_cols = pc.spread_cols;
@@ -897,7 +932,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     ja.n_inst = b->n_instances; ja.btrace = e->d_btrace; ja.dtrace = e->d_dtrace;
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
     ja.cks = cks_dev; ja.job_counter = e->d_counter;
-    uint64_t n_jobs = b->n_instances * (uint64_t)(e->blocks_per_inst + D);
+    uint64_t n_jobs = b->n_instances * ((uint64_t)e->blocks_per_inst * P.n_block_parts + D);
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     k_expand<EXPAND_THREADS><<<grid, EXPAND_THREADS, e->dplan.smem_bytes, st>>>(e->dplan, ja);

@@ -67,15 +67,36 @@ static inline uint32_t vm_operand_slot(uint32_t slot, uint32_t sh, uint32_t w) {
 static inline uint32_t vm_operand_const(uint32_t idx) { return 1u | (idx << 1); }
 
 // ---------------------------------------------------------------------------------------------
-// Unit type: program + templates (offsets into the plan's flat arrays).
+// Phase 2 works chunk by chunk (a chunk = up to a few hundred consecutive cells of one unit):
+//   fill:  every DISTINCT non-constant value of the chunk is converted once (TmplEntry, `dst` unused) into the
+//          warp's scratch table: KIND_TABLE entries are copied from the static Montgomery table, the others go
+//          through the Barrett conversion; entries are sorted TABLE | GENERIC <= 32 bit | GENERIC > 32 bit / SIGNED;
+//   copy:  every cell is a 32-byte copy  scratch-or-constant -> its (column,row)  (CellEntry).
 // ---------------------------------------------------------------------------------------------
+struct CellEntry {
+  uint32_t v;  // src (16) | dst (16).  src bit 15 set: warp scratch index (src & 0x7fff); else static table index.
+};
+#define H2SHA_CE_SRC(e) ((e).v & 0xffffu)
+#define H2SHA_CE_DST(e) ((e).v >> 16)
+enum { H2SHA_SCRATCH_FLAG = 0x8000, H2SHA_MAX_FILL = 128 };
+
+struct Chunk {
+  uint32_t fill_off;   // TmplEntry index
+  uint16_t n_fill, n_fill_table;
+  uint32_t gate_off;   // CellEntry index; dst = gate-stream offset inside the unit
+  uint16_t gate_len, pad0;
+  uint32_t lk_off;     // dst = lookup index inside the unit
+  uint16_t lk_len, pad1;
+  uint32_t limb_off;   // dst = (limb index inside the unit) << 1 | (0 dense, 1 spread)
+  uint16_t limb_len, pad2;
+};
+
+// Unit type: slot program + chunks (offsets into the plan's flat arrays).
 struct UnitType {
   uint32_t n_in, n_slots;        // input slots, total slots (slot stride is n_slots | 1)
   uint32_t prog_off, prog_len;   // VmIns
-  uint32_t gate_off, gate_len;   // TmplEntry, table-kind entries first
-  uint32_t gate_n_table;         // number of leading KIND_TABLE entries in the gate template
-  uint32_t lk_off, lk_len;       // lookup-column template (dst = index in the unit's lookup span)
-  uint32_t limb_off, limb_len;   // spread-column template: 2 entries per limb (dense, spread); dst = limb index in unit
+  uint32_t chunk_off, n_chunks;  // Chunk
+  uint32_t gate_len, lk_len, limb_len;   // cells per instance (limb_len = 2 per limb)
 };
 
 // Input source of slot k of a unit instance u: trace[in_base + in_stride * u]; or the instance index u itself.
@@ -101,10 +122,17 @@ struct WarpTask {
   uint32_t group, first;
 };
 
-// A job class: the block job (one sha256_compression) or the per-digest prologue/epilogue job.
+// Work item of phase 2: one chunk of one unit instance.  group (8) | instance (12) | chunk (12)
+#define H2SHA_ITEM(g, u, c) (((uint32_t)(g) << 24) | ((uint32_t)(u) << 12) | (uint32_t)(c))
+#define H2SHA_ITEM_GROUP(x) ((x) >> 24)
+#define H2SHA_ITEM_UNIT(x) (((x) >> 12) & 0xfffu)
+#define H2SHA_ITEM_CHUNK(x) ((x) & 0xfffu)
+
+// A job class: (a part of) the block job (one sha256_compression) or the per-digest prologue/epilogue job.
 struct JobClass {
   uint32_t group_off, n_groups;  // UnitGroup
-  uint32_t task_off, n_tasks;    // WarpTask
+  uint32_t task_off, n_tasks;    // WarpTask (phase 1)
+  uint32_t item_off, n_items;    // phase-2 work items, heaviest first
   uint32_t n_slots_total;        // u64 slots needed in shared memory
   uint32_t n_trace_words;        // u32 words of trace the job loads
 };
@@ -122,7 +150,7 @@ struct DigestPlace {
   uint32_t gate_base, lk_base, limb_base;   // start of this digest's prologue
   uint32_t blk_gate_base, blk_lk_base, blk_limb_base;   // block 0 of this digest (after the one-time zero cell, if any)
   uint32_t blk_gate_stride, blk_lk_stride, blk_limb_stride;
-  uint32_t job_class;            // digest-job class index (block jobs all share class 0)
+  uint32_t job_class;            // digest-job class index (block-job parts are classes 0 .. n_block_parts-1)
   uint32_t trace_words;          // digest-job trace words
 };
 

@@ -42,8 +42,14 @@ struct QC {
   bool dyn = false;      // QC_CONSTANT whose value differs per unit instance (cell comes from a slot)
 };
 
+enum : uint8_t { EV_GATE = 0, EV_LK = 1, EV_LIMB = 2 };
+struct Event {
+  uint8_t kind;
+  Sym s;
+};
 struct UnitRec {
   std::vector<Sym> gate, lk, limb;
+  std::vector<Event> ev;  // the same cells in emission order (chunking needs the interleaving)
   std::vector<VmIns> prog;
   std::vector<InputMap> in;
   uint32_t n_slots = 0;
@@ -310,6 +316,7 @@ class Builder {
       const QC& q = cells[i];
       if (q.kind == QC_EXISTING && q.ex.serial != 0 && q.ex.serial != serial_) fail("cell from another unit used without rebind in " + grp_->type);
       cur_.gate.push_back(q.s);
+      cur_.ev.push_back(Event{EV_GATE, q.s});
       if (cfg_.record_shape) {
         P_->selectors.push_back(0);
         if (q.kind == QC_EXISTING) add_copy(CP_GATE, base + i, CP_GATE, q.ex.idx);
@@ -358,6 +365,7 @@ class Builder {
 
   void lk_push(const AV& a) {
     cur_.lk.push_back(a.s);
+    cur_.ev.push_back(Event{EV_LK, a.s});
     if (a.serial != 0 && a.serial != serial_) fail("lookup of a cell from another unit");
     if (cfg_.record_shape) P_->lookup_cells.push_back(a.idx);
     n_lk_++;
@@ -413,6 +421,8 @@ class Builder {
     Sym sp = table(T_SBYTE, limb.s);
     cur_.limb.push_back(limb.s);  // dense column cell (:203-208)
     cur_.limb.push_back(sp);      // spread column cell (:219-224)
+    cur_.ev.push_back(Event{EV_LIMB, limb.s});
+    cur_.ev.push_back(Event{EV_LIMB, sp});
     AV as = load_witness(sp);     // :225
     if (cfg_.record_shape) { P_->limb_gate_dense.push_back(limb.idx); P_->limb_gate_spread.push_back(as.idx); }
     n_limb_++;
@@ -866,24 +876,169 @@ class Builder {
   }
 
   // ======================================================================================
-  // finalize: pack templates, build tables, layout
+  // finalize: chunk + de-duplicate the cells of every unit type, build tables, job classes, layout
   // ======================================================================================
-  TmplEntry pack(const Sym& s0, uint32_t dst) {
+  // normalised form of a symbolic value: small plain values come from the byte table instead of a Barrett reduction
+  Sym normalise(const Sym& s0) const {
     Sym s = s0;
-    // small plain values come from the byte table instead of a Barrett reduction
     if (s.kind == KIND_GENERIC && !s.neg && s.shl == 0 && s.w <= 8) { s.kind = KIND_TABLE; s.table = T_BYTE; s.tbl_off = 0; }
+    if (s.kind == KIND_TABLE && s.w == 0) { s.slot = 0; s.sh = 0; s.shl = 0; s.neg = 0; }
+    if (s.kind == KIND_SIGNED) { s.sh = 0; s.w = 64; s.shl = 0; s.neg = 0; }
+    return s;
+  }
+  uint32_t table_index(const Sym& s) const {
     uint32_t tbl = 0;
-    if (s.kind == KIND_TABLE) {
-      switch (s.table) {
-        case T_CONST: tbl = s.tbl_off; break;
-        case T_BYTE: tbl = P_->tb_byte + s.tbl_off; break;
-        case T_SBYTE: tbl = P_->tb_sbyte + s.tbl_off; break;
-        case T_INV: tbl = P_->tb_inv + s.tbl_off; break;
-      }
-      if (s.table == T_SBYTE && s.w > cfg_.limb_bits) fail("spread-table index wider than a limb");
-      if (tbl > 0xffff) fail("table too large");
+    switch (s.table) {
+      case T_CONST: tbl = s.tbl_off; break;
+      case T_BYTE: tbl = P_->tb_byte + s.tbl_off; break;
+      case T_SBYTE: tbl = P_->tb_sbyte + s.tbl_off; break;
+      case T_INV: tbl = P_->tb_inv + s.tbl_off; break;
     }
-    return tmpl_pack(dst, tbl, s.slot, s.sh, s.w, s.shl, s.kind, s.neg);
+    if (s.table == T_SBYTE && s.w > cfg_.limb_bits) fail("spread-table index wider than a limb");
+    if (tbl >= H2SHA_SCRATCH_FLAG) fail("static table too large");
+    return tbl;
+  }
+  // sort class of a fill entry: table copies, then <= 32-bit Barrett, then the full 64-bit / signed path
+  static int fill_class(const Sym& s) {
+    if (s.kind == KIND_TABLE) return 0;
+    if (s.kind == KIND_GENERIC && (uint32_t)s.w + s.shl <= 32) return 1;
+    return 2;
+  }
+  static uint64_t sym_key(const Sym& s) {
+    return (uint64_t)s.kind | ((uint64_t)s.neg << 2) | ((uint64_t)s.slot << 3) | ((uint64_t)s.sh << 11) | ((uint64_t)s.w << 17) |
+           ((uint64_t)s.shl << 24) | ((uint64_t)s.table << 29) | ((uint64_t)s.tbl_off << 32);
+  }
+
+  // Cuts one unit's cell stream into chunks of at most H2SHA_MAX_FILL distinct non-constant values.
+  void build_chunks(const UnitRec& u, UnitType* ut) {
+    Plan& P = *P_;
+    ut->chunk_off = (uint32_t)P.chunks.size();
+    struct Pending { uint8_t kind; Sym s; uint32_t dst; };
+    std::vector<Pending> cur;
+    std::map<uint64_t, Sym> distinct;
+    uint32_t n_gate = 0, n_lk = 0, n_limb = 0, gate_in_chunk = 0;
+    auto flush = [&]() {
+      if (cur.empty()) return;
+      // order the distinct values: TABLE | GENERIC32 | GENERIC64, stable by first use
+      std::vector<Sym> order;
+      std::map<uint64_t, uint32_t> index;
+      for (int cls = 0; cls < 3; cls++)
+        for (auto& pc : cur) {
+          if (pc.s.kind == KIND_TABLE && pc.s.w == 0) continue;  // constants are read straight from the static table
+          if (fill_class(pc.s) != cls) continue;
+          uint64_t k = sym_key(pc.s);
+          if (index.count(k)) continue;
+          index[k] = (uint32_t)order.size();
+          order.push_back(pc.s);
+        }
+      if (order.size() > H2SHA_MAX_FILL) fail("chunk has too many distinct values");
+      Chunk c{};
+      c.fill_off = (uint32_t)P.fill.size();
+      c.n_fill = (uint16_t)order.size();
+      for (auto& sy : order) {
+        if (fill_class(sy) == 0) c.n_fill_table++;
+        P.fill.push_back(tmpl_pack(0, sy.kind == KIND_TABLE ? table_index(sy) : 0, sy.slot, sy.sh, sy.w, sy.shl, sy.kind, sy.neg));
+      }
+      for (int kind = 0; kind < 3; kind++) {
+        uint32_t off = (uint32_t)P.cells.size(), n = 0;
+        for (auto& pc : cur) {
+          if (pc.kind != kind) continue;
+          uint32_t src = (pc.s.kind == KIND_TABLE && pc.s.w == 0) ? table_index(pc.s) : (H2SHA_SCRATCH_FLAG | index.at(sym_key(pc.s)));
+          P.cells.push_back(CellEntry{src | (pc.dst << 16)});
+          n++;
+        }
+        if (kind == EV_GATE) { c.gate_off = off; c.gate_len = (uint16_t)n; }
+        if (kind == EV_LK) { c.lk_off = off; c.lk_len = (uint16_t)n; }
+        if (kind == EV_LIMB) { c.limb_off = off; c.limb_len = (uint16_t)n; }
+      }
+      P.chunks.push_back(c);
+      cur.clear(); distinct.clear(); gate_in_chunk = 0;
+    };
+    // greedy: close the chunk at a multiple of 32 gate cells once the next 32-cell group could overflow the scratch table
+    size_t i = 0;
+    while (i < u.ev.size()) {
+      // next group: events up to and including the 32nd gate cell from here (plus the lookup / limb events in between)
+      size_t j = i; uint32_t g = 0;
+      while (j < u.ev.size() && !(g == 32 && u.ev[j].kind == EV_GATE)) { if (u.ev[j].kind == EV_GATE) g++; j++; }
+      std::map<uint64_t, Sym> trial = distinct;
+      for (size_t k = i; k < j; k++) {
+        Sym sy = normalise(u.ev[k].s);
+        if (!(sy.kind == KIND_TABLE && sy.w == 0)) trial[sym_key(sy)] = sy;
+      }
+      if (trial.size() > H2SHA_MAX_FILL && !cur.empty()) { flush(); continue; }
+      if (trial.size() > H2SHA_MAX_FILL) fail("a 32-cell group has more than H2SHA_MAX_FILL distinct values");
+      for (size_t k = i; k < j; k++) {
+        Sym sy = normalise(u.ev[k].s);
+        uint32_t dst = (u.ev[k].kind == EV_GATE) ? n_gate++ : (u.ev[k].kind == EV_LK) ? n_lk++ : n_limb++;
+        if (dst > 0xffff) fail("unit too large");
+        cur.push_back(Pending{u.ev[k].kind, sy, dst});
+        if (u.ev[k].kind == EV_GATE) gate_in_chunk++;
+      }
+      distinct.swap(trial);
+      i = j;
+    }
+    flush();
+    ut->n_chunks = (uint32_t)P.chunks.size() - ut->chunk_off;
+    ut->gate_len = n_gate; ut->lk_len = n_lk; ut->limb_len = n_limb;
+    if (n_gate != u.gate.size() || n_lk != u.lk.size() || n_limb != u.limb.size()) fail("event list out of sync");
+  }
+
+  // cost estimate of one work item (for the heaviest-first ordering)
+  uint32_t chunk_cost(const Chunk& c) const {
+    return 3u * c.n_fill_table + 12u * (c.n_fill - c.n_fill_table) + c.gate_len + c.lk_len + c.limb_len + 32u;
+  }
+
+  // appends a JobClass made of `groups` (already with final counts / bases / input maps)
+  void add_class(const std::vector<UnitGroup>& groups, uint32_t n_trace_words) {
+    Plan& P = *P_;
+    JobClass jc{};
+    jc.group_off = (uint32_t)P.groups.size(); jc.n_groups = (uint32_t)groups.size();
+    if (groups.size() > 255) fail("too many groups in a job class");
+    uint32_t slot_base = 0;
+    for (UnitGroup g : groups) {
+      g.slot_base = slot_base;
+      slot_base += g.count * (P.types[g.type].n_slots | 1u);
+      P.groups.push_back(g);
+    }
+    jc.n_slots_total = slot_base;
+    P.max_slots = std::max(P.max_slots, slot_base);
+    // phase-1 warp tasks, longest program first
+    jc.task_off = (uint32_t)P.tasks.size();
+    std::vector<std::pair<uint32_t, WarpTask>> ts;
+    for (uint32_t gi = 0; gi < groups.size(); gi++)
+      for (uint32_t first = 0; first < groups[gi].count; first += 32) ts.push_back({P.types[groups[gi].type].prog_len, WarpTask{gi, first}});
+    std::stable_sort(ts.begin(), ts.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    for (auto& t : ts) P.tasks.push_back(t.second);
+    jc.n_tasks = (uint32_t)ts.size();
+    // phase-2 items, heaviest first
+    jc.item_off = (uint32_t)P.items.size();
+    std::vector<std::pair<uint32_t, uint32_t>> its;
+    for (uint32_t gi = 0; gi < groups.size(); gi++) {
+      const UnitType& ut = P.types[groups[gi].type];
+      if (groups[gi].count > 0xfff || ut.n_chunks > 0xfff) fail("item encoding overflow");
+      for (uint32_t u = 0; u < groups[gi].count; u++)
+        for (uint32_t c = 0; c < ut.n_chunks; c++) its.push_back({chunk_cost(P.chunks[ut.chunk_off + c]), H2SHA_ITEM(gi, u, c)});
+    }
+    std::stable_sort(its.begin(), its.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    for (auto& it : its) P.items.push_back(it.second);
+    jc.n_items = (uint32_t)its.size();
+    jc.n_trace_words = n_trace_words;
+    P.max_trace_words = std::max(P.max_trace_words, n_trace_words);
+    P.classes.push_back(jc);
+  }
+
+  UnitGroup make_group(const GroupRec& g, uint32_t first, uint32_t count) const {
+    UnitGroup ug{};
+    ug.type = type_idx_.at(g.type); ug.count = count;
+    ug.gate_base = g.gate_base + first * g.gate_stride; ug.gate_stride = g.gate_stride;
+    ug.lk_base = g.lk_base + first * g.lk_stride; ug.lk_stride = g.lk_stride;
+    ug.limb_base = g.limb_base + first * g.limb_stride; ug.limb_stride = g.limb_stride;
+    for (size_t i = 0; i < g.in.size(); i++) {
+      ug.in[i] = g.in[i];
+      if (ug.in[i].base >= 0) ug.in[i].base += g.in[i].stride * (int32_t)first;
+      else ug.in[i].stride = (int32_t)first;  // instance-index input: value = stride + u
+    }
+    return ug;
   }
 
   void finalize() {
@@ -914,55 +1069,39 @@ class Builder {
       ut.n_in = (uint32_t)u.in.size(); ut.n_slots = u.n_slots;
       ut.prog_off = (uint32_t)P.prog.size(); ut.prog_len = (uint32_t)u.prog.size();
       P.prog.insert(P.prog.end(), u.prog.begin(), u.prog.end());
-      // gate template: table-kind entries first (stable), then generic/signed
-      ut.gate_off = (uint32_t)P.tmpl.size(); ut.gate_len = (uint32_t)u.gate.size();
-      if (u.gate.size() > 0xffff) fail("unit too large");
-      std::vector<TmplEntry> tab, gen;
-      for (size_t i = 0; i < u.gate.size(); i++) {
-        TmplEntry e = pack(u.gate[i], (uint32_t)i);
-        (H2SHA_TE_KIND(e) == KIND_TABLE ? tab : gen).push_back(e);
-      }
-      ut.gate_n_table = (uint32_t)tab.size();
-      P.tmpl.insert(P.tmpl.end(), tab.begin(), tab.end());
-      P.tmpl.insert(P.tmpl.end(), gen.begin(), gen.end());
-      ut.lk_off = (uint32_t)P.tmpl.size(); ut.lk_len = (uint32_t)u.lk.size();
-      for (size_t i = 0; i < u.lk.size(); i++) P.tmpl.push_back(pack(u.lk[i], (uint32_t)i));
-      ut.limb_off = (uint32_t)P.tmpl.size(); ut.limb_len = (uint32_t)u.limb.size();
-      for (size_t i = 0; i < u.limb.size(); i++) P.tmpl.push_back(pack(u.limb[i], (uint32_t)i));
+      build_chunks(u, &ut);
       P.types.push_back(ut);
-      P.max_slots = std::max(P.max_slots, ut.n_slots);
     }
-    // ---- job classes ----
+    // ---- job classes: the block job is split into `block_parts` parts of roughly equal cell count ----
     P.max_slots = 0;
-    for (size_t ci = 0; ci < class_recs_.size(); ci++) {
-      const ClassRec& c = class_recs_[ci];
-      JobClass jc{};
-      jc.group_off = (uint32_t)P.groups.size(); jc.n_groups = (uint32_t)c.groups.size();
-      uint32_t slot_base = 0;
+    {
+      const ClassRec& c = class_recs_[0];
+      uint64_t total = 0;
+      for (const GroupRec& g : c.groups) total += (uint64_t)g.count * P.types[type_idx_.at(g.type)].gate_len;
+      const uint32_t parts = std::max(1u, cfg_.block_parts);
+      std::vector<std::vector<UnitGroup>> part_groups(1);
+      uint64_t acc = 0;
       for (const GroupRec& g : c.groups) {
-        UnitGroup ug{};
-        ug.type = type_idx_.at(g.type); ug.count = g.count; ug.slot_base = slot_base;
-        ug.gate_base = g.gate_base; ug.gate_stride = g.gate_stride; ug.lk_base = g.lk_base; ug.lk_stride = g.lk_stride;
-        ug.limb_base = g.limb_base; ug.limb_stride = g.limb_stride;
-        for (size_t i = 0; i < g.in.size(); i++) ug.in[i] = g.in[i];
-        slot_base += g.count * (P.types[ug.type].n_slots | 1u);
-        P.groups.push_back(ug);
+        const uint64_t per = P.types[type_idx_.at(g.type)].gate_len;
+        uint32_t first = 0;
+        while (first < g.count) {
+          uint64_t target = total * part_groups.size() / parts;   // cumulative cell target at the end of the current part
+          uint32_t fit = per ? (uint32_t)std::min<uint64_t>(g.count - first, (target > acc ? (target - acc + per / 2) / per : 0)) : g.count - first;
+          if (part_groups.size() == parts) fit = g.count - first;
+          if (fit == 0) { part_groups.emplace_back(); continue; }
+          part_groups.back().push_back(make_group(g, first, fit));
+          acc += per * fit; first += fit;
+        }
       }
-      jc.n_slots_total = slot_base;
-      P.max_slots = std::max(P.max_slots, slot_base);
-      // warp tasks, longest program first
-      jc.task_off = (uint32_t)P.tasks.size();
-      std::vector<std::pair<uint32_t, WarpTask>> ts;
-      for (uint32_t gi = 0; gi < c.groups.size(); gi++) {
-        const UnitGroup& ug = P.groups[jc.group_off + gi];
-        for (uint32_t first = 0; first < ug.count; first += 32) ts.push_back({P.types[ug.type].prog_len, WarpTask{gi, first}});
-      }
-      std::stable_sort(ts.begin(), ts.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
-      for (auto& t : ts) P.tasks.push_back(t.second);
-      jc.n_tasks = (uint32_t)ts.size();
-      jc.n_trace_words = (ci == 0) ? (uint32_t)TR_BLOCK_WORDS_WITH_K : P.digests[ci - 1].trace_words;
-      P.max_trace_words = std::max(P.max_trace_words, jc.n_trace_words);
-      P.classes.push_back(jc);
+      while (!part_groups.empty() && part_groups.back().empty()) part_groups.pop_back();
+      P.n_block_parts = (uint32_t)part_groups.size();
+      for (auto& pg : part_groups) add_class(pg, (uint32_t)TR_BLOCK_WORDS_WITH_K);
+    }
+    for (size_t ci = 1; ci < class_recs_.size(); ci++) {
+      std::vector<UnitGroup> gs;
+      for (const GroupRec& g : class_recs_[ci].groups) gs.push_back(make_group(g, 0, g.count));
+      P.digests[ci - 1].job_class = (uint32_t)P.classes.size();
+      add_class(gs, P.digests[ci - 1].trace_words);
     }
     // ---- layout ----
     auto up4 = [](uint32_t x) { return (x + 3u) & ~3u; };

@@ -23,6 +23,7 @@ struct Config {
   uint32_t spread_cols = 2;                       // SpreadConfig num_advice_columns
   uint32_t is_input_range_check = 1;
   uint32_t record_shape = 1;                      // also build selectors / copy constraints / fixed column
+  uint32_t block_parts = 3;                       // engine tuning: jobs per sha256_compression (load balance vs. overhead)
 };
 
 enum : uint32_t { CP_GATE = 0, CP_FIXED = 1 };
@@ -46,10 +47,14 @@ struct Plan {
   std::vector<UnitType> types;
   std::vector<std::string> type_names;
   std::vector<VmIns> prog;
-  std::vector<TmplEntry> tmpl;
+  std::vector<TmplEntry> fill;          // fill lists of all chunks
+  std::vector<CellEntry> cells;         // cell lists of all chunks
+  std::vector<Chunk> chunks;
+  std::vector<uint32_t> items;          // phase-2 work items of all classes
+  uint32_t n_block_parts = 1;
   std::vector<UnitGroup> groups;
   std::vector<WarpTask> tasks;
-  std::vector<JobClass> classes;        // class 0 = block job; class 1+d = digest job of digest d
+  std::vector<JobClass> classes;        // classes [0, n_block_parts) = block-job parts; then one digest job class per digest
   std::vector<uint64_t> raw_consts;     // VM constants
   std::vector<U256> mont_table;         // Montgomery-form table: [fixed constants | byte | spread-byte | inverses]
   uint32_t tb_byte = 0, tb_sbyte = 0, tb_inv = 0, inv_bias = 0;

@@ -57,6 +57,7 @@ typedef struct {
   uint32_t spread_rows;                     /* 0 -> tight                                                       */
   int32_t device;                           /* CUDA device ordinal; -1 = plan-only (host queries, no witness)   */
   uint32_t build_shape;                     /* also build selectors / copy constraints / fixed column (host)    */
+  uint32_t block_parts;                     /* tuning: GPU jobs per sha256_compression; 0 -> default            */
 } h2sha_config_t;
 
 typedef struct {

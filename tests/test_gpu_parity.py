@@ -140,7 +140,7 @@ def test_precomputed_prefix(pkg):
     rng = np.random.default_rng(9)
     kw = dict(max_variable_byte_sizes=(128, 128))
     instances = [[bytes(rng.integers(0, 256, 192, dtype=np.uint8)) for _ in range(2)] for _ in range(3)]
-    pre = [[128, 128], [128, 64], [64, 128]]
+    pre = [[128, 128], [192, 128], [256, 192]]
     res, _ = _compare(pkg, kw, instances, pre)
     for inst, ds in zip(instances, res.digests.reshape(3, 2, 32)):
         assert [hashlib.sha256(m).digest() for m in inst] == [bytes(x) for x in ds]
