@@ -55,7 +55,8 @@ struct DevPlan {
       off_raw, off_breaks, off_digests;
   uint32_t n_breaks, n_digests, n_block_parts;
   // dynamic shared memory layout after the blob
-  uint32_t off_trace, off_slots, off_scratch, off_misc, smem_bytes;
+  uint32_t off_trace, off_scratch, off_misc, smem_bytes;
+  uint32_t stage_bytes, stage_off_slots, stage_off_desc;   // per producer warp: trace | slots | StageDesc
   // layout
   uint32_t max_rows, spread_cols, n_gate_cols, gate_col_rows, n_lookup_cols, lookup_col_rows, spread_rows;
   uint32_t blocks_per_inst, dtrace_words_per_inst;
@@ -158,19 +159,6 @@ __device__ __forceinline__ void fr_negate(uint64_t r[4]) {
       : "=l"(s0), "=l"(s1), "=l"(s2), "=l"(s3)
       : "l"(c_fr.p[0]), "l"(c_fr.p[1]), "l"(c_fr.p[2]), "l"(c_fr.p[3]), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]));
   r[0] = s0; r[1] = s1; r[2] = s2; r[3] = s3;
-}
-
-// one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
-__device__ __forceinline__ void store_cell(uint32_t* p, const uint32_t x[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]),
-               "r"(x[5]), "r"(x[6]), "r"(x[7])
-               : "memory");
-}
-__device__ __forceinline__ unsigned long long cell_ck(const uint32_t x[8], uint64_t pos) {
-  uint32_t h = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) h += x[k] * c_CKM[k];
-  return (unsigned long long)h * (unsigned long long)(uint32_t)(2u * (uint32_t)pos + 1u);
 }
 
 // bit i -> bit 2i of the low 32 bits
@@ -317,15 +305,41 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
 // ---------------------------------------------------------------------------------------------------
 // k_expand
 // ---------------------------------------------------------------------------------------------------
-struct Misc {
-  unsigned long long ck[3];
-  uint32_t job_lo, job_hi;
-};
-// per-warp scratch of phase 2: Montgomery values of the chunk's distinct non-constant cells + their checksum hashes
+// per-consumer-warp scratch of phase 2: Montgomery values of the chunk's distinct non-constant cells (low / high
+// 16 bytes in separate arrays so that random 128-bit reads spread over all bank groups) + their checksum hashes
 struct WarpScratch {
-  uint32_t val[H2SHA_MAX_FILL][8];
+  uint4 lo[H2SHA_MAX_FILL];
+  uint4 hi[H2SHA_MAX_FILL];
   uint32_t h[H2SHA_MAX_FILL];
 };
+// job descriptor a producer warp leaves in its stage
+struct StageDesc {
+  unsigned long long inst;
+  uint32_t cls, gate0, lk0, limb0;
+  uint32_t valid, pad;
+};
+
+// ---- mbarrier helpers (shared::cta) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 __device__ __forceinline__ uint64_t vm_operand(uint32_t o, const uint64_t* slots, const uint64_t* raw) {
   if (o & 1u) return raw[o >> 1];
@@ -372,17 +386,15 @@ __device__ __forceinline__ uint32_t cell_hash(const uint32_t x[8]) {
   return h;
 }
 
-// fill phase: Fr value (+ hash) of one distinct value of the chunk -> warp scratch
-__device__ __forceinline__ void fill_entry(const TmplEntry e, const uint64_t* slots, const uint32_t* table, const uint32_t* table_h,
-                                           uint32_t* out_val, uint32_t* out_h) {
+// fill phase: Fr value (+ hash) of one distinct value of the chunk -> warp scratch entry i
+__device__ __forceinline__ void fill_entry(const TmplEntry e, const uint64_t* slots, const uint4* table, const uint32_t* table_h,
+                                           WarpScratch* ws, uint32_t i) {
   const uint32_t kind = H2SHA_TE_KIND(e);
   const uint64_t s = slots[H2SHA_TE_SLOT(e)];
   if (kind == KIND_TABLE) {
     const uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
-    const uint4* t = reinterpret_cast<const uint4*>(table + 8 * idx);
-    uint4* o = reinterpret_cast<uint4*>(out_val);
-    o[0] = t[0]; o[1] = t[1];
-    *out_h = table_h[idx];
+    ws->lo[i] = table[2 * idx]; ws->hi[i] = table[2 * idx + 1];
+    ws->h[i] = table_h[idx];
     return;
   }
   bool neg = H2SHA_TE_NEG(e);
@@ -399,26 +411,32 @@ __device__ __forceinline__ void fill_entry(const TmplEntry e, const uint64_t* sl
   if (neg) fr_negate(r);
   uint32_t x[8] = {(uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32),
                    (uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32)};
-  uint4* o = reinterpret_cast<uint4*>(out_val);
-  o[0] = make_uint4(x[0], x[1], x[2], x[3]); o[1] = make_uint4(x[4], x[5], x[6], x[7]);
-  *out_h = cell_hash(x);
+  ws->lo[i] = make_uint4(x[0], x[1], x[2], x[3]); ws->hi[i] = make_uint4(x[4], x[5], x[6], x[7]);
+  ws->h[i] = cell_hash(x);
 }
 
 // copy phase: source of a cell (static constant or warp scratch) -> registers + hash
-__device__ __forceinline__ uint32_t load_cell(uint32_t src, const uint32_t* table, const uint32_t* table_h, const WarpScratch* ws, uint32_t x[8]) {
-  const bool dyn = (src & H2SHA_SCRATCH_FLAG) != 0;
+__device__ __forceinline__ uint32_t load_cell(uint32_t src, const uint4* table, const uint32_t* table_h, const WarpScratch* ws, uint4& lo, uint4& hi) {
   const uint32_t idx = src & (H2SHA_SCRATCH_FLAG - 1);
-  const uint4* t = reinterpret_cast<const uint4*>(dyn ? &ws->val[idx][0] : table + 8 * idx);
-  uint4 lo = t[0], hi = t[1];
-  x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
-  return dyn ? ws->h[idx] : table_h[idx];
+  if (src & H2SHA_SCRATCH_FLAG) { lo = ws->lo[idx]; hi = ws->hi[idx]; return ws->h[idx]; }
+  lo = table[2 * idx]; hi = table[2 * idx + 1];
+  return table_h[idx];
+}
+// one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
+__device__ __forceinline__ void store_cell2(uint32_t* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
+               "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs A) {
+// Warp-specialised persistent kernel: NPROD producer warps run phase 1 (job fetch, trace load, slot programs) into
+// their own stage buffer; NCONS consumer warps run phase 2 (fill + copy) stage after stage.  Stages are handed over
+// with mbarriers, so no warp ever waits at a CTA-wide barrier inside the job loop.
+template <int NCONS, int NPROD>
+__global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPlan P, const JobArgs A) {
   extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int NT = (NCONS + NPROD) * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = NT / 32;
   // ---- static plan -> shared memory (once per persistent CTA) ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.blob);
@@ -429,7 +447,7 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
   const CellEntry* s_cells = reinterpret_cast<const CellEntry*>(smem + P.off_cells);
   const Chunk* s_chunks = reinterpret_cast<const Chunk*>(smem + P.off_chunks);
   const uint32_t* s_items = reinterpret_cast<const uint32_t*>(smem + P.off_items);
-  const uint32_t* s_table = reinterpret_cast<const uint32_t*>(smem + P.off_table);
+  const uint4* s_table = reinterpret_cast<const uint4*>(smem + P.off_table);
   const uint32_t* s_table_h = reinterpret_cast<const uint32_t*>(smem + P.off_table_h);
   const VmIns* s_prog = reinterpret_cast<const VmIns*>(smem + P.off_prog);
   const UnitGroup* s_groups = reinterpret_cast<const UnitGroup*>(smem + P.off_groups);
@@ -439,69 +457,104 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
   const uint64_t* s_raw = reinterpret_cast<const uint64_t*>(smem + P.off_raw);
   const uint32_t* s_breaks = reinterpret_cast<const uint32_t*>(smem + P.off_breaks);
   const DevDigest* s_digests = reinterpret_cast<const DevDigest*>(smem + P.off_digests);
-  uint32_t* s_trace = reinterpret_cast<uint32_t*>(smem + P.off_trace);
-  uint64_t* s_slots = reinterpret_cast<uint64_t*>(smem + P.off_slots);
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + P.off_scratch) + warp;
-  Misc* s_misc = reinterpret_cast<Misc*>(smem + P.off_misc);
-  for (int i = tid; i < 64; i += NT) s_trace[TR_K + i] = c_K[i];
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + P.off_misc);   // [NPROD]
+  uint64_t* s_empty = s_full + NPROD;                                  // [NPROD]
+  if (tid == 0) {
+    for (int i = 0; i < NPROD; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], NCONS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // blob + barriers visible; the only CTA-wide barrier
 
   const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst * P.n_block_parts;
   const uint64_t n_jobs = n_block_jobs + A.n_inst * P.n_digests;
 
-  for (;;) {
-    __syncthreads();  // previous job fully done (slots / trace / misc reusable); blob visible on the first pass
-    if (tid == 0) {
-      unsigned long long j = atomicAdd(A.job_counter, 1ULL);
-      s_misc->job_lo = (uint32_t)j; s_misc->job_hi = (uint32_t)(j >> 32);
-      s_misc->ck[0] = 0; s_misc->ck[1] = 0; s_misc->ck[2] = 0;
+  if (warp >= NCONS) {
+    // =========================== producer warp: owns stage `st` ===========================
+    const int st = warp - NCONS;
+    uint8_t* stage = smem + P.off_trace + (size_t)st * P.stage_bytes;
+    uint32_t* s_trace = reinterpret_cast<uint32_t*>(stage);
+    uint64_t* s_slots = reinterpret_cast<uint64_t*>(stage + P.stage_off_slots);
+    StageDesc* desc = reinterpret_cast<StageDesc*>(stage + P.stage_off_desc);
+    for (int i = lane; i < 64; i += 32) s_trace[TR_K + i] = c_K[i];
+    for (uint32_t k = 0;; k++) {
+      mbar_wait(&s_empty[st], (k & 1u) ^ 1u);   // consumers are done with this stage's previous job
+      unsigned long long job = 0;
+      if (lane == 0) job = atomicAdd(A.job_counter, 1ULL);
+      job = __shfl_sync(0xffffffffu, job, 0);
+      if (job >= n_jobs) {
+        if (lane == 0) { desc->valid = 0; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[st]);
+        break;
+      }
+      // ---- decode job ----
+      uint64_t inst; uint32_t cls, gate0, lk0, limb0; const uint32_t* tr_src; uint32_t tr_words;
+      if (job < n_block_jobs) {
+        const uint64_t blk = job / P.n_block_parts;          // global block index = inst * blocks_per_inst + r
+        cls = (uint32_t)(job - blk * P.n_block_parts);        // part of the block job
+        inst = blk / P.blocks_per_inst;
+        uint32_t r = (uint32_t)(blk - inst * P.blocks_per_inst);
+        uint32_t d = 0;
+        while (d + 1 < P.n_digests && r >= s_digests[d + 1].blk_prefix) d++;
+        const DevDigest& dd = s_digests[d];
+        uint32_t jb = r - dd.blk_prefix;
+        gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
+        lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
+        limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
+        tr_src = A.btrace + blk * (uint64_t)TR_BLOCK_WORDS;
+        tr_words = TR_BLOCK_WORDS;
+      } else {
+        uint64_t kk = job - n_block_jobs;
+        inst = kk / P.n_digests;
+        uint32_t d = (uint32_t)(kk - inst * P.n_digests);
+        const DevDigest& dd = s_digests[d];
+        cls = dd.dp.job_class;
+        gate0 = 0; lk0 = 0; limb0 = 0;
+        tr_src = A.dtrace + inst * P.dtrace_words_per_inst + dd.dtrace_off;
+        tr_words = dd.dp.trace_words;
+      }
+      const JobClass jc = s_classes[cls];
+      for (uint32_t i = lane; i < tr_words; i += 32) s_trace[i] = tr_src[i];
+      if (lane == 0) { desc->inst = inst; desc->cls = cls; desc->gate0 = gate0; desc->lk0 = lk0; desc->limb0 = limb0; desc->valid = 1; }
+      __syncwarp();
+      // ---- phase 1: slot programs, lanes = unit instances ----
+      for (uint32_t t = 0; t < jc.n_tasks; t++) {
+        const WarpTask wt = s_tasks[jc.task_off + t];
+        const UnitGroup& g = s_groups[jc.group_off + wt.group];
+        const UnitType& ut = s_types[g.type];
+        uint32_t u = wt.first + lane;
+        if (u < g.count) run_unit_program(g, ut, u, s_prog, s_raw, s_trace, s_slots + g.slot_base + u * (ut.n_slots | 1u));
+      }
+      if (tr_words > TR_K) {  // a long digest trace overwrote the round constants kept at TR_K for block jobs: restore them
+        __syncwarp();
+        for (int i = lane; i < 64; i += 32) s_trace[TR_K + i] = c_K[i];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[st]);
     }
-    __syncthreads();
-    const uint64_t job = ((uint64_t)s_misc->job_hi << 32) | s_misc->job_lo;
-    if (job >= n_jobs) break;
-    // ---- decode job ----
-    uint64_t inst; uint32_t cls, gate0, lk0, limb0; const uint32_t* tr_src; uint32_t tr_words;
-    if (job < n_block_jobs) {
-      const uint64_t blk = job / P.n_block_parts;          // global block index = inst * blocks_per_inst + r
-      cls = (uint32_t)(job - blk * P.n_block_parts);        // part of the block job
-      inst = blk / P.blocks_per_inst;
-      uint32_t r = (uint32_t)(blk - inst * P.blocks_per_inst);
-      uint32_t d = 0;
-      while (d + 1 < P.n_digests && r >= s_digests[d + 1].blk_prefix) d++;
-      const DevDigest& dd = s_digests[d];
-      uint32_t jb = r - dd.blk_prefix;
-      gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
-      lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
-      limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
-      tr_src = A.btrace + blk * (uint64_t)TR_BLOCK_WORDS;
-      tr_words = TR_BLOCK_WORDS;
-    } else {
-      uint64_t k = job - n_block_jobs;
-      inst = k / P.n_digests;
-      uint32_t d = (uint32_t)(k - inst * P.n_digests);
-      const DevDigest& dd = s_digests[d];
-      cls = dd.dp.job_class;
-      gate0 = 0; lk0 = 0; limb0 = 0;
-      tr_src = A.dtrace + inst * P.dtrace_words_per_inst + dd.dtrace_off;
-      tr_words = dd.dp.trace_words;
-    }
-    const JobClass jc = s_classes[cls];
-    for (uint32_t i = tid; i < tr_words; i += NT) s_trace[i] = tr_src[i];
-    __syncthreads();
-    // ---- phase 1: slot programs, lanes = unit instances ----
-    for (uint32_t t = warp; t < jc.n_tasks; t += NW) {
-      const WarpTask wt = s_tasks[jc.task_off + t];
-      const UnitGroup& g = s_groups[jc.group_off + wt.group];
-      const UnitType& ut = s_types[g.type];
-      uint32_t u = wt.first + lane;
-      if (u < g.count) run_unit_program(g, ut, u, s_prog, s_raw, s_trace, s_slots + g.slot_base + u * (ut.n_slots | 1u));
-    }
-    __syncthreads();
-    // ---- phase 2: one warp per (unit instance, chunk); fill the distinct values, then copy the cells out ----
+    return;
+  }
+
+  // =========================== consumer warp ===========================
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + P.off_scratch) + warp;
+  uint32_t finished = 0;   // bit st: producer st has run out of jobs
+  for (uint32_t k = 0; finished != (1u << NPROD) - 1u; k++) {
+    const int st = k % NPROD;
+    const uint32_t round = k / NPROD;
+    if (finished & (1u << st)) continue;
+    mbar_wait(&s_full[st], round & 1u);
+    const uint8_t* stage = smem + P.off_trace + (size_t)st * P.stage_bytes;
+    const uint64_t* s_slots = reinterpret_cast<const uint64_t*>(stage + P.stage_off_slots);
+    const StageDesc* desc = reinterpret_cast<const StageDesc*>(stage + P.stage_off_desc);
+    if (!desc->valid) { finished |= 1u << st; continue; }   // this producer has run out of jobs and exited
+    const uint64_t inst = desc->inst;
+    const uint32_t gate0 = desc->gate0, lk0 = desc->lk0, limb0 = desc->limb0;
+    const JobClass jc = s_classes[desc->cls];
     unsigned long long ck_g = 0, ck_l = 0, ck_s = 0;
     uint32_t* gate_out = A.gate ? A.gate + inst * P.gate_inst_cells * 8 : nullptr;
     uint32_t* lk_out = A.lookup ? A.lookup + inst * P.lookup_inst_cells * 8 : nullptr;
     uint32_t* sp_out = A.spread ? A.spread + inst * P.spread_inst_cells * 8 : nullptr;
-    for (uint32_t it = warp; it < jc.n_items; it += NW) {
+    for (uint32_t it = warp; it < jc.n_items; it += NCONS) {
       const uint32_t item = s_items[jc.item_off + it];
       const UnitGroup& g = s_groups[jc.group_off + H2SHA_ITEM_GROUP(item)];
       const UnitType& ut = s_types[g.type];
@@ -509,7 +562,7 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
       const Chunk ch = s_chunks[ut.chunk_off + H2SHA_ITEM_CHUNK(item)];
       const uint64_t* slots = s_slots + g.slot_base + u * (ut.n_slots | 1u);
       // fill
-      for (uint32_t i = lane; i < ch.n_fill; i += 32) fill_entry(s_fill[ch.fill_off + i], slots, s_table, s_table_h, &ws->val[i][0], &ws->h[i]);
+      for (uint32_t i = lane; i < ch.n_fill; i += 32) fill_entry(s_fill[ch.fill_off + i], slots, s_table, s_table_h, ws, i);
       __syncwarp();
       // gate cells
       if (ch.gate_len) {
@@ -518,13 +571,15 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
         while (c0 + 1 < P.n_breaks && s_breaks[c0 + 1] <= g_lo) c0++;
         const uint32_t next_brk = (c0 + 1 < P.n_breaks) ? s_breaks[c0 + 1] : 0xffffffffu;
         const uint32_t brk0 = s_breaks[c0];
+        const CellEntry* cells = s_cells + ch.gate_off;
+#pragma unroll 2
         for (uint32_t i = lane; i < ch.gate_len; i += 32) {
-          const CellEntry ce = s_cells[ch.gate_off + i];
-          uint32_t x[8];
-          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, x);
+          const CellEntry ce = cells[i];
+          uint4 lo, hi;
+          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, lo, hi);
           const uint32_t gidx = g_lo + H2SHA_CE_DST(ce);
           const uint32_t pos = (gidx >= next_brk) ? (c0 + 1) * P.gate_col_rows + (gidx - next_brk) : c0 * P.gate_col_rows + (gidx - brk0);
-          if (gate_out) store_cell(gate_out + (uint64_t)pos * 8, x);
+          if (gate_out) store_cell2(gate_out + (uint64_t)pos * 8, lo, hi);
           ck_g += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
@@ -533,12 +588,12 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
         const uint32_t l_lo = lk0 + g.lk_base + u * g.lk_stride;
         for (uint32_t i = lane; i < ch.lk_len; i += 32) {
           const CellEntry ce = s_cells[ch.lk_off + i];
-          uint32_t x[8];
-          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, x);
+          uint4 lo, hi;
+          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, lo, hi);
           const uint32_t li = l_lo + H2SHA_CE_DST(ce);
           const uint32_t col = li / P.max_rows, row = li - col * P.max_rows;
           const uint32_t pos = col * P.lookup_col_rows + row;
-          if (lk_out) store_cell(lk_out + (uint64_t)pos * 8, x);
+          if (lk_out) store_cell2(lk_out + (uint64_t)pos * 8, lo, hi);
           ck_l += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
@@ -547,18 +602,20 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
         const uint32_t m_lo = limb0 + g.limb_base + u * g.limb_stride;
         for (uint32_t i = lane; i < ch.limb_len; i += 32) {
           const CellEntry ce = s_cells[ch.limb_off + i];
-          uint32_t x[8];
-          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, x);
+          uint4 lo, hi;
+          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, lo, hi);
           const uint32_t n = m_lo + (H2SHA_CE_DST(ce) >> 1), which = H2SHA_CE_DST(ce) & 1u;
           const uint32_t row = n / P.spread_cols, col = n - row * P.spread_cols;
           const uint32_t pos = (which * P.spread_cols + col) * P.spread_rows + row;
-          if (sp_out) store_cell(sp_out + (uint64_t)pos * 8, x);
+          if (sp_out) store_cell2(sp_out + (uint64_t)pos * 8, lo, hi);
           ck_s += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
       __syncwarp();  // scratch is overwritten by the next item's fill
     }
-    // ---- checksums: warp reduce, CTA reduce in shared memory, one global atomic per kind ----
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[st]);   // this warp no longer reads the stage
+    // ---- checksums: warp reduce, one global atomic per kind and warp ----
     if (A.cks) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -566,12 +623,11 @@ __global__ void __launch_bounds__(NT, 2) k_expand(const DevPlan P, const JobArgs
         ck_l += __shfl_xor_sync(0xffffffffu, ck_l, o);
         ck_s += __shfl_xor_sync(0xffffffffu, ck_s, o);
       }
-      if (lane == 0) { atomicAdd(&s_misc->ck[0], ck_g); atomicAdd(&s_misc->ck[1], ck_l); atomicAdd(&s_misc->ck[2], ck_s); }
-      __syncthreads();
-      if (tid < 3) {
-        unsigned long long v = s_misc->ck[tid];
-        atomicAdd(&A.cks[inst * 4 + tid], v);
-        atomicAdd(&A.cks[inst * 4 + 3], v);
+      if (lane == 0) {
+        if (ck_g) atomicAdd(&A.cks[inst * 4 + 0], ck_g);
+        if (ck_l) atomicAdd(&A.cks[inst * 4 + 1], ck_l);
+        if (ck_s) atomicAdd(&A.cks[inst * 4 + 2], ck_s);
+        atomicAdd(&A.cks[inst * 4 + 3], ck_g + ck_l + ck_s);
       }
     }
   }
@@ -596,7 +652,8 @@ __global__ void k_zero_ranges(uint4* buf, uint64_t inst_cells, uint64_t n_inst, 
   }
 }
 
-constexpr int EXPAND_THREADS = 256;
+constexpr int EXPAND_NCONS = 16, EXPAND_NPROD = 4;
+constexpr int EXPAND_THREADS = (EXPAND_NCONS + EXPAND_NPROD) * 32;
 uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -766,10 +823,12 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.n_digests = (uint32_t)P.digests.size();
   D.n_block_parts = P.n_block_parts;
   D.off_trace = D.blob_bytes;
-  D.off_slots = align_up(D.off_trace + 4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
-  D.off_scratch = align_up(D.off_slots + 8 * (P.max_slots + 1), 16);
-  D.off_misc = align_up(D.off_scratch + (EXPAND_THREADS / 32) * (uint32_t)sizeof(WarpScratch), 16);
-  D.smem_bytes = D.off_misc + (uint32_t)sizeof(Misc);
+  D.stage_off_slots = align_up(4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
+  D.stage_off_desc = align_up(D.stage_off_slots + 8 * (P.max_slots + 1), 16);
+  D.stage_bytes = align_up(D.stage_off_desc + (uint32_t)sizeof(StageDesc), 16);
+  D.off_scratch = D.off_trace + EXPAND_NPROD * D.stage_bytes;
+  D.off_misc = align_up(D.off_scratch + EXPAND_NCONS * (uint32_t)sizeof(WarpScratch), 16);
+  D.smem_bytes = D.off_misc + 2 * EXPAND_NPROD * 8;
   if (D.smem_bytes > 227 * 1024) { delete e; return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory"); }
   D.max_rows = pc.max_rows; D.spread_cols = pc.spread_cols;
   D.n_gate_cols = P.n_gate_cols; D.gate_col_rows = P.gate_col_rows;
@@ -793,9 +852,9 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
       CUDA_TRY(cudaMemcpy(e->d_zero_ranges[b], rr.data(), rr.size() * 4, cudaMemcpyHostToDevice));
     }
   }
-  CUDA_TRY(cudaFuncSetAttribute(k_expand<EXPAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_expand<EXPAND_NCONS, EXPAND_NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand<EXPAND_THREADS>, EXPAND_THREADS, D.smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand<EXPAND_NCONS, EXPAND_NPROD>, EXPAND_THREADS, D.smem_bytes));
   if (occ < 1) { delete e; return set_err(H2SHA_ECUDA, "expand kernel does not fit on an SM"); }
   e->expand_ctas = occ * e->n_sms;
   *out = e;
@@ -935,7 +994,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     uint64_t n_jobs = b->n_instances * ((uint64_t)e->blocks_per_inst * P.n_block_parts + D);
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
-    k_expand<EXPAND_THREADS><<<grid, EXPAND_THREADS, e->dplan.smem_bytes, st>>>(e->dplan, ja);
+    k_expand<EXPAND_NCONS, EXPAND_NPROD><<<grid, EXPAND_THREADS, e->dplan.smem_bytes, st>>>(e->dplan, ja);
     launches++;
     CUDA_TRY(cudaGetLastError());
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[3], st));
