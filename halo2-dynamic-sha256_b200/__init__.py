@@ -29,7 +29,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape",
-    "h2sha_digest_batch", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
+    "h2sha_digest_batch", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
 
@@ -87,6 +87,7 @@ def load_library():
     L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
     L.h2sha_zero_outputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.h2sha_debug_mont_from_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.h2sha_debug_mont_from_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.h2sha_last_launch_count.argtypes = [C.c_void_p]
     L.h2sha_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L
@@ -310,13 +311,13 @@ class Sha256DynamicConfig:
     def launches_last_batch(self) -> int:
         return int(load_library().h2sha_last_launch_count(self._h))
 
-    def mont_from_u64(self, vals: np.ndarray) -> np.ndarray:
-        """Test hook: device Montgomery conversion of raw u64 values -> [n,4] u64."""
+    def mont_from_u64(self, vals: np.ndarray, path32: bool = False) -> np.ndarray:
+        """Test hook: device Montgomery conversion of raw u64 values -> [n,4] u64 (path32: the < 2^32 fast path)."""
         import torch
         dev = torch.device("cuda", self.device)
         v = torch.from_numpy(vals.astype(np.uint64).view(np.int64)).to(dev)
         out = torch.empty((v.numel(), 4), dtype=torch.int64, device=dev)
-        _check(load_library().h2sha_debug_mont_from_u64(self._h, v.data_ptr(), out.data_ptr(), v.numel(),
-                                                       torch.cuda.current_stream(self.device).cuda_stream))
+        fn = load_library().h2sha_debug_mont_from_u32 if path32 else load_library().h2sha_debug_mont_from_u64
+        _check(fn(self._h, v.data_ptr(), out.data_ptr(), v.numel(), torch.cuda.current_stream(self.device).cuda_stream))
         torch.cuda.current_stream(self.device).synchronize()
         return out.cpu().numpy().view(np.uint64)

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,13 +52,15 @@ struct DevPlan {
   const uint8_t* blob;
   uint32_t blob_bytes;
   // byte offsets inside the blob (all 16-byte aligned)
-  uint32_t off_fill, off_cells, off_chunks, off_items, off_table, off_table_h, off_prog, off_groups, off_tasks, off_types, off_classes,
+  uint32_t off_fill, off_cells, off_chunks, off_items, off_table_lo, off_table_hi, off_table_h, off_prog, off_groups, off_tasks, off_types, off_classes,
       off_raw, off_breaks, off_digests;
   uint32_t n_breaks, n_digests, n_block_parts;
   // dynamic shared memory layout after the blob
   uint32_t off_trace, off_scratch, off_misc, smem_bytes;
   uint32_t stage_bytes, stage_off_slots, stage_off_desc;   // per producer warp: trace | slots | StageDesc
+  uint32_t max_fill, scratch_bytes;                        // per consumer warp: lo[max_fill] | hi[max_fill] | h[max_fill]
   // layout
+  int32_t spread_cols_shift;   // log2(spread_cols) when it is a power of two, else -1
   uint32_t max_rows, spread_cols, n_gate_cols, gate_col_rows, n_lookup_cols, lookup_col_rows, spread_rows;
   uint32_t blocks_per_inst, dtrace_words_per_inst;
   uint64_t gate_inst_cells, lookup_inst_cells, spread_inst_cells;
@@ -89,6 +92,8 @@ struct FrConsts {
   uint64_t p[4];    // modulus
   uint64_t r1[4];   // 2^256 mod p  (Montgomery form of 1)
   uint64_t mu;      // floor(2^317 / p)
+  uint32_t mu32;    // floor(2^285 / p)
+  uint32_t pad;
 };
 __constant__ FrConsts c_fr;
 
@@ -159,6 +164,66 @@ __device__ __forceinline__ void fr_negate(uint64_t r[4]) {
       : "=l"(s0), "=l"(s1), "=l"(s2), "=l"(s3)
       : "l"(c_fr.p[0]), "l"(c_fr.p[1]), "l"(c_fr.p[2]), "l"(c_fr.p[3]), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]));
   r[0] = s0; r[1] = s1; r[2] = s2; r[3] = s3;
+}
+
+// Same conversion for v < 2^32: 32x256 multiply, 32-bit quotient estimate q_hat = ((P >> 254) * floor(2^285/p)) >> 31
+// (q_hat in {q-2, q-1, q}), r = P - q_hat * p, two conditional subtractions.  About half the work of the 64-bit path.
+__device__ __forceinline__ void mont_from_u32(uint32_t v, uint32_t x[8]) {
+  const uint32_t* R = reinterpret_cast<const uint32_t*>(c_fr.r1);
+  const uint32_t* PM = reinterpret_cast<const uint32_t*>(c_fr.p);
+  uint32_t pl[9];
+  uint64_t t = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    t = (uint64_t)v * R[k] + (t >> 32);
+    pl[k] = (uint32_t)t;
+  }
+  pl[8] = (uint32_t)(t >> 32);
+  const uint32_t ph = (pl[7] >> 30) | (pl[8] << 2);
+  const uint32_t q = (uint32_t)(((uint64_t)ph * c_fr.mu32) >> 31);
+  // r = P - q * p over the low 256 bits
+  uint32_t r[8];
+  uint64_t c = 0;       // carry of q * p
+  uint32_t borrow = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    c = (uint64_t)q * PM[k] + (c >> 32);
+    const uint32_t m = (uint32_t)c;
+    const uint64_t d = (uint64_t)pl[k] - m - borrow;
+    r[k] = (uint32_t)d;
+    borrow = (uint32_t)(d >> 63);
+  }
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    uint32_t s[8];
+    uint32_t b = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint64_t d = (uint64_t)r[k] - PM[k] - b;
+      s[k] = (uint32_t)d;
+      b = (uint32_t)(d >> 63);
+    }
+    if (b == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) r[k] = s[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = r[k];
+}
+__device__ __forceinline__ void fr_negate32(uint32_t x[8]) {
+  const uint32_t* PM = reinterpret_cast<const uint32_t*>(c_fr.p);
+  uint32_t any = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) any |= x[k];
+  if (!any) return;
+  uint32_t b = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint64_t d = (uint64_t)PM[k] - x[k] - b;
+    x[k] = (uint32_t)d;
+    b = (uint32_t)(d >> 63);
+  }
 }
 
 // bit i -> bit 2i of the low 32 bits
@@ -307,10 +372,10 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
 // ---------------------------------------------------------------------------------------------------
 // per-consumer-warp scratch of phase 2: Montgomery values of the chunk's distinct non-constant cells (low / high
 // 16 bytes in separate arrays so that random 128-bit reads spread over all bank groups) + their checksum hashes
-struct WarpScratch {
-  uint4 lo[H2SHA_MAX_FILL];
-  uint4 hi[H2SHA_MAX_FILL];
-  uint32_t h[H2SHA_MAX_FILL];
+struct WarpScratch {   // runtime-sized: lo[max_fill] | hi[max_fill] | h[max_fill]
+  uint4* lo;
+  uint4* hi;
+  uint32_t* h;
 };
 // job descriptor a producer warp leaves in its stage
 struct StageDesc {
@@ -386,20 +451,31 @@ __device__ __forceinline__ uint32_t cell_hash(const uint32_t x[8]) {
   return h;
 }
 
-// fill phase: Fr value (+ hash) of one distinct value of the chunk -> warp scratch entry i
-__device__ __forceinline__ void fill_entry(const TmplEntry e, const uint64_t* slots, const uint4* table, const uint32_t* table_h,
-                                           WarpScratch* ws, uint32_t i) {
-  const uint32_t kind = H2SHA_TE_KIND(e);
+// fill phase: the chunk's distinct values -> warp scratch.  Three warp-uniform loops over the sorted fill list.
+__device__ __forceinline__ void fill_table(const TmplEntry e, const uint64_t* slots, const uint4* table_lo, const uint4* table_hi,
+                                           const uint32_t* table_h, const WarpScratch& ws) {
+  const uint32_t i = H2SHA_TE_DST(e);
   const uint64_t s = slots[H2SHA_TE_SLOT(e)];
-  if (kind == KIND_TABLE) {
-    const uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
-    ws->lo[i] = table[2 * idx]; ws->hi[i] = table[2 * idx + 1];
-    ws->h[i] = table_h[idx];
-    return;
-  }
+  const uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
+  ws.lo[i] = table_lo[idx]; ws.hi[i] = table_hi[idx];
+  ws.h[i] = table_h[idx];
+}
+__device__ __forceinline__ void fill_gen32(const TmplEntry e, const uint64_t* slots, const WarpScratch& ws) {
+  const uint32_t i = H2SHA_TE_DST(e);
+  const uint64_t s = slots[H2SHA_TE_SLOT(e)];
+  const uint32_t v = (uint32_t)(extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e)) << H2SHA_TE_SHL(e));
+  uint32_t x[8];
+  mont_from_u32(v, x);
+  if (H2SHA_TE_NEG(e)) fr_negate32(x);
+  ws.lo[i] = make_uint4(x[0], x[1], x[2], x[3]); ws.hi[i] = make_uint4(x[4], x[5], x[6], x[7]);
+  ws.h[i] = cell_hash(x);
+}
+__device__ __forceinline__ void fill_gen64(const TmplEntry e, const uint64_t* slots, const WarpScratch& ws) {
+  const uint32_t i = H2SHA_TE_DST(e);
+  const uint64_t s = slots[H2SHA_TE_SLOT(e)];
   bool neg = H2SHA_TE_NEG(e);
   uint64_t v;
-  if (kind == KIND_SIGNED) {
+  if (H2SHA_TE_KIND(e) == KIND_SIGNED) {
     int64_t sv = (int64_t)s;
     neg = sv < 0;
     v = neg ? (uint64_t)(-sv) : (uint64_t)sv;
@@ -411,17 +487,10 @@ __device__ __forceinline__ void fill_entry(const TmplEntry e, const uint64_t* sl
   if (neg) fr_negate(r);
   uint32_t x[8] = {(uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32),
                    (uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32)};
-  ws->lo[i] = make_uint4(x[0], x[1], x[2], x[3]); ws->hi[i] = make_uint4(x[4], x[5], x[6], x[7]);
-  ws->h[i] = cell_hash(x);
+  ws.lo[i] = make_uint4(x[0], x[1], x[2], x[3]); ws.hi[i] = make_uint4(x[4], x[5], x[6], x[7]);
+  ws.h[i] = cell_hash(x);
 }
 
-// copy phase: source of a cell (static constant or warp scratch) -> registers + hash
-__device__ __forceinline__ uint32_t load_cell(uint32_t src, const uint4* table, const uint32_t* table_h, const WarpScratch* ws, uint4& lo, uint4& hi) {
-  const uint32_t idx = src & (H2SHA_SCRATCH_FLAG - 1);
-  if (src & H2SHA_SCRATCH_FLAG) { lo = ws->lo[idx]; hi = ws->hi[idx]; return ws->h[idx]; }
-  lo = table[2 * idx]; hi = table[2 * idx + 1];
-  return table_h[idx];
-}
 // one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
 __device__ __forceinline__ void store_cell2(uint32_t* p, const uint4& lo, const uint4& hi) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
@@ -446,8 +515,9 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
   const TmplEntry* s_fill = reinterpret_cast<const TmplEntry*>(smem + P.off_fill);
   const CellEntry* s_cells = reinterpret_cast<const CellEntry*>(smem + P.off_cells);
   const Chunk* s_chunks = reinterpret_cast<const Chunk*>(smem + P.off_chunks);
-  const uint32_t* s_items = reinterpret_cast<const uint32_t*>(smem + P.off_items);
-  const uint4* s_table = reinterpret_cast<const uint4*>(smem + P.off_table);
+  const ItemDesc* s_items = reinterpret_cast<const ItemDesc*>(smem + P.off_items);
+  const uint4* s_table_lo = reinterpret_cast<const uint4*>(smem + P.off_table_lo);
+  const uint4* s_table_hi = reinterpret_cast<const uint4*>(smem + P.off_table_hi);
   const uint32_t* s_table_h = reinterpret_cast<const uint32_t*>(smem + P.off_table_h);
   const VmIns* s_prog = reinterpret_cast<const VmIns*>(smem + P.off_prog);
   const UnitGroup* s_groups = reinterpret_cast<const UnitGroup*>(smem + P.off_groups);
@@ -536,7 +606,13 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
   }
 
   // =========================== consumer warp ===========================
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + P.off_scratch) + warp;
+  WarpScratch ws;
+  {
+    uint8_t* base = smem + P.off_scratch + (size_t)warp * P.scratch_bytes;
+    ws.lo = reinterpret_cast<uint4*>(base);
+    ws.hi = ws.lo + P.max_fill;
+    ws.h = reinterpret_cast<uint32_t*>(ws.hi + P.max_fill);
+  }
   uint32_t finished = 0;   // bit st: producer st has run out of jobs
   for (uint32_t k = 0; finished != (1u << NPROD) - 1u; k++) {
     const int st = k % NPROD;
@@ -554,58 +630,76 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     uint32_t* gate_out = A.gate ? A.gate + inst * P.gate_inst_cells * 8 : nullptr;
     uint32_t* lk_out = A.lookup ? A.lookup + inst * P.lookup_inst_cells * 8 : nullptr;
     uint32_t* sp_out = A.spread ? A.spread + inst * P.spread_inst_cells * 8 : nullptr;
-    for (uint32_t it = warp; it < jc.n_items; it += NCONS) {
-      const uint32_t item = s_items[jc.item_off + it];
-      const UnitGroup& g = s_groups[jc.group_off + H2SHA_ITEM_GROUP(item)];
-      const UnitType& ut = s_types[g.type];
-      const uint32_t u = H2SHA_ITEM_UNIT(item);
-      const Chunk ch = s_chunks[ut.chunk_off + H2SHA_ITEM_CHUNK(item)];
-      const uint64_t* slots = s_slots + g.slot_base + u * (ut.n_slots | 1u);
-      // fill
-      for (uint32_t i = lane; i < ch.n_fill; i += 32) fill_entry(s_fill[ch.fill_off + i], slots, s_table, s_table_h, ws, i);
+    // static item -> warp assignment, rotated per job so that the heavier leading items do not always hit the same warps
+    for (uint32_t it = (uint32_t)(warp + k) % NCONS; it < jc.n_items; it += NCONS) {
+      const ItemDesc item = s_items[jc.item_off + it];
+      const Chunk ch = s_chunks[item.chunk];
+      const uint64_t* slots = s_slots + item.slot_off;
+      // ---- fill: table copies | Barrett < 2^32 | Barrett 64-bit / signed ----
+      {
+        const TmplEntry* fl = s_fill + ch.fill_off;
+        const uint32_t n_tab = ch.n_fill_table, n_32 = n_tab + ch.n_fill32, n_all = ch.n_fill;
+        for (uint32_t i = lane; i < n_tab; i += 32) fill_table(fl[i], slots, s_table_lo, s_table_hi, s_table_h, ws);
+        for (uint32_t i = n_tab + lane; i < n_32; i += 32) fill_gen32(fl[i], slots, ws);
+        for (uint32_t i = n_32 + lane; i < n_all; i += 32) fill_gen64(fl[i], slots, ws);
+      }
       __syncwarp();
-      // gate cells
+      // ---- copy: gate cells ----
       if (ch.gate_len) {
-        const uint32_t g_lo = gate0 + g.gate_base + u * g.gate_stride;   // instance-relative gate-stream index of the unit's first cell
+        const uint32_t g_lo = gate0 + item.gate_rel;   // instance-relative gate-stream index of the unit's first cell
         uint32_t c0 = 0;
         while (c0 + 1 < P.n_breaks && s_breaks[c0 + 1] <= g_lo) c0++;
         const uint32_t next_brk = (c0 + 1 < P.n_breaks) ? s_breaks[c0 + 1] : 0xffffffffu;
-        const uint32_t brk0 = s_breaks[c0];
+        // pos = gidx + off0 before the break, gidx + off1 from the break on
+        const uint32_t off0 = c0 * P.gate_col_rows - s_breaks[c0];
+        const uint32_t off1 = (c0 + 1) * P.gate_col_rows - next_brk;
         const CellEntry* cells = s_cells + ch.gate_off;
-#pragma unroll 2
+#pragma unroll 4
         for (uint32_t i = lane; i < ch.gate_len; i += 32) {
           const CellEntry ce = cells[i];
-          uint4 lo, hi;
-          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, lo, hi);
+          const uint32_t src = H2SHA_CE_SRC(ce);
+          const uint4 lo = ws.lo[src], hi = ws.hi[src];
+          const uint32_t h = ws.h[src];
           const uint32_t gidx = g_lo + H2SHA_CE_DST(ce);
-          const uint32_t pos = (gidx >= next_brk) ? (c0 + 1) * P.gate_col_rows + (gidx - next_brk) : c0 * P.gate_col_rows + (gidx - brk0);
+          const uint32_t pos = gidx + ((gidx >= next_brk) ? off1 : off0);
           if (gate_out) store_cell2(gate_out + (uint64_t)pos * 8, lo, hi);
           ck_g += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
-      // lookup-column cells (range.finalize copies cells_to_lookup in push order, wrapping at max_rows)
+      // ---- lookup-column cells (range.finalize copies cells_to_lookup in push order, wrapping at max_rows) ----
       if (ch.lk_len) {
-        const uint32_t l_lo = lk0 + g.lk_base + u * g.lk_stride;
+        const uint32_t l_lo = lk0 + item.lk_rel;
+        // pos = li + off0 before the column wrap at `wrap`, li + off1 after it (no division in the loop)
+        uint32_t off0 = 0, off1 = 0, wrap = 0xffffffffu;
+        if (P.n_lookup_cols > 1) {
+          const uint32_t col0 = l_lo / P.max_rows;
+          wrap = (col0 + 1) * P.max_rows;
+          off0 = col0 * (P.lookup_col_rows - P.max_rows);
+          off1 = (col0 + 1) * (P.lookup_col_rows - P.max_rows);
+        }
         for (uint32_t i = lane; i < ch.lk_len; i += 32) {
           const CellEntry ce = s_cells[ch.lk_off + i];
-          uint4 lo, hi;
-          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, lo, hi);
+          const uint32_t src = H2SHA_CE_SRC(ce);
+          const uint4 lo = ws.lo[src], hi = ws.hi[src];
+          const uint32_t h = ws.h[src];
           const uint32_t li = l_lo + H2SHA_CE_DST(ce);
-          const uint32_t col = li / P.max_rows, row = li - col * P.max_rows;
-          const uint32_t pos = col * P.lookup_col_rows + row;
+          const uint32_t pos = li + ((li >= wrap) ? off1 : off0);
           if (lk_out) store_cell2(lk_out + (uint64_t)pos * 8, lo, hi);
           ck_l += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
         }
       }
-      // spread-table columns: limb n -> column n % cols, row n / cols (spread.rs:202,228-231); dense then spread
+      // ---- spread-table columns: limb n -> column n % cols, row n / cols (spread.rs:202,228-231); dense then spread ----
       if (ch.limb_len) {
-        const uint32_t m_lo = limb0 + g.limb_base + u * g.limb_stride;
+        const uint32_t m_lo = limb0 + item.limb_rel;
         for (uint32_t i = lane; i < ch.limb_len; i += 32) {
           const CellEntry ce = s_cells[ch.limb_off + i];
-          uint4 lo, hi;
-          const uint32_t h = load_cell(H2SHA_CE_SRC(ce), s_table, s_table_h, ws, lo, hi);
+          const uint32_t src = H2SHA_CE_SRC(ce);
+          const uint4 lo = ws.lo[src], hi = ws.hi[src];
+          const uint32_t h = ws.h[src];
           const uint32_t n = m_lo + (H2SHA_CE_DST(ce) >> 1), which = H2SHA_CE_DST(ce) & 1u;
-          const uint32_t row = n / P.spread_cols, col = n - row * P.spread_cols;
+          uint32_t row, col;
+          if (P.spread_cols_shift >= 0) { row = n >> P.spread_cols_shift; col = n & (P.spread_cols - 1u); }
+          else { row = n / P.spread_cols; col = n - row * P.spread_cols; }
           const uint32_t pos = (which * P.spread_cols + col) * P.spread_rows + row;
           if (sp_out) store_cell2(sp_out + (uint64_t)pos * 8, lo, hi);
           ck_s += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
@@ -641,6 +735,14 @@ __global__ void k_mont_debug(const uint64_t* vals, uint64_t* out, uint64_t n) {
   out[4 * i] = r[0]; out[4 * i + 1] = r[1]; out[4 * i + 2] = r[2]; out[4 * i + 3] = r[3];
 }
 
+__global__ void k_mont_debug32(const uint64_t* vals, uint64_t* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x[8];
+  mont_from_u32((uint32_t)vals[i], x);
+  for (int k = 0; k < 4; k++) out[4 * i + k] = (uint64_t)x[2 * k] | ((uint64_t)x[2 * k + 1] << 32);
+}
+
 __global__ void k_zero_ranges(uint4* buf, uint64_t inst_cells, uint64_t n_inst, const uint32_t* ranges /*pos,count pairs*/, uint32_t n_ranges) {
   // grid.y = instance, grid.x strides over the cells of all ranges
   uint64_t inst = blockIdx.y;
@@ -652,8 +754,27 @@ __global__ void k_zero_ranges(uint4* buf, uint64_t inst_cells, uint64_t n_inst, 
   }
 }
 
-constexpr int EXPAND_NCONS = 16, EXPAND_NPROD = 4;
-constexpr int EXPAND_THREADS = (EXPAND_NCONS + EXPAND_NPROD) * 32;
+// launch variants (consumer warps, producer warps); selected at engine creation (H2SHA_TUNE "cons=..,prod=..")
+struct ExpandVariant {
+  int ncons, nprod;
+  const void* fn;
+};
+template <int NC, int NP>
+ExpandVariant make_variant() { return ExpandVariant{NC, NP, (const void*)k_expand<NC, NP>}; }
+const ExpandVariant* expand_variants(int* n) {
+  static const ExpandVariant v[] = {make_variant<16, 4>(), make_variant<12, 4>(), make_variant<20, 4>(), make_variant<24, 4>(), make_variant<16, 2>(),
+                                    make_variant<20, 2>(), make_variant<24, 6>(), make_variant<8, 2>(), make_variant<8, 4>()};
+  *n = (int)(sizeof v / sizeof v[0]);
+  return v;
+}
+int tune_value(const char* key, int dflt) {
+  const char* t = getenv("H2SHA_TUNE");
+  if (!t) return dflt;
+  std::string s(t), k = std::string(key) + "=";
+  size_t p = s.find(k);
+  if (p == std::string::npos) return dflt;
+  return atoi(s.c_str() + p + k.size());
+}
 uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -684,6 +805,7 @@ struct h2sha_engine {
   uint32_t blocks_per_inst = 0, dtrace_words_per_inst = 0;
   int last_launches = 0;
   int expand_ctas = 0;
+  ExpandVariant variant{};
   uint64_t resident_instances = 0;   // instances whose inputs are in the workspace (reuse_inputs)
   bool resident_has_pre = false;
   const uint8_t* resident_msgs = nullptr;
@@ -750,6 +872,8 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   pc.is_input_range_check = cfg->is_input_range_check ? 1 : 0;
   pc.record_shape = cfg->build_shape ? 1 : 0;
   if (cfg->block_parts) pc.block_parts = cfg->block_parts;
+  pc.block_parts = (uint32_t)tune_value("parts", (int)pc.block_parts);
+  pc.max_fill = (uint32_t)tune_value("fill", (int)pc.max_fill);
   h2sha_engine* e = new h2sha_engine();
   std::string err;
   if (!build_plan(pc, &e->plan, &err)) { delete e; return set_err(H2SHA_EINVAL, err); }
@@ -774,6 +898,8 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   U256 r1 = fr::mont_r();
   memcpy(fc.r1, r1.l, 32);
   fc.mu = fr::floor_pow2_div_p(317);
+  fc.mu32 = (uint32_t)fr::floor_pow2_div_p(285);
+  fc.pad = 0;
   CUDA_TRY(cudaMemcpyToSymbol(c_fr, &fc, sizeof fc));
 
   // ---- per-digest device info ----
@@ -798,8 +924,16 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.off_fill = put(P.fill.data(), P.fill.size() * sizeof(TmplEntry));
   D.off_cells = put(P.cells.data(), P.cells.size() * sizeof(CellEntry));
   D.off_chunks = put(P.chunks.data(), P.chunks.size() * sizeof(Chunk));
-  D.off_items = put(P.items.data(), P.items.size() * 4);
-  D.off_table = put(P.mont_table.data(), P.mont_table.size() * 32);
+  D.off_items = put(P.items.data(), P.items.size() * sizeof(ItemDesc));
+  {
+    std::vector<uint64_t> lo(2 * P.mont_table.size()), hi(2 * P.mont_table.size());
+    for (size_t i = 0; i < P.mont_table.size(); i++) {
+      lo[2 * i] = P.mont_table[i].l[0]; lo[2 * i + 1] = P.mont_table[i].l[1];
+      hi[2 * i] = P.mont_table[i].l[2]; hi[2 * i + 1] = P.mont_table[i].l[3];
+    }
+    D.off_table_lo = put(lo.data(), lo.size() * 8);
+    D.off_table_hi = put(hi.data(), hi.size() * 8);
+  }
   {
     std::vector<uint32_t> th(P.mont_table.size());
     for (size_t i = 0; i < th.size(); i++) {
@@ -826,11 +960,24 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.stage_off_slots = align_up(4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
   D.stage_off_desc = align_up(D.stage_off_slots + 8 * (P.max_slots + 1), 16);
   D.stage_bytes = align_up(D.stage_off_desc + (uint32_t)sizeof(StageDesc), 16);
-  D.off_scratch = D.off_trace + EXPAND_NPROD * D.stage_bytes;
-  D.off_misc = align_up(D.off_scratch + EXPAND_NCONS * (uint32_t)sizeof(WarpScratch), 16);
-  D.smem_bytes = D.off_misc + 2 * EXPAND_NPROD * 8;
+  {
+    int nv = 0;
+    const ExpandVariant* vs = expand_variants(&nv);
+    const int want_c = tune_value("cons", 20), want_p = tune_value("prod", 4);
+    e->variant = vs[0];
+    bool found = false;
+    for (int i = 0; i < nv; i++) if (vs[i].ncons == want_c && vs[i].nprod == want_p) { e->variant = vs[i]; found = true; }
+    if (!found) { delete e; return set_err(H2SHA_EINVAL, "H2SHA_TUNE: no such (cons, prod) launch variant"); }
+  }
+  D.max_fill = pc.max_fill;
+  D.scratch_bytes = pc.max_fill * 36;
+  D.off_scratch = D.off_trace + e->variant.nprod * D.stage_bytes;
+  D.off_misc = align_up(D.off_scratch + e->variant.ncons * D.scratch_bytes, 16);
+  D.smem_bytes = D.off_misc + 2 * e->variant.nprod * 8;
   if (D.smem_bytes > 227 * 1024) { delete e; return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory"); }
   D.max_rows = pc.max_rows; D.spread_cols = pc.spread_cols;
+  D.spread_cols_shift = -1;
+  for (int sh = 0; sh < 16; sh++) if ((1u << sh) == pc.spread_cols) D.spread_cols_shift = sh;
   D.n_gate_cols = P.n_gate_cols; D.gate_col_rows = P.gate_col_rows;
   D.n_lookup_cols = P.n_lookup_cols; D.lookup_col_rows = P.lookup_col_rows; D.spread_rows = P.spread_rows;
   D.blocks_per_inst = bp; D.dtrace_words_per_inst = dw;
@@ -852,9 +999,10 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
       CUDA_TRY(cudaMemcpy(e->d_zero_ranges[b], rr.data(), rr.size() * 4, cudaMemcpyHostToDevice));
     }
   }
-  CUDA_TRY(cudaFuncSetAttribute(k_expand<EXPAND_NCONS, EXPAND_NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
+  const int expand_threads = (e->variant.ncons + e->variant.nprod) * 32;
+  CUDA_TRY(cudaFuncSetAttribute(e->variant.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_expand<EXPAND_NCONS, EXPAND_NPROD>, EXPAND_THREADS, D.smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e->variant.fn, expand_threads, D.smem_bytes));
   if (occ < 1) { delete e; return set_err(H2SHA_ECUDA, "expand kernel does not fit on an SM"); }
   e->expand_ctas = occ * e->n_sms;
   *out = e;
@@ -994,7 +1142,10 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     uint64_t n_jobs = b->n_instances * ((uint64_t)e->blocks_per_inst * P.n_block_parts + D);
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
-    k_expand<EXPAND_NCONS, EXPAND_NPROD><<<grid, EXPAND_THREADS, e->dplan.smem_bytes, st>>>(e->dplan, ja);
+    {
+      void* args[2] = {(void*)&e->dplan, (void*)&ja};
+      CUDA_TRY(cudaLaunchKernel(e->variant.fn, dim3(grid), dim3((e->variant.ncons + e->variant.nprod) * 32), args, e->dplan.smem_bytes, st));
+    }
     launches++;
     CUDA_TRY(cudaGetLastError());
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[3], st));
@@ -1033,6 +1184,16 @@ int h2sha_debug_mont_from_u64(h2sha_engine_t* e, const uint64_t* vals_dev, uint6
   CUDA_TRY(cudaSetDevice(e->device));
   if (n == 0) return H2SHA_OK;
   k_mont_debug<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals_dev, out_dev, n);
+  CUDA_TRY(cudaGetLastError());
+  return H2SHA_OK;
+}
+
+int h2sha_debug_mont_from_u32(h2sha_engine_t* e, const uint64_t* vals_dev, uint64_t* out_dev, uint64_t n, void* stream) {
+  if (!e) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (n == 0) return H2SHA_OK;
+  k_mont_debug32<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals_dev, out_dev, n);
   CUDA_TRY(cudaGetLastError());
   return H2SHA_OK;
 }

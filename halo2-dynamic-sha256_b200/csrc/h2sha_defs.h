@@ -68,23 +68,24 @@ static inline uint32_t vm_operand_const(uint32_t idx) { return 1u | (idx << 1); 
 
 // ---------------------------------------------------------------------------------------------
 // Phase 2 works chunk by chunk (a chunk = up to a few hundred consecutive cells of one unit):
-//   fill:  every DISTINCT non-constant value of the chunk is converted once (TmplEntry, `dst` unused) into the
-//          warp's scratch table: KIND_TABLE entries are copied from the static Montgomery table, the others go
-//          through the Barrett conversion; entries are sorted TABLE | GENERIC <= 32 bit | GENERIC > 32 bit / SIGNED;
-//   copy:  every cell is a 32-byte copy  scratch-or-constant -> its (column,row)  (CellEntry).
+//   fill:  every DISTINCT value of the chunk is materialised once (TmplEntry, `dst` = scratch slot) in the warp's scratch
+//          table: KIND_TABLE entries (constants, 8-bit limbs, spread limbs, inverses) are copied from the static
+//          Montgomery table, the others go through the Barrett conversion; entries are sorted
+//          TABLE | GENERIC <= 32 bit | GENERIC > 32 bit / SIGNED;
+//   copy:  every cell is a 32-byte copy  scratch[src] -> its (column,row)  (CellEntry).
 // ---------------------------------------------------------------------------------------------
 struct CellEntry {
-  uint32_t v;  // src (16) | dst (16).  src bit 15 set: warp scratch index (src & 0x7fff); else static table index.
+  uint32_t v;  // src (16) | dst (16).  src = index into the warp's scratch table
 };
 #define H2SHA_CE_SRC(e) ((e).v & 0xffffu)
 #define H2SHA_CE_DST(e) ((e).v >> 16)
-enum { H2SHA_SCRATCH_FLAG = 0x8000, H2SHA_MAX_FILL = 128 };
+enum { H2SHA_MAX_FILL_LIMIT = 256 };   // the actual limit is Config::max_fill (runtime, <= this)
 
 struct Chunk {
   uint32_t fill_off;   // TmplEntry index
-  uint16_t n_fill, n_fill_table;
+  uint16_t n_fill, n_fill_table;   // total distinct values; the first n_fill_table are table copies
   uint32_t gate_off;   // CellEntry index; dst = gate-stream offset inside the unit
-  uint16_t gate_len, pad0;
+  uint16_t gate_len, n_fill32;     // n_fill32: Barrett entries known to be < 2^32 (they follow the table copies)
   uint32_t lk_off;     // dst = lookup index inside the unit
   uint16_t lk_len, pad1;
   uint32_t limb_off;   // dst = (limb index inside the unit) << 1 | (0 dense, 1 spread)
@@ -122,11 +123,15 @@ struct WarpTask {
   uint32_t group, first;
 };
 
-// Work item of phase 2: one chunk of one unit instance.  group (8) | instance (12) | chunk (12)
-#define H2SHA_ITEM(g, u, c) (((uint32_t)(g) << 24) | ((uint32_t)(u) << 12) | (uint32_t)(c))
-#define H2SHA_ITEM_GROUP(x) ((x) >> 24)
-#define H2SHA_ITEM_UNIT(x) (((x) >> 12) & 0xfffu)
-#define H2SHA_ITEM_CHUNK(x) ((x) & 0xfffu)
+// Work item of phase 2: one chunk of one unit instance, with everything that does not depend on the job precomputed.
+struct ItemDesc {
+  uint32_t slot_off;   // offset (u64 units) of the unit instance's slots in the job's slot area
+  uint32_t gate_rel;   // gate-stream index of the unit's first cell, relative to the job's gate base
+  uint32_t lk_rel;     // same for the lookup stream
+  uint32_t limb_rel;   // same for spread limbs
+  uint32_t chunk;      // Chunk index
+  uint32_t pad[3];
+};
 
 // A job class: (a part of) the block job (one sha256_compression) or the per-digest prologue/epilogue job.
 struct JobClass {

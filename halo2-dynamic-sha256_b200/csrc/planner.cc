@@ -100,6 +100,7 @@ class Builder {
     if (cfg_.spread_cols == 0) fail("num_advice_columns must be >= 1");
     if (cfg_.lookup_bits < 8 || cfg_.lookup_bits > 32) fail("lookup_bits must be in [8, 32]");
     if (cfg_.max_rows < 64) fail("max_rows too small");
+    if (cfg_.max_fill < 64 || cfg_.max_fill > H2SHA_MAX_FILL_LIMIT || cfg_.max_fill % 8) fail("max_fill must be a multiple of 8 in [64, 256]");
     uint32_t max_r = 0;
     for (uint32_t m : cfg_.max_variable_byte_sizes) {
       if (m == 0 || m % 64 != 0) fail("max_variable_byte_size must be a positive multiple of 64 (lib.rs:57-59)");
@@ -895,7 +896,7 @@ class Builder {
       case T_INV: tbl = P_->tb_inv + s.tbl_off; break;
     }
     if (s.table == T_SBYTE && s.w > cfg_.limb_bits) fail("spread-table index wider than a limb");
-    if (tbl >= H2SHA_SCRATCH_FLAG) fail("static table too large");
+    if (tbl > 0xffff) fail("static table too large");
     return tbl;
   }
   // sort class of a fill entry: table copies, then <= 32-bit Barrett, then the full 64-bit / signed path
@@ -909,8 +910,21 @@ class Builder {
            ((uint64_t)s.shl << 24) | ((uint64_t)s.table << 29) | ((uint64_t)s.tbl_off << 32);
   }
 
-  // Cuts one unit's cell stream into chunks of at most H2SHA_MAX_FILL distinct non-constant values.
+  // Cuts one unit's cell stream into chunks of at most cfg_.max_fill distinct values.
   void build_chunks(const UnitRec& u, UnitType* ut) {
+    // pass 1: greedy, to learn how many chunks the distinct-value limit forces; pass 2: the same number of chunks with
+    // balanced cell counts (multiples of 32 gate cells)
+    Plan& P = *P_;
+    const size_t f0 = P.fill.size(), c0 = P.cells.size(), k0 = P.chunks.size();
+    build_chunks_pass(u, ut, 0xffffffffu);
+    const uint32_t n = ut->n_chunks;
+    if (n > 1) {
+      P.fill.resize(f0); P.cells.resize(c0); P.chunks.resize(k0);
+      uint32_t cap = ((ut->gate_len + n - 1) / n + 31) / 32 * 32;
+      build_chunks_pass(u, ut, cap);
+    }
+  }
+  void build_chunks_pass(const UnitRec& u, UnitType* ut, uint32_t max_gate_cells) {
     Plan& P = *P_;
     ut->chunk_off = (uint32_t)P.chunks.size();
     struct Pending { uint8_t kind; Sym s; uint32_t dst; };
@@ -924,27 +938,60 @@ class Builder {
       std::map<uint64_t, uint32_t> index;
       for (int cls = 0; cls < 3; cls++)
         for (auto& pc : cur) {
-          if (pc.s.kind == KIND_TABLE && pc.s.w == 0) continue;  // constants are read straight from the static table
           if (fill_class(pc.s) != cls) continue;
           uint64_t k = sym_key(pc.s);
           if (index.count(k)) continue;
           index[k] = (uint32_t)order.size();
           order.push_back(pc.s);
         }
-      if (order.size() > H2SHA_MAX_FILL) fail("chunk has too many distinct values");
+      if (order.size() > cfg_.max_fill) fail("chunk has too many distinct values");
+      // ---- scratch slot of every distinct value, chosen to avoid shared-memory bank conflicts in the copy loops ----
+      // A 128-bit shared load is served one quarter-warp (8 lanes x 16 B) at a time: two lanes of a quarter conflict
+      // when they read different slots with the same (slot mod 8).  Greedy colouring of the co-occurrence graph.
+      const uint32_t nd = (uint32_t)order.size();
+      std::vector<std::map<uint32_t, uint32_t>> adj(nd);
+      for (int kind = 0; kind < 3; kind++) {
+        std::vector<uint32_t> seq;
+        for (auto& pc : cur) if (pc.kind == kind) seq.push_back(index.at(sym_key(pc.s)));
+        for (size_t q = 0; q < seq.size(); q += 8) {
+          size_t qe = std::min(seq.size(), q + 8);
+          for (size_t a = q; a < qe; a++)
+            for (size_t b = a + 1; b < qe; b++)
+              if (seq[a] != seq[b]) { adj[seq[a]][seq[b]]++; adj[seq[b]][seq[a]]++; }
+        }
+      }
+      std::vector<uint32_t> by_weight(nd);
+      std::vector<uint64_t> wsum(nd, 0);
+      for (uint32_t i2 = 0; i2 < nd; i2++) { by_weight[i2] = i2; for (auto& kv : adj[i2]) wsum[i2] += kv.second; }
+      std::stable_sort(by_weight.begin(), by_weight.end(), [&](uint32_t a, uint32_t b) { return wsum[a] > wsum[b]; });
+      const uint32_t cap = cfg_.max_fill / 8;
+      std::vector<int> residue(nd, -1);
+      std::vector<uint32_t> loc(nd, 0);
+      uint32_t used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (uint32_t vi : by_weight) {
+        uint64_t cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (auto& kv : adj[vi]) if (residue[kv.first] >= 0) cost[residue[kv.first]] += kv.second;
+        int best = -1;
+        for (int r = 0; r < 8; r++)
+          if (used[r] < cap && (best < 0 || cost[r] < cost[best] || (cost[r] == cost[best] && used[r] < used[best]))) best = r;
+        if (best < 0) fail("scratch colouring out of space");
+        residue[vi] = best;
+        loc[vi] = (uint32_t)best + 8u * used[best]++;
+      }
       Chunk c{};
       c.fill_off = (uint32_t)P.fill.size();
       c.n_fill = (uint16_t)order.size();
-      for (auto& sy : order) {
+      for (uint32_t i2 = 0; i2 < nd; i2++) {
+        const Sym& sy = order[i2];
         if (fill_class(sy) == 0) c.n_fill_table++;
-        P.fill.push_back(tmpl_pack(0, sy.kind == KIND_TABLE ? table_index(sy) : 0, sy.slot, sy.sh, sy.w, sy.shl, sy.kind, sy.neg));
+        if (fill_class(sy) == 1) c.n_fill32++;
+        P.fill.push_back(tmpl_pack(loc[i2], sy.kind == KIND_TABLE ? table_index(sy) : 0, sy.slot, sy.sh, sy.w, sy.shl, sy.kind, sy.neg));
       }
       for (int kind = 0; kind < 3; kind++) {
         uint32_t off = (uint32_t)P.cells.size(), n = 0;
         for (auto& pc : cur) {
           if (pc.kind != kind) continue;
-          uint32_t src = (pc.s.kind == KIND_TABLE && pc.s.w == 0) ? table_index(pc.s) : (H2SHA_SCRATCH_FLAG | index.at(sym_key(pc.s)));
-          P.cells.push_back(CellEntry{src | (pc.dst << 16)});
+          P.cells.push_back(CellEntry{loc[index.at(sym_key(pc.s))] | (pc.dst << 16)});
           n++;
         }
         if (kind == EV_GATE) { c.gate_off = off; c.gate_len = (uint16_t)n; }
@@ -963,10 +1010,10 @@ class Builder {
       std::map<uint64_t, Sym> trial = distinct;
       for (size_t k = i; k < j; k++) {
         Sym sy = normalise(u.ev[k].s);
-        if (!(sy.kind == KIND_TABLE && sy.w == 0)) trial[sym_key(sy)] = sy;
+        trial[sym_key(sy)] = sy;
       }
-      if (trial.size() > H2SHA_MAX_FILL && !cur.empty()) { flush(); continue; }
-      if (trial.size() > H2SHA_MAX_FILL) fail("a 32-cell group has more than H2SHA_MAX_FILL distinct values");
+      if ((trial.size() > cfg_.max_fill || gate_in_chunk + g > max_gate_cells) && !cur.empty()) { flush(); continue; }
+      if (trial.size() > cfg_.max_fill) fail("a 32-cell group has more than cfg_.max_fill distinct values");
       for (size_t k = i; k < j; k++) {
         Sym sy = normalise(u.ev[k].s);
         uint32_t dst = (u.ev[k].kind == EV_GATE) ? n_gate++ : (u.ev[k].kind == EV_LK) ? n_lk++ : n_limb++;
@@ -1012,12 +1059,20 @@ class Builder {
     jc.n_tasks = (uint32_t)ts.size();
     // phase-2 items, heaviest first
     jc.item_off = (uint32_t)P.items.size();
-    std::vector<std::pair<uint32_t, uint32_t>> its;
+    std::vector<std::pair<uint32_t, ItemDesc>> its;
     for (uint32_t gi = 0; gi < groups.size(); gi++) {
-      const UnitType& ut = P.types[groups[gi].type];
-      if (groups[gi].count > 0xfff || ut.n_chunks > 0xfff) fail("item encoding overflow");
-      for (uint32_t u = 0; u < groups[gi].count; u++)
-        for (uint32_t c = 0; c < ut.n_chunks; c++) its.push_back({chunk_cost(P.chunks[ut.chunk_off + c]), H2SHA_ITEM(gi, u, c)});
+      const UnitGroup& g = P.groups[jc.group_off + gi];
+      const UnitType& ut = P.types[g.type];
+      for (uint32_t u = 0; u < g.count; u++)
+        for (uint32_t c = 0; c < ut.n_chunks; c++) {
+          ItemDesc d{};
+          d.slot_off = g.slot_base + u * (ut.n_slots | 1u);
+          d.gate_rel = g.gate_base + u * g.gate_stride;
+          d.lk_rel = g.lk_base + u * g.lk_stride;
+          d.limb_rel = g.limb_base + u * g.limb_stride;
+          d.chunk = ut.chunk_off + c;
+          its.push_back({chunk_cost(P.chunks[ut.chunk_off + c]), d});
+        }
     }
     std::stable_sort(its.begin(), its.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
     for (auto& it : its) P.items.push_back(it.second);
@@ -1079,19 +1134,35 @@ class Builder {
       uint64_t total = 0;
       for (const GroupRec& g : c.groups) total += (uint64_t)g.count * P.types[type_idx_.at(g.type)].gate_len;
       const uint32_t parts = std::max(1u, cfg_.block_parts);
+      // atoms: runs of <= 32 instances of one group (one phase-1 warp task each); greedy packing into `parts` bins
+      struct Atom { const GroupRec* g; uint32_t first, count; uint64_t cells; };
+      std::vector<Atom> atoms;
+      for (const GroupRec& g : c.groups)
+        for (uint32_t first = 0; first < g.count; first += 32) {
+          uint32_t cnt = std::min(32u, g.count - first);
+          atoms.push_back(Atom{&g, first, cnt, (uint64_t)cnt * P.types[type_idx_.at(g.type)].gate_len});
+        }
       std::vector<std::vector<UnitGroup>> part_groups(1);
       uint64_t acc = 0;
-      for (const GroupRec& g : c.groups) {
-        const uint64_t per = P.types[type_idx_.at(g.type)].gate_len;
-        uint32_t first = 0;
-        while (first < g.count) {
-          uint64_t target = total * part_groups.size() / parts;   // cumulative cell target at the end of the current part
-          uint32_t fit = per ? (uint32_t)std::min<uint64_t>(g.count - first, (target > acc ? (target - acc + per / 2) / per : 0)) : g.count - first;
-          if (part_groups.size() == parts) fit = g.count - first;
-          if (fit == 0) { part_groups.emplace_back(); continue; }
-          part_groups.back().push_back(make_group(g, first, fit));
-          acc += per * fit; first += fit;
+      auto push_atom = [&](const Atom& a) {
+        auto& pg = part_groups.back();
+        // merge with the previous sub-group when it continues the same group
+        if (!pg.empty() && pg.back().type == type_idx_.at(a.g->type) &&
+            pg.back().gate_base + pg.back().count * pg.back().gate_stride == a.g->gate_base + a.first * a.g->gate_stride && a.g->gate_stride &&
+            pg.back().count + a.count <= 0xfff) {
+          pg.back().count += a.count;
+        } else {
+          pg.push_back(make_group(*a.g, a.first, a.count));
         }
+      };
+      for (const Atom& a : atoms) {
+        const uint64_t target = total * part_groups.size() / parts;   // cumulative target at the end of the current part
+        const bool can_close = part_groups.size() < parts && !part_groups.back().empty();
+        const uint64_t over = acc + a.cells > target ? acc + a.cells - target : target - acc - a.cells;
+        const uint64_t under = target > acc ? target - acc : acc - target;
+        if (can_close && under < over) part_groups.emplace_back();
+        push_atom(a);
+        acc += a.cells;
       }
       while (!part_groups.empty() && part_groups.back().empty()) part_groups.pop_back();
       P.n_block_parts = (uint32_t)part_groups.size();

@@ -24,6 +24,7 @@ struct Config {
   uint32_t is_input_range_check = 1;
   uint32_t record_shape = 1;                      // also build selectors / copy constraints / fixed column
   uint32_t block_parts = 3;                       // engine tuning: jobs per sha256_compression (load balance vs. overhead)
+  uint32_t max_fill = 144;                        // engine tuning: distinct values per chunk (size of a warp's scratch table)
 };
 
 enum : uint32_t { CP_GATE = 0, CP_FIXED = 1 };
@@ -50,7 +51,7 @@ struct Plan {
   std::vector<TmplEntry> fill;          // fill lists of all chunks
   std::vector<CellEntry> cells;         // cell lists of all chunks
   std::vector<Chunk> chunks;
-  std::vector<uint32_t> items;          // phase-2 work items of all classes
+  std::vector<ItemDesc> items;          // phase-2 work items of all classes
   uint32_t n_block_parts = 1;
   std::vector<UnitGroup> groups;
   std::vector<WarpTask> tasks;

@@ -133,6 +133,8 @@ extern const uint32_t H2SHA_CK_M[8];
 /* Test hook: Montgomery form of n raw u64 values (device pointers), through the same device function the
  * expansion kernel uses.  out: [n][4] u64. */
 int h2sha_debug_mont_from_u64(h2sha_engine_t* e, const uint64_t* vals_dev, uint64_t* out_dev, uint64_t n, void* stream);
+/* Same for the 32-bit fast path (the low 32 bits of each value are converted). */
+int h2sha_debug_mont_from_u32(h2sha_engine_t* e, const uint64_t* vals_dev, uint64_t* out_dev, uint64_t n, void* stream);
 
 /* Kernel launch statistics of the last h2sha_digest_batch (for bench.py's gpu_launches). */
 int h2sha_last_launch_count(const h2sha_engine_t* e);

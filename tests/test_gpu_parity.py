@@ -64,6 +64,13 @@ def test_montgomery_conversion_matches_python_ints(pkg):
         assert got == int(vals[i]) * R % P, f"value {int(vals[i]):#x}"
     # all results are canonical (< p): compare the top limb cheaply for the whole batch
     assert (out[:, 3] <= np.uint64(P >> 192)).all()
+    # the < 2^32 fast path: every 16-bit value, edge values, 2^20 random ones; and it must agree with the 64-bit path
+    v32 = np.concatenate([np.arange(1 << 16, dtype=np.uint64), np.array([e for e in edge if e < (1 << 32)], dtype=np.uint64),
+                          rng.integers(0, 1 << 32, size=1 << 20, dtype=np.uint64)])
+    o32 = cfg.mont_from_u64(v32, path32=True)
+    assert (o32 == cfg.mont_from_u64(v32)).all()
+    for i in list(range(0, 1 << 16, 97)) + list(rng.integers(0, len(v32), size=5000)):
+        assert sum(int(o32[i, k]) << (64 * k) for k in range(4)) == int(v32[i]) * R % P
     cfg.close()
 
 
