@@ -27,6 +27,7 @@
 using namespace h2sha;
 
 extern "C" const uint32_t H2SHA_CK_M[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+static_assert(sizeof(h2sha::kCkM) == 32, "checksum multipliers");
 
 namespace {
 
@@ -52,13 +53,13 @@ struct DevPlan {
   const uint8_t* blob;
   uint32_t blob_bytes;
   // byte offsets inside the blob (all 16-byte aligned)
-  uint32_t off_fill, off_cells, off_chunks, off_items, off_table_lo, off_table_hi, off_table_h, off_prog, off_groups, off_tasks, off_types, off_classes,
+  uint32_t off_fill, off_cells, off_chunks, off_items, off_table_lo, off_table_hi, off_resident, off_prog, off_groups, off_tasks, off_types, off_classes,
       off_raw, off_breaks, off_digests;
   uint32_t n_breaks, n_digests, n_block_parts;
   // dynamic shared memory layout after the blob
   uint32_t off_trace, off_scratch, off_misc, smem_bytes;
   uint32_t stage_bytes, stage_off_slots, stage_off_desc;   // per producer warp: trace | slots | StageDesc
-  uint32_t max_fill, scratch_bytes;                        // per consumer warp: lo[max_fill] | hi[max_fill] | h[max_fill]
+  uint32_t max_fill, scratch_bytes, n_resident;            // per consumer warp: lo[max_fill] | hi[max_fill]
   // layout
   int32_t spread_cols_shift;   // log2(spread_cols) when it is a power of two, else -1
   uint32_t max_rows, spread_cols, n_gate_cols, gate_col_rows, n_lookup_cols, lookup_col_rows, spread_rows;
@@ -167,42 +168,69 @@ __device__ __forceinline__ void fr_negate(uint64_t r[4]) {
 }
 
 // Same conversion for v < 2^32: 32x256 multiply, 32-bit quotient estimate q_hat = ((P >> 254) * floor(2^285/p)) >> 31
-// (q_hat in {q-2, q-1, q}), r = P - q_hat * p, two conditional subtractions.  About half the work of the 64-bit path.
+// (q_hat in {q-2, q-1, q}), r = P - q_hat * p, two conditional subtractions; carry chains in PTX.
 __device__ __forceinline__ void mont_from_u32(uint32_t v, uint32_t x[8]) {
   const uint32_t* R = reinterpret_cast<const uint32_t*>(c_fr.r1);
   const uint32_t* PM = reinterpret_cast<const uint32_t*>(c_fr.p);
-  uint32_t pl[9];
-  uint64_t t = 0;
+  // P = v * R  (9 limbs): limb k = lo(v*R[k]) + hi(v*R[k-1]) + carry
+  uint32_t lo[8], hi[8], pl[9];
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    t = (uint64_t)v * R[k] + (t >> 32);
-    pl[k] = (uint32_t)t;
-  }
-  pl[8] = (uint32_t)(t >> 32);
-  const uint32_t ph = (pl[7] >> 30) | (pl[8] << 2);
+  for (int k = 0; k < 8; k++) { lo[k] = v * R[k]; hi[k] = __umulhi(v, R[k]); }
+  pl[0] = lo[0];
+  asm("add.cc.u32 %0, %8, %15;\n\t"
+      "addc.cc.u32 %1, %9, %16;\n\t"
+      "addc.cc.u32 %2, %10, %17;\n\t"
+      "addc.cc.u32 %3, %11, %18;\n\t"
+      "addc.cc.u32 %4, %12, %19;\n\t"
+      "addc.cc.u32 %5, %13, %20;\n\t"
+      "addc.cc.u32 %6, %14, %21;\n\t"
+      "addc.u32 %7, %22, 0;"
+      : "=r"(pl[1]), "=r"(pl[2]), "=r"(pl[3]), "=r"(pl[4]), "=r"(pl[5]), "=r"(pl[6]), "=r"(pl[7]), "=r"(pl[8])
+      : "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]),
+        "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]));
+  const uint32_t ph = __funnelshift_r(pl[7], pl[8], 30);   // (P >> 254), < 2^32
   const uint32_t q = (uint32_t)(((uint64_t)ph * c_fr.mu32) >> 31);
-  // r = P - q * p over the low 256 bits
-  uint32_t r[8];
-  uint64_t c = 0;       // carry of q * p
-  uint32_t borrow = 0;
+  // M = low 256 bits of q * p, then r = P - M
+  uint32_t ml[8], mh[8], m[8], r[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    c = (uint64_t)q * PM[k] + (c >> 32);
-    const uint32_t m = (uint32_t)c;
-    const uint64_t d = (uint64_t)pl[k] - m - borrow;
-    r[k] = (uint32_t)d;
-    borrow = (uint32_t)(d >> 63);
-  }
+  for (int k = 0; k < 8; k++) { ml[k] = q * PM[k]; mh[k] = __umulhi(q, PM[k]); }
+  m[0] = ml[0];
+  asm("add.cc.u32 %0, %7, %14;\n\t"
+      "addc.cc.u32 %1, %8, %15;\n\t"
+      "addc.cc.u32 %2, %9, %16;\n\t"
+      "addc.cc.u32 %3, %10, %17;\n\t"
+      "addc.cc.u32 %4, %11, %18;\n\t"
+      "addc.cc.u32 %5, %12, %19;\n\t"
+      "addc.u32 %6, %13, %20;"
+      : "=r"(m[1]), "=r"(m[2]), "=r"(m[3]), "=r"(m[4]), "=r"(m[5]), "=r"(m[6]), "=r"(m[7])
+      : "r"(ml[1]), "r"(ml[2]), "r"(ml[3]), "r"(ml[4]), "r"(ml[5]), "r"(ml[6]), "r"(ml[7]),
+        "r"(mh[0]), "r"(mh[1]), "r"(mh[2]), "r"(mh[3]), "r"(mh[4]), "r"(mh[5]), "r"(mh[6]));
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]), "r"(pl[4]), "r"(pl[5]), "r"(pl[6]), "r"(pl[7]),
+        "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7]));
 #pragma unroll
   for (int it = 0; it < 2; it++) {
-    uint32_t s[8];
-    uint32_t b = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const uint64_t d = (uint64_t)r[k] - PM[k] - b;
-      s[k] = (uint32_t)d;
-      b = (uint32_t)(d >> 63);
-    }
+    uint32_t s[8], b;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(b)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(PM[0]), "r"(PM[1]), "r"(PM[2]), "r"(PM[3]), "r"(PM[4]), "r"(PM[5]), "r"(PM[6]), "r"(PM[7]));
     if (b == 0) {
 #pragma unroll
       for (int k = 0; k < 8; k++) r[k] = s[k];
@@ -372,10 +400,9 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
 // ---------------------------------------------------------------------------------------------------
 // per-consumer-warp scratch of phase 2: Montgomery values of the chunk's distinct non-constant cells (low / high
 // 16 bytes in separate arrays so that random 128-bit reads spread over all bank groups) + their checksum hashes
-struct WarpScratch {   // runtime-sized: lo[max_fill] | hi[max_fill] | h[max_fill]
+struct WarpScratch {   // runtime-sized: lo[max_fill] | hi[max_fill]; slots [0, n_resident) hold the resident constants
   uint4* lo;
   uint4* hi;
-  uint32_t* h;
 };
 // job descriptor a producer warp leaves in its stage
 struct StageDesc {
@@ -443,52 +470,50 @@ __device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitT
   }
 }
 
-// checksum hash of a cell: sum_k x[k] * M[k] mod 2^32
-__device__ __forceinline__ uint32_t cell_hash(const uint32_t x[8]) {
-  uint32_t h = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k++) h += x[k] * c_CKM[k];
-  return h;
+// fill phase: the chunk's distinct values -> warp scratch.  Each function returns the checksum hash of the value.
+__device__ __forceinline__ uint32_t hash8(const uint4& lo, const uint4& hi) {
+  return lo.x * c_CKM[0] + lo.y * c_CKM[1] + lo.z * c_CKM[2] + lo.w * c_CKM[3] + hi.x * c_CKM[4] + hi.y * c_CKM[5] + hi.z * c_CKM[6] +
+         hi.w * c_CKM[7];
 }
-
-// fill phase: the chunk's distinct values -> warp scratch.  Three warp-uniform loops over the sorted fill list.
-__device__ __forceinline__ void fill_table(const TmplEntry e, const uint64_t* slots, const uint4* table_lo, const uint4* table_hi,
-                                           const uint32_t* table_h, const WarpScratch& ws) {
+__device__ __forceinline__ uint32_t fill_table(const FillEntry& e, const uint64_t* slots, const uint4* table_lo, const uint4* table_hi,
+                                               const WarpScratch& ws) {
   const uint32_t i = H2SHA_TE_DST(e);
   const uint64_t s = slots[H2SHA_TE_SLOT(e)];
   const uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
-  ws.lo[i] = table_lo[idx]; ws.hi[i] = table_hi[idx];
-  ws.h[i] = table_h[idx];
+  const uint4 lo = table_lo[idx], hi = table_hi[idx];
+  ws.lo[i] = lo; ws.hi[i] = hi;
+  return hash8(lo, hi);
 }
-__device__ __forceinline__ void fill_gen32(const TmplEntry e, const uint64_t* slots, const WarpScratch& ws) {
+// Barrett entries: the 32-bit path when every lane of the warp iteration holds a value < 2^32, else the 64-bit path
+__device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint64_t* slots, const WarpScratch& ws, bool active) {
   const uint32_t i = H2SHA_TE_DST(e);
-  const uint64_t s = slots[H2SHA_TE_SLOT(e)];
-  const uint32_t v = (uint32_t)(extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e)) << H2SHA_TE_SHL(e));
-  uint32_t x[8];
-  mont_from_u32(v, x);
-  if (H2SHA_TE_NEG(e)) fr_negate32(x);
-  ws.lo[i] = make_uint4(x[0], x[1], x[2], x[3]); ws.hi[i] = make_uint4(x[4], x[5], x[6], x[7]);
-  ws.h[i] = cell_hash(x);
-}
-__device__ __forceinline__ void fill_gen64(const TmplEntry e, const uint64_t* slots, const WarpScratch& ws) {
-  const uint32_t i = H2SHA_TE_DST(e);
-  const uint64_t s = slots[H2SHA_TE_SLOT(e)];
-  bool neg = H2SHA_TE_NEG(e);
-  uint64_t v;
-  if (H2SHA_TE_KIND(e) == KIND_SIGNED) {
-    int64_t sv = (int64_t)s;
-    neg = sv < 0;
-    v = neg ? (uint64_t)(-sv) : (uint64_t)sv;
-  } else {
-    v = extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e)) << H2SHA_TE_SHL(e);
+  bool neg = false;
+  uint64_t v = 0;
+  if (active) {
+    const uint64_t s = slots[H2SHA_TE_SLOT(e)];
+    neg = H2SHA_TE_NEG(e);
+    if (H2SHA_TE_KIND(e) == KIND_SIGNED) {
+      int64_t sv = (int64_t)s;
+      neg = sv < 0;
+      v = neg ? (uint64_t)(-sv) : (uint64_t)sv;
+    } else {
+      v = extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e)) << H2SHA_TE_SHL(e);
+    }
   }
-  uint64_t r[4];
-  mont_from_u64(v, r);
-  if (neg) fr_negate(r);
-  uint32_t x[8] = {(uint32_t)r[0], (uint32_t)(r[0] >> 32), (uint32_t)r[1], (uint32_t)(r[1] >> 32),
-                   (uint32_t)r[2], (uint32_t)(r[2] >> 32), (uint32_t)r[3], (uint32_t)(r[3] >> 32)};
-  ws.lo[i] = make_uint4(x[0], x[1], x[2], x[3]); ws.hi[i] = make_uint4(x[4], x[5], x[6], x[7]);
-  ws.h[i] = cell_hash(x);
+  uint32_t x[8];
+  if (__any_sync(0xffffffffu, (v >> 32) != 0)) {
+    uint64_t r[4];
+    mont_from_u64(v, r);
+    if (neg) fr_negate(r);
+    x[0] = (uint32_t)r[0]; x[1] = (uint32_t)(r[0] >> 32); x[2] = (uint32_t)r[1]; x[3] = (uint32_t)(r[1] >> 32);
+    x[4] = (uint32_t)r[2]; x[5] = (uint32_t)(r[2] >> 32); x[6] = (uint32_t)r[3]; x[7] = (uint32_t)(r[3] >> 32);
+  } else {
+    mont_from_u32((uint32_t)v, x);
+    if (neg) fr_negate32(x);
+  }
+  const uint4 lo = make_uint4(x[0], x[1], x[2], x[3]), hi = make_uint4(x[4], x[5], x[6], x[7]);
+  if (active) { ws.lo[i] = lo; ws.hi[i] = hi; }
+  return hash8(lo, hi);
 }
 
 // one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
@@ -512,13 +537,13 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (uint32_t i = tid; i < P.blob_bytes / 16; i += NT) dst[i] = src[i];
   }
-  const TmplEntry* s_fill = reinterpret_cast<const TmplEntry*>(smem + P.off_fill);
+  const FillEntry* s_fill = reinterpret_cast<const FillEntry*>(smem + P.off_fill);
   const CellEntry* s_cells = reinterpret_cast<const CellEntry*>(smem + P.off_cells);
   const Chunk* s_chunks = reinterpret_cast<const Chunk*>(smem + P.off_chunks);
   const ItemDesc* s_items = reinterpret_cast<const ItemDesc*>(smem + P.off_items);
   const uint4* s_table_lo = reinterpret_cast<const uint4*>(smem + P.off_table_lo);
   const uint4* s_table_hi = reinterpret_cast<const uint4*>(smem + P.off_table_hi);
-  const uint32_t* s_table_h = reinterpret_cast<const uint32_t*>(smem + P.off_table_h);
+  const uint32_t* s_resident = reinterpret_cast<const uint32_t*>(smem + P.off_resident);
   const VmIns* s_prog = reinterpret_cast<const VmIns*>(smem + P.off_prog);
   const UnitGroup* s_groups = reinterpret_cast<const UnitGroup*>(smem + P.off_groups);
   const WarpTask* s_tasks = reinterpret_cast<const WarpTask*>(smem + P.off_tasks);
@@ -611,7 +636,8 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     uint8_t* base = smem + P.off_scratch + (size_t)warp * P.scratch_bytes;
     ws.lo = reinterpret_cast<uint4*>(base);
     ws.hi = ws.lo + P.max_fill;
-    ws.h = reinterpret_cast<uint32_t*>(ws.hi + P.max_fill);
+    for (uint32_t i = lane; i < P.n_resident; i += 32) { ws.lo[i] = s_table_lo[s_resident[i]]; ws.hi[i] = s_table_hi[s_resident[i]]; }
+    __syncwarp();
   }
   uint32_t finished = 0;   // bit st: producer st has run out of jobs
   for (uint32_t k = 0; finished != (1u << NPROD) - 1u; k++) {
@@ -633,59 +659,82 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     // static item -> warp assignment, rotated per job so that the heavier leading items do not always hit the same warps
     for (uint32_t it = (uint32_t)(warp + k) % NCONS; it < jc.n_items; it += NCONS) {
       const ItemDesc item = s_items[jc.item_off + it];
-      const Chunk ch = s_chunks[item.chunk];
-      const uint64_t* slots = s_slots + item.slot_off;
-      // ---- fill: table copies | Barrett < 2^32 | Barrett 64-bit / signed ----
+      const Chunk ch = s_chunks[item.slot_chunk >> 16];
+      const uint64_t* slots = s_slots + (item.slot_chunk & 0xffffu);
+      // ---- positions of the chunk's gate cells; a column break inside the chunk (rare) takes the per-cell path ----
+      const uint32_t g_lo = gate0 + item.gate_rel;   // instance-relative gate-stream index of the unit's first cell
+      uint32_t c0 = 0;
+      if (P.n_breaks > 1)
+        while (c0 + 1 < P.n_breaks && s_breaks[c0 + 1] <= g_lo + ch.gate_dst_min) c0++;
+      const uint32_t next_brk = (c0 + 1 < P.n_breaks) ? s_breaks[c0 + 1] : 0xffffffffu;
+      const uint32_t off0 = c0 * P.gate_col_rows - s_breaks[c0];          // pos = gidx + off0 before the break,
+      const uint32_t off1 = (c0 + 1) * P.gate_col_rows - next_brk;        //       gidx + off1 from the break on
+      const bool straddle = g_lo + ch.gate_dst_max >= next_brk;
+      // checksum weight of a value carried by cnt cells whose offsets sum to sumdst: sum (2*pos+1) = cnt*w0 + 2*sumdst
+      const unsigned long long w0 = straddle ? 0ull : (unsigned long long)(2u * (g_lo + off0) + 1u);
+      const unsigned long long w1 = straddle ? 0ull : 2ull;
+      // ---- fill: table copies, then Barrett conversions ----
       {
-        const TmplEntry* fl = s_fill + ch.fill_off;
-        const uint32_t n_tab = ch.n_fill_table, n_32 = n_tab + ch.n_fill32, n_all = ch.n_fill;
-        for (uint32_t i = lane; i < n_tab; i += 32) fill_table(fl[i], slots, s_table_lo, s_table_hi, s_table_h, ws);
-        for (uint32_t i = n_tab + lane; i < n_32; i += 32) fill_gen32(fl[i], slots, ws);
-        for (uint32_t i = n_32 + lane; i < n_all; i += 32) fill_gen64(fl[i], slots, ws);
+        const FillEntry* fl = s_fill + ch.fill_off;
+        const uint32_t n_tab = ch.n_fill_table, n_all = ch.n_fill;
+        for (uint32_t i = lane; i < n_tab; i += 32) {
+          const FillEntry e = fl[i];
+          const uint32_t h = fill_table(e, slots, s_table_lo, s_table_hi, ws);
+          ck_g += (unsigned long long)h * (e.cnt * w0 + e.sumdst * w1);
+        }
+        for (uint32_t i0 = n_tab; i0 < n_all; i0 += 32) {
+          const uint32_t i = i0 + lane;
+          const bool active = i < n_all;
+          FillEntry e = fl[active ? i : n_tab];
+          const uint32_t h = fill_generic(e, slots, ws, active);
+          if (active) ck_g += (unsigned long long)h * (e.cnt * w0 + e.sumdst * w1);
+        }
+        if (lane == 0 && !straddle) ck_g += ch.res_a + ch.res_b * w0;
       }
       __syncwarp();
       // ---- copy: gate cells ----
       if (ch.gate_len) {
-        const uint32_t g_lo = gate0 + item.gate_rel;   // instance-relative gate-stream index of the unit's first cell
-        uint32_t c0 = 0;
-        while (c0 + 1 < P.n_breaks && s_breaks[c0 + 1] <= g_lo) c0++;
-        const uint32_t next_brk = (c0 + 1 < P.n_breaks) ? s_breaks[c0 + 1] : 0xffffffffu;
-        // pos = gidx + off0 before the break, gidx + off1 from the break on
-        const uint32_t off0 = c0 * P.gate_col_rows - s_breaks[c0];
-        const uint32_t off1 = (c0 + 1) * P.gate_col_rows - next_brk;
         const CellEntry* cells = s_cells + ch.gate_off;
+        if (!straddle) {
+          uint32_t* out0 = gate_out + (uint64_t)(g_lo + off0) * 8;
 #pragma unroll 4
-        for (uint32_t i = lane; i < ch.gate_len; i += 32) {
-          const CellEntry ce = cells[i];
-          const uint32_t src = H2SHA_CE_SRC(ce);
-          const uint4 lo = ws.lo[src], hi = ws.hi[src];
-          const uint32_t h = ws.h[src];
-          const uint32_t gidx = g_lo + H2SHA_CE_DST(ce);
-          const uint32_t pos = gidx + ((gidx >= next_brk) ? off1 : off0);
-          if (gate_out) store_cell2(gate_out + (uint64_t)pos * 8, lo, hi);
-          ck_g += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
+          for (uint32_t i = lane; i < ch.gate_len; i += 32) {
+            const CellEntry ce = cells[i];
+            const uint32_t src = H2SHA_CE_SRC(ce);
+            const uint4 lo = ws.lo[src], hi = ws.hi[src];
+            if (gate_out) store_cell2(out0 + (uint64_t)H2SHA_CE_DST(ce) * 8, lo, hi);
+          }
+        } else {
+          for (uint32_t i = lane; i < ch.gate_len; i += 32) {
+            const CellEntry ce = cells[i];
+            const uint32_t src = H2SHA_CE_SRC(ce);
+            const uint4 lo = ws.lo[src], hi = ws.hi[src];
+            const uint32_t gidx = g_lo + H2SHA_CE_DST(ce);
+            const uint32_t pos = gidx + ((gidx >= next_brk) ? off1 : off0);
+            if (gate_out) store_cell2(gate_out + (uint64_t)pos * 8, lo, hi);
+            ck_g += (unsigned long long)hash8(lo, hi) * (unsigned long long)(2u * pos + 1u);
+          }
         }
       }
       // ---- lookup-column cells (range.finalize copies cells_to_lookup in push order, wrapping at max_rows) ----
       if (ch.lk_len) {
         const uint32_t l_lo = lk0 + item.lk_rel;
-        // pos = li + off0 before the column wrap at `wrap`, li + off1 after it (no division in the loop)
-        uint32_t off0 = 0, off1 = 0, wrap = 0xffffffffu;
+        // pos = li + loff0 before the column wrap at `wrap`, li + loff1 after it (no division in the loop)
+        uint32_t loff0 = 0, loff1 = 0, wrap = 0xffffffffu;
         if (P.n_lookup_cols > 1) {
           const uint32_t col0 = l_lo / P.max_rows;
           wrap = (col0 + 1) * P.max_rows;
-          off0 = col0 * (P.lookup_col_rows - P.max_rows);
-          off1 = (col0 + 1) * (P.lookup_col_rows - P.max_rows);
+          loff0 = col0 * (P.lookup_col_rows - P.max_rows);
+          loff1 = (col0 + 1) * (P.lookup_col_rows - P.max_rows);
         }
         for (uint32_t i = lane; i < ch.lk_len; i += 32) {
           const CellEntry ce = s_cells[ch.lk_off + i];
           const uint32_t src = H2SHA_CE_SRC(ce);
           const uint4 lo = ws.lo[src], hi = ws.hi[src];
-          const uint32_t h = ws.h[src];
           const uint32_t li = l_lo + H2SHA_CE_DST(ce);
-          const uint32_t pos = li + ((li >= wrap) ? off1 : off0);
+          const uint32_t pos = li + ((li >= wrap) ? loff1 : loff0);
           if (lk_out) store_cell2(lk_out + (uint64_t)pos * 8, lo, hi);
-          ck_l += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
+          ck_l += (unsigned long long)hash8(lo, hi) * (unsigned long long)(2u * pos + 1u);
         }
       }
       // ---- spread-table columns: limb n -> column n % cols, row n / cols (spread.rs:202,228-231); dense then spread ----
@@ -695,14 +744,13 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           const CellEntry ce = s_cells[ch.limb_off + i];
           const uint32_t src = H2SHA_CE_SRC(ce);
           const uint4 lo = ws.lo[src], hi = ws.hi[src];
-          const uint32_t h = ws.h[src];
           const uint32_t n = m_lo + (H2SHA_CE_DST(ce) >> 1), which = H2SHA_CE_DST(ce) & 1u;
           uint32_t row, col;
           if (P.spread_cols_shift >= 0) { row = n >> P.spread_cols_shift; col = n & (P.spread_cols - 1u); }
           else { row = n / P.spread_cols; col = n - row * P.spread_cols; }
           const uint32_t pos = (which * P.spread_cols + col) * P.spread_rows + row;
           if (sp_out) store_cell2(sp_out + (uint64_t)pos * 8, lo, hi);
-          ck_s += (unsigned long long)h * (unsigned long long)(2u * pos + 1u);
+          ck_s += (unsigned long long)hash8(lo, hi) * (unsigned long long)(2u * pos + 1u);
         }
       }
       __syncwarp();  // scratch is overwritten by the next item's fill
@@ -874,6 +922,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   if (cfg->block_parts) pc.block_parts = cfg->block_parts;
   pc.block_parts = (uint32_t)tune_value("parts", (int)pc.block_parts);
   pc.max_fill = (uint32_t)tune_value("fill", (int)pc.max_fill);
+  pc.resident_consts = (uint32_t)tune_value("res", (int)pc.resident_consts);
   h2sha_engine* e = new h2sha_engine();
   std::string err;
   if (!build_plan(pc, &e->plan, &err)) { delete e; return set_err(H2SHA_EINVAL, err); }
@@ -921,7 +970,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
     if (bytes) memcpy(blob.data() + off, p, bytes);
     return off;
   };
-  D.off_fill = put(P.fill.data(), P.fill.size() * sizeof(TmplEntry));
+  D.off_fill = put(P.fill.data(), P.fill.size() * sizeof(FillEntry));
   D.off_cells = put(P.cells.data(), P.cells.size() * sizeof(CellEntry));
   D.off_chunks = put(P.chunks.data(), P.chunks.size() * sizeof(Chunk));
   D.off_items = put(P.items.data(), P.items.size() * sizeof(ItemDesc));
@@ -934,16 +983,8 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
     D.off_table_lo = put(lo.data(), lo.size() * 8);
     D.off_table_hi = put(hi.data(), hi.size() * 8);
   }
-  {
-    std::vector<uint32_t> th(P.mont_table.size());
-    for (size_t i = 0; i < th.size(); i++) {
-      const uint32_t* x = reinterpret_cast<const uint32_t*>(P.mont_table[i].l);
-      uint32_t h = 0;
-      for (int k = 0; k < 8; k++) h += x[k] * H2SHA_CK_M[k];
-      th[i] = h;
-    }
-    D.off_table_h = put(th.data(), th.size() * 4);
-  }
+  D.off_resident = put(P.resident.data(), P.resident.size() * 4);
+  D.n_resident = (uint32_t)P.resident.size();
   D.off_prog = put(P.prog.data(), P.prog.size() * sizeof(VmIns));
   D.off_groups = put(P.groups.data(), P.groups.size() * sizeof(UnitGroup));
   D.off_tasks = put(P.tasks.data(), P.tasks.size() * sizeof(WarpTask));
@@ -961,20 +1002,27 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.stage_off_desc = align_up(D.stage_off_slots + 8 * (P.max_slots + 1), 16);
   D.stage_bytes = align_up(D.stage_off_desc + (uint32_t)sizeof(StageDesc), 16);
   {
+    // launch variant: the tuned default (or H2SHA_TUNE cons=/prod=); when the plan of an unusual configuration does not
+    // fit in shared memory with it, fall back to variants with fewer consumer warps
     int nv = 0;
     const ExpandVariant* vs = expand_variants(&nv);
-    const int want_c = tune_value("cons", 20), want_p = tune_value("prod", 4);
-    e->variant = vs[0];
-    bool found = false;
-    for (int i = 0; i < nv; i++) if (vs[i].ncons == want_c && vs[i].nprod == want_p) { e->variant = vs[i]; found = true; }
-    if (!found) { delete e; return set_err(H2SHA_EINVAL, "H2SHA_TUNE: no such (cons, prod) launch variant"); }
+    const bool forced = getenv("H2SHA_TUNE") && (strstr(getenv("H2SHA_TUNE"), "cons=") || strstr(getenv("H2SHA_TUNE"), "prod="));
+    const int pref[][2] = {{tune_value("cons", 20), tune_value("prod", 4)}, {16, 4}, {12, 4}, {8, 4}, {8, 2}};
+    bool ok = false;
+    for (int pi = 0; pi < (forced ? 1 : 5) && !ok; pi++) {
+      for (int i = 0; i < nv && !ok; i++) {
+        if (vs[i].ncons != pref[pi][0] || vs[i].nprod != pref[pi][1]) continue;
+        e->variant = vs[i];
+        D.max_fill = pc.max_fill;
+        D.scratch_bytes = pc.max_fill * 32;
+        D.off_scratch = D.off_trace + e->variant.nprod * D.stage_bytes;
+        D.off_misc = align_up(D.off_scratch + e->variant.ncons * D.scratch_bytes, 16);
+        D.smem_bytes = D.off_misc + 2 * e->variant.nprod * 8;
+        ok = D.smem_bytes <= 227 * 1024;
+      }
+    }
+    if (!ok) { delete e; return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory (or H2SHA_TUNE names no launch variant)"); }
   }
-  D.max_fill = pc.max_fill;
-  D.scratch_bytes = pc.max_fill * 36;
-  D.off_scratch = D.off_trace + e->variant.nprod * D.stage_bytes;
-  D.off_misc = align_up(D.off_scratch + e->variant.ncons * D.scratch_bytes, 16);
-  D.smem_bytes = D.off_misc + 2 * e->variant.nprod * 8;
-  if (D.smem_bytes > 227 * 1024) { delete e; return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory"); }
   D.max_rows = pc.max_rows; D.spread_cols = pc.spread_cols;
   D.spread_cols_shift = -1;
   for (int sh = 0; sh < 16; sh++) if ((1u << sh) == pc.spread_cols) D.spread_cols_shift = sh;

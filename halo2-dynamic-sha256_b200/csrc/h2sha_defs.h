@@ -81,15 +81,26 @@ struct CellEntry {
 #define H2SHA_CE_DST(e) ((e).v >> 16)
 enum { H2SHA_MAX_FILL_LIMIT = 256 };   // the actual limit is Config::max_fill (runtime, <= this)
 
+// Fill entry: how to materialise one distinct value (same packing as TmplEntry, dst = scratch slot) plus the weight of
+// the value in the gate checksum: it is carried by `cnt` gate cells of the chunk whose unit-relative offsets sum to `sumdst`.
+struct FillEntry {
+  uint32_t lo, hi;
+  uint32_t cnt, sumdst;
+};
+
+// multipliers of the cell checksum hash (include/h2sha_b200.h: H2SHA_CK_M)
+static const uint32_t kCkM[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+
 struct Chunk {
-  uint32_t fill_off;   // TmplEntry index
-  uint16_t n_fill, n_fill_table;   // total distinct values; the first n_fill_table are table copies
+  uint64_t res_a, res_b;   // gate-checksum contribution of the resident constants of the chunk: res_a + res_b * (2*pos0 + 1)
+  uint32_t fill_off;   // FillEntry index
+  uint16_t n_fill, n_fill_table;   // distinct values to materialise; the first n_fill_table are table copies
   uint32_t gate_off;   // CellEntry index; dst = gate-stream offset inside the unit
   uint16_t gate_len, n_fill32;     // n_fill32: Barrett entries known to be < 2^32 (they follow the table copies)
   uint32_t lk_off;     // dst = lookup index inside the unit
-  uint16_t lk_len, pad1;
+  uint16_t lk_len, gate_dst_min;   // smallest / largest gate dst of the chunk (to detect a column break inside it)
   uint32_t limb_off;   // dst = (limb index inside the unit) << 1 | (0 dense, 1 spread)
-  uint16_t limb_len, pad2;
+  uint16_t limb_len, gate_dst_max;
 };
 
 // Unit type: slot program + chunks (offsets into the plan's flat arrays).
@@ -125,12 +136,10 @@ struct WarpTask {
 
 // Work item of phase 2: one chunk of one unit instance, with everything that does not depend on the job precomputed.
 struct ItemDesc {
-  uint32_t slot_off;   // offset (u64 units) of the unit instance's slots in the job's slot area
   uint32_t gate_rel;   // gate-stream index of the unit's first cell, relative to the job's gate base
   uint32_t lk_rel;     // same for the lookup stream
   uint32_t limb_rel;   // same for spread limbs
-  uint32_t chunk;      // Chunk index
-  uint32_t pad[3];
+  uint32_t slot_chunk; // slot_off (16: offset in u64 units of the unit instance's slots in the job's slot area) | Chunk index (16)
 };
 
 // A job class: (a part of) the block job (one sha256_compression) or the per-digest prologue/epilogue job.

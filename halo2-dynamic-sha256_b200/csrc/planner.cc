@@ -899,6 +899,8 @@ class Builder {
     if (tbl > 0xffff) fail("static table too large");
     return tbl;
   }
+  std::map<uint32_t, uint32_t> resident_slot_;   // const table index -> fixed scratch slot
+  bool is_resident(const Sym& s) const { return s.kind == KIND_TABLE && s.w == 0 && resident_slot_.count(table_index(s)); }
   // sort class of a fill entry: table copies, then <= 32-bit Barrett, then the full 64-bit / signed path
   static int fill_class(const Sym& s) {
     if (s.kind == KIND_TABLE) return 0;
@@ -944,10 +946,10 @@ class Builder {
           index[k] = (uint32_t)order.size();
           order.push_back(pc.s);
         }
-      if (order.size() > cfg_.max_fill) fail("chunk has too many distinct values");
       // ---- scratch slot of every distinct value, chosen to avoid shared-memory bank conflicts in the copy loops ----
       // A 128-bit shared load is served one quarter-warp (8 lanes x 16 B) at a time: two lanes of a quarter conflict
-      // when they read different slots with the same (slot mod 8).  Greedy colouring of the co-occurrence graph.
+      // when they read different slots with the same (slot mod 8).  Greedy colouring of the co-occurrence graph;
+      // resident constants have fixed slots [0, n_resident).
       const uint32_t nd = (uint32_t)order.size();
       std::vector<std::map<uint32_t, uint32_t>> adj(nd);
       for (int kind = 0; kind < 3; kind++) {
@@ -960,32 +962,69 @@ class Builder {
               if (seq[a] != seq[b]) { adj[seq[a]][seq[b]]++; adj[seq[b]][seq[a]]++; }
         }
       }
-      std::vector<uint32_t> by_weight(nd);
-      std::vector<uint64_t> wsum(nd, 0);
-      for (uint32_t i2 = 0; i2 < nd; i2++) { by_weight[i2] = i2; for (auto& kv : adj[i2]) wsum[i2] += kv.second; }
-      std::stable_sort(by_weight.begin(), by_weight.end(), [&](uint32_t a, uint32_t b) { return wsum[a] > wsum[b]; });
-      const uint32_t cap = cfg_.max_fill / 8;
+      const uint32_t n_res = (uint32_t)P.resident.size();
       std::vector<int> residue(nd, -1);
       std::vector<uint32_t> loc(nd, 0);
-      uint32_t used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      std::vector<uint8_t> resident(nd, 0);
+      // free slots per residue class: all slots >= n_res
+      std::vector<std::vector<uint32_t>> free_slots(8);
+      for (uint32_t sl = cfg_.max_fill; sl-- > n_res;) free_slots[sl % 8].push_back(sl);   // back() = smallest free slot
+      uint32_t n_dyn = 0;
+      for (uint32_t i2 = 0; i2 < nd; i2++) {
+        if (is_resident(order[i2])) { resident[i2] = 1; loc[i2] = resident_slot_.at(table_index(order[i2])); residue[i2] = (int)(loc[i2] % 8); }
+        else n_dyn++;
+      }
+      if (n_dyn + n_res > cfg_.max_fill) fail("chunk has too many distinct values");
+      std::vector<uint32_t> by_weight;
+      std::vector<uint64_t> wsum(nd, 0);
+      for (uint32_t i2 = 0; i2 < nd; i2++) { if (!resident[i2]) by_weight.push_back(i2); for (auto& kv : adj[i2]) wsum[i2] += kv.second; }
+      std::stable_sort(by_weight.begin(), by_weight.end(), [&](uint32_t a, uint32_t b) { return wsum[a] > wsum[b]; });
       for (uint32_t vi : by_weight) {
         uint64_t cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (auto& kv : adj[vi]) if (residue[kv.first] >= 0) cost[residue[kv.first]] += kv.second;
         int best = -1;
         for (int r = 0; r < 8; r++)
-          if (used[r] < cap && (best < 0 || cost[r] < cost[best] || (cost[r] == cost[best] && used[r] < used[best]))) best = r;
+          if (!free_slots[r].empty() && (best < 0 || cost[r] < cost[best] || (cost[r] == cost[best] && free_slots[r].size() > free_slots[best].size()))) best = r;
         if (best < 0) fail("scratch colouring out of space");
         residue[vi] = best;
-        loc[vi] = (uint32_t)best + 8u * used[best]++;
+        loc[vi] = free_slots[best].back();
+        free_slots[best].pop_back();
       }
+      // gate-checksum weights of every distinct value
+      std::vector<uint32_t> cnt(nd, 0), sumdst(nd, 0);
+      uint32_t dmin = 0xffff, dmax = 0;
+      for (auto& pc : cur)
+        if (pc.kind == EV_GATE) {
+          uint32_t vi = index.at(sym_key(pc.s));
+          cnt[vi]++; sumdst[vi] += pc.dst;
+          dmin = std::min(dmin, pc.dst); dmax = std::max(dmax, pc.dst);
+        }
       Chunk c{};
       c.fill_off = (uint32_t)P.fill.size();
-      c.n_fill = (uint16_t)order.size();
-      for (uint32_t i2 = 0; i2 < nd; i2++) {
-        const Sym& sy = order[i2];
-        if (fill_class(sy) == 0) c.n_fill_table++;
-        if (fill_class(sy) == 1) c.n_fill32++;
-        P.fill.push_back(tmpl_pack(loc[i2], sy.kind == KIND_TABLE ? table_index(sy) : 0, sy.slot, sy.sh, sy.w, sy.shl, sy.kind, sy.neg));
+      c.gate_dst_min = (uint16_t)dmin; c.gate_dst_max = (uint16_t)dmax;
+      for (uint32_t i2 = 0; i2 < nd; i2++)
+        if (resident[i2] && cnt[i2]) {
+          const uint32_t* x = reinterpret_cast<const uint32_t*>(P.mont_table[table_index(order[i2])].l);
+          uint32_t h = 0;
+          for (int k = 0; k < 8; k++) h += x[k] * kCkM[k];
+          c.res_a += (uint64_t)h * (2ull * sumdst[i2]);
+          c.res_b += (uint64_t)h * (uint64_t)cnt[i2];
+        }
+      // emit the fill list class by class, each class sorted by scratch slot (conflict-free scratch writes); resident
+      // constants need no fill entry but their gate-checksum weight is folded into one "virtual" entry per constant
+      for (int cls = 0; cls < 3; cls++) {
+        std::vector<uint32_t> ids;
+        for (uint32_t i2 = 0; i2 < nd; i2++) if (fill_class(order[i2]) == cls) ids.push_back(i2);
+        std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return loc[a] < loc[b]; });
+        for (uint32_t i2 : ids) {
+          const Sym& sy = order[i2];
+          if (resident[i2]) continue;
+          if (cls == 0) c.n_fill_table++;
+          if (cls == 1) c.n_fill32++;
+          c.n_fill++;
+          TmplEntry te = tmpl_pack(loc[i2], sy.kind == KIND_TABLE ? table_index(sy) : 0, sy.slot, sy.sh, sy.w, sy.shl, sy.kind, sy.neg);
+          P.fill.push_back(FillEntry{te.lo, te.hi, cnt[i2], sumdst[i2]});
+        }
       }
       for (int kind = 0; kind < 3; kind++) {
         uint32_t off = (uint32_t)P.cells.size(), n = 0;
@@ -1012,8 +1051,13 @@ class Builder {
         Sym sy = normalise(u.ev[k].s);
         trial[sym_key(sy)] = sy;
       }
-      if ((trial.size() > cfg_.max_fill || gate_in_chunk + g > max_gate_cells) && !cur.empty()) { flush(); continue; }
-      if (trial.size() > cfg_.max_fill) fail("a 32-cell group has more than cfg_.max_fill distinct values");
+      auto scratch_need = [&](const std::map<uint64_t, Sym>& m) {
+        size_t n = P.resident.size();
+        for (auto& kv : m) if (!is_resident(kv.second)) n++;
+        return n;
+      };
+      if ((scratch_need(trial) > cfg_.max_fill || gate_in_chunk + g > max_gate_cells) && !cur.empty()) { flush(); continue; }
+      if (scratch_need(trial) > cfg_.max_fill) fail("a 32-cell group has more distinct values than max_fill");
       for (size_t k = i; k < j; k++) {
         Sym sy = normalise(u.ev[k].s);
         uint32_t dst = (u.ev[k].kind == EV_GATE) ? n_gate++ : (u.ev[k].kind == EV_LK) ? n_lk++ : n_limb++;
@@ -1066,11 +1110,12 @@ class Builder {
       for (uint32_t u = 0; u < g.count; u++)
         for (uint32_t c = 0; c < ut.n_chunks; c++) {
           ItemDesc d{};
-          d.slot_off = g.slot_base + u * (ut.n_slots | 1u);
+          const uint32_t slot_off = g.slot_base + u * (ut.n_slots | 1u);
+          if (slot_off > 0xffff || ut.chunk_off + c > 0xffff) fail("item descriptor overflow (job class too large)");
           d.gate_rel = g.gate_base + u * g.gate_stride;
           d.lk_rel = g.lk_base + u * g.lk_stride;
           d.limb_rel = g.limb_base + u * g.limb_stride;
-          d.chunk = ut.chunk_off + c;
+          d.slot_chunk = slot_off | ((ut.chunk_off + c) << 16);
           its.push_back({chunk_cost(P.chunks[ut.chunk_off + c]), d});
         }
     }
@@ -1115,6 +1160,24 @@ class Builder {
     for (int64_t dv = -(int64_t)inv_bias_; dv <= (int64_t)inv_bias_; dv++) {
       U256 v = fr::from_i64(dv);
       P.mont_table.push_back(fr::to_mont(dv == 0 ? fr::from_u64(1) : fr::inv(v)));
+    }
+    // ---- constants kept resident in every warp's scratch: the most used ones, weighted by instances per block ----
+    {
+      std::map<uint32_t, uint64_t> use;   // const table index -> weighted use count
+      std::map<std::string, uint64_t> weight;
+      for (const GroupRec& g : class_recs_[0].groups) weight[g.type] += g.count;
+      for (auto& kv : type_idx_) {
+        const uint64_t w = weight.count(kv.first) ? weight[kv.first] : 1;
+        for (const Event& ev : type_recs_[kv.second].ev) {
+          Sym sy = normalise(ev.s);
+          if (sy.kind == KIND_TABLE && sy.w == 0) use[table_index(sy)] += w;
+        }
+      }
+      std::vector<std::pair<uint64_t, uint32_t>> byuse;
+      for (auto& kv : use) byuse.push_back({kv.second, kv.first});
+      std::sort(byuse.begin(), byuse.end(), [](const auto& a, const auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+      const uint32_t nres = std::min<uint32_t>({cfg_.resident_consts, (uint32_t)byuse.size(), cfg_.max_fill / 2});
+      for (uint32_t i = 0; i < nres; i++) { resident_slot_[byuse[i].second] = i; P.resident.push_back(byuse[i].second); }
     }
     // ---- unit types ----
     for (auto& kv : type_idx_) { if (P.type_names.size() <= kv.second) P.type_names.resize(kv.second + 1); P.type_names[kv.second] = kv.first; }

@@ -25,6 +25,7 @@ struct Config {
   uint32_t record_shape = 1;                      // also build selectors / copy constraints / fixed column
   uint32_t block_parts = 3;                       // engine tuning: jobs per sha256_compression (load balance vs. overhead)
   uint32_t max_fill = 144;                        // engine tuning: distinct values per chunk (size of a warp's scratch table)
+  uint32_t resident_consts = 16;                  // engine tuning: most-used constants kept permanently in every warp's scratch
 };
 
 enum : uint32_t { CP_GATE = 0, CP_FIXED = 1 };
@@ -48,7 +49,8 @@ struct Plan {
   std::vector<UnitType> types;
   std::vector<std::string> type_names;
   std::vector<VmIns> prog;
-  std::vector<TmplEntry> fill;          // fill lists of all chunks
+  std::vector<FillEntry> fill;          // fill lists of all chunks
+  std::vector<uint32_t> resident;       // static-table indices of the constants every warp keeps in scratch slots [0, n)
   std::vector<CellEntry> cells;         // cell lists of all chunks
   std::vector<Chunk> chunks;
   std::vector<ItemDesc> items;          // phase-2 work items of all classes
