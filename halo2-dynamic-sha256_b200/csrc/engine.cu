@@ -69,8 +69,8 @@ struct DevPlan {
 
 struct JobArgs {
   uint64_t n_inst;
-  const uint32_t* btrace;   // [n_inst * blocks_per_inst][TR_BLOCK_WORDS]
-  const uint32_t* dtrace;   // [n_inst][dtrace_words_per_inst]
+  const uint32_t* btrace;   // word-major: [TR_BLOCK_WORDS][blocks_per_inst][n_inst]  (coalesced writes in k_trace)
+  const uint32_t* dtrace;   // word-major: [dtrace_words_per_inst][n_inst]
   uint32_t* gate;           // Fr as 8 x u32
   uint32_t* lookup;
   uint32_t* spread;
@@ -297,15 +297,24 @@ struct TraceArgs {
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
-// byte `pos` of the padded message (lib.rs:98-117): message | 0x80 | zeros | 64-bit BE bit length | zeros up to max
-__device__ __forceinline__ uint32_t padded_byte(const uint8_t* msg, uint32_t len, uint32_t padded_size, uint32_t pos) {
-  if (pos < len) return msg[pos];
-  if (pos == len) return 0x80u;
-  if (pos >= padded_size - 8 && pos < padded_size) {
-    uint64_t bits = 8ull * len;
-    return (uint32_t)(bits >> (8 * (padded_size - 1 - pos))) & 0xffu;
+// word `i` of 64-byte block `blk` of the padded message (lib.rs:98-117): message | 0x80 | zeros | 64-bit BE bit length |
+// zeros up to max.  Branch-free predicated byte loads so that all loads of a block are in flight together.
+__device__ __forceinline__ uint32_t padded_word(const uint8_t* msg, uint32_t len, uint32_t num_round, uint32_t blk, int i) {
+  const uint32_t pos = 64 * blk + 4 * i;
+  uint32_t x = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t p = pos + k;
+    uint32_t byte = (p < len) ? (uint32_t)msg[p] : 0u;
+    byte = (p == len) ? 0x80u : byte;
+    x = (x << 8) | byte;
   }
-  return 0u;
+  if (blk + 1 == num_round) {   // the bit length occupies the last two words of the last padded block
+    const uint64_t bits = 8ull * len;
+    if (i == 14) x = (uint32_t)(bits >> 32);
+    if (i == 15) x = (uint32_t)bits;
+  }
+  return x;
 }
 
 __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
@@ -319,13 +328,15 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
   const uint32_t len = A.lens[m];
   const uint32_t pre = A.pre_lens ? A.pre_lens[m] : 0u;
   const uint32_t num_round = (len + 9 + 63) / 64;          // lib.rs:80-84
-  const uint32_t padded_size = 64 * num_round;             // lib.rs:85
   const uint32_t pre_round = pre / 64;                     // lib.rs:93
   uint32_t st[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) st[i] = c_H0[i];
-  uint32_t* dt = A.dtrace + inst * A.dtrace_words_per_inst + dd.dtrace_off;
-  uint32_t* bt = A.btrace + (inst * A.blocks_per_inst + dd.blk_prefix) * (uint64_t)TR_BLOCK_WORDS;
+  // word-major layouts: consecutive threads (instances) write consecutive addresses
+  const uint64_t n_inst = A.n_msgs / A.n_digests;
+  uint32_t* dt = A.dtrace + (uint64_t)dd.dtrace_off * n_inst + inst;            // word k at dt + k * n_inst
+  uint32_t* bt = A.btrace + (uint64_t)dd.blk_prefix * n_inst + inst;            // word k of block j at bt[(k * bpi + j) * n_inst]
+  const uint64_t bstride = (uint64_t)A.blocks_per_inst * n_inst;
   const uint32_t words_base = TD_STATES + 8 * (R + 1);
   uint32_t hfin[8];
 #pragma unroll
@@ -334,24 +345,22 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
   for (uint32_t blk = 0; blk < pre_round + R; blk++) {
     const bool traced = blk >= pre_round;
     const uint32_t j = blk - pre_round;
-    uint32_t* tw = bt + (uint64_t)j * TR_BLOCK_WORDS;
+    uint32_t* tw = bt + (uint64_t)j * n_inst;   // word k at tw + k * bstride
     if (traced) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) dt[TD_STATES + 8 * j + i] = st[i];
+      for (int i = 0; i < 8; i++) dt[(uint64_t)(TD_STATES + 8 * j + i) * n_inst] = st[i];
     }
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-      uint32_t pos = 64 * blk + 4 * i;
-      uint32_t x = (padded_byte(msg, len, padded_size, pos) << 24) | (padded_byte(msg, len, padded_size, pos + 1) << 16) |
-                   (padded_byte(msg, len, padded_size, pos + 2) << 8) | padded_byte(msg, len, padded_size, pos + 3);
+      const uint32_t x = padded_word(msg, len, num_round, blk, i);
       w[i] = x;
-      if (traced) { tw[TR_W + i] = x; dt[words_base + 16 * j + i] = x; }
+      if (traced) { tw[(uint64_t)(TR_W + i) * bstride] = x; dt[(uint64_t)(words_base + 16 * j + i) * n_inst] = x; }
     }
     uint32_t a = st[0], b = st[1], c = st[2], dd_ = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
     if (traced) {
-      tw[TR_A + 3] = a; tw[TR_A + 2] = b; tw[TR_A + 1] = c; tw[TR_A + 0] = dd_;
-      tw[TR_E + 3] = e; tw[TR_E + 2] = f; tw[TR_E + 1] = g; tw[TR_E + 0] = h;
+      tw[(uint64_t)(TR_A + 3) * bstride] = a; tw[(uint64_t)(TR_A + 2) * bstride] = b; tw[(uint64_t)(TR_A + 1) * bstride] = c; tw[(uint64_t)(TR_A + 0) * bstride] = dd_;
+      tw[(uint64_t)(TR_E + 3) * bstride] = e; tw[(uint64_t)(TR_E + 2) * bstride] = f; tw[(uint64_t)(TR_E + 1) * bstride] = g; tw[(uint64_t)(TR_E + 0) * bstride] = h;
     }
     for (int t0 = 0; t0 < 64; t0 += 16) {
 #pragma unroll
@@ -366,12 +375,12 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
           uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
           wt = w[i] + s0 + w[(i + 9) & 15] + s1;
           w[i] = wt;
-          if (traced) tw[TR_W + t] = wt;
+          if (traced) tw[(uint64_t)(TR_W + t) * bstride] = wt;
         }
         uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + c_K[t] + wt;
         uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
         h = g; g = f; f = e; e = dd_ + t1; dd_ = c; c = b; b = a; a = t1 + t2;
-        if (traced) { tw[TR_A + 4 + t] = a; tw[TR_E + 4 + t] = e; }
+        if (traced) { tw[(uint64_t)(TR_A + 4 + t) * bstride] = a; tw[(uint64_t)(TR_E + 4 + t) * bstride] = e; }
       }
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += dd_; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
@@ -381,10 +390,10 @@ __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; i++) dt[TD_STATES + 8 * R + i] = st[i];
-  dt[TD_LEN] = len; dt[TD_NUM_ROUND] = num_round; dt[TD_PRE_ROUND] = pre_round; dt[TD_TARGET] = num_round - pre_round;
+  for (int i = 0; i < 8; i++) dt[(uint64_t)(TD_STATES + 8 * R + i) * n_inst] = st[i];
+  dt[(uint64_t)(TD_LEN) * n_inst] = len; dt[(uint64_t)(TD_NUM_ROUND) * n_inst] = num_round; dt[(uint64_t)(TD_PRE_ROUND) * n_inst] = pre_round; dt[(uint64_t)(TD_TARGET) * n_inst] = num_round - pre_round;
 #pragma unroll
-  for (int i = 0; i < 8; i++) dt[TD_H + i] = hfin[i];
+  for (int i = 0; i < 8; i++) dt[(uint64_t)(TD_H + i) * n_inst] = hfin[i];
   if (A.digests) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -583,7 +592,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         break;
       }
       // ---- decode job ----
-      uint64_t inst; uint32_t cls, gate0, lk0, limb0; const uint32_t* tr_src; uint32_t tr_words;
+      uint64_t inst, tr_stride; uint32_t cls, gate0, lk0, limb0; const uint32_t* tr_src; uint32_t tr_words;
       if (job < n_block_jobs) {
         const uint64_t blk = job / P.n_block_parts;          // global block index = inst * blocks_per_inst + r
         cls = (uint32_t)(job - blk * P.n_block_parts);        // part of the block job
@@ -596,7 +605,8 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
         lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
         limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
-        tr_src = A.btrace + blk * (uint64_t)TR_BLOCK_WORDS;
+        tr_src = A.btrace + (uint64_t)r * A.n_inst + inst;
+        tr_stride = (uint64_t)P.blocks_per_inst * A.n_inst;
         tr_words = TR_BLOCK_WORDS;
       } else {
         uint64_t kk = job - n_block_jobs;
@@ -605,11 +615,12 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         const DevDigest& dd = s_digests[d];
         cls = dd.dp.job_class;
         gate0 = 0; lk0 = 0; limb0 = 0;
-        tr_src = A.dtrace + inst * P.dtrace_words_per_inst + dd.dtrace_off;
+        tr_src = A.dtrace + (uint64_t)dd.dtrace_off * A.n_inst + inst;
+        tr_stride = A.n_inst;
         tr_words = dd.dp.trace_words;
       }
       const JobClass jc = s_classes[cls];
-      for (uint32_t i = lane; i < tr_words; i += 32) s_trace[i] = tr_src[i];
+      for (uint32_t i = lane; i < tr_words; i += 32) s_trace[i] = tr_src[(uint64_t)i * tr_stride];
       if (lane == 0) { desc->inst = inst; desc->cls = cls; desc->gate0 = gate0; desc->lk0 = lk0; desc->limb0 = limb0; desc->valid = 1; }
       __syncwarp();
       // ---- phase 1: slot programs, lanes = unit instances ----
