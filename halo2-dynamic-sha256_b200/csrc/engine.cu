@@ -707,13 +707,20 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       if (ch.gate_len) {
         const CellEntry* cells = s_cells + ch.gate_off;
         if (!straddle) {
+          // warp stores are aligned to the 128-byte lines of the output: iteration k covers the 32 cells starting at
+          // (pos0 - shift) + 32 k, shift = pos0 mod 4 cells, so only the first iteration has idle lanes
+          const uint32_t pos0 = g_lo + off0 + ch.gate_dst_min;          // position of cells[0]
+          const int shift = (int)(pos0 & 3u);
           uint32_t* out0 = gate_out + (uint64_t)(g_lo + off0) * 8;
+          const int n = (int)ch.gate_len;
 #pragma unroll 4
-          for (uint32_t i = lane; i < ch.gate_len; i += 32) {
-            const CellEntry ce = cells[i];
-            const uint32_t src = H2SHA_CE_SRC(ce);
-            const uint4 lo = ws.lo[src], hi = ws.hi[src];
-            if (gate_out) store_cell2(out0 + (uint64_t)H2SHA_CE_DST(ce) * 8, lo, hi);
+          for (int i = (int)lane - shift; i < n; i += 32) {
+            if (i >= 0) {
+              const CellEntry ce = cells[i];
+              const uint32_t src = H2SHA_CE_SRC(ce);
+              const uint4 lo = ws.lo[src], hi = ws.hi[src];
+              if (gate_out) store_cell2(out0 + (uint64_t)H2SHA_CE_DST(ce) * 8, lo, hi);
+            }
           }
         } else {
           for (uint32_t i = lane; i < ch.gate_len; i += 32) {

@@ -83,7 +83,7 @@ enum { H2SHA_MAX_FILL_LIMIT = 256 };   // the actual limit is Config::max_fill (
 
 // Fill entry: how to materialise one distinct value (same packing as TmplEntry, dst = scratch slot) plus the weight of
 // the value in the gate checksum: it is carried by `cnt` gate cells of the chunk whose unit-relative offsets sum to `sumdst`.
-struct FillEntry {
+struct alignas(16) FillEntry {
   uint32_t lo, hi;
   uint32_t cnt, sumdst;
 };
@@ -91,7 +91,7 @@ struct FillEntry {
 // multipliers of the cell checksum hash (include/h2sha_b200.h: H2SHA_CK_M)
 static const uint32_t kCkM[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
 
-struct Chunk {
+struct alignas(16) Chunk {
   uint64_t res_a, res_b;   // gate-checksum contribution of the resident constants of the chunk: res_a + res_b * (2*pos0 + 1)
   uint32_t fill_off;   // FillEntry index
   uint16_t n_fill, n_fill_table;   // distinct values to materialise; the first n_fill_table are table copies
@@ -135,7 +135,7 @@ struct WarpTask {
 };
 
 // Work item of phase 2: one chunk of one unit instance, with everything that does not depend on the job precomputed.
-struct ItemDesc {
+struct alignas(16) ItemDesc {
   uint32_t gate_rel;   // gate-stream index of the unit's first cell, relative to the job's gate base
   uint32_t lk_rel;     // same for the lookup stream
   uint32_t limb_rel;   // same for spread limbs

@@ -1015,7 +1015,18 @@ class Builder {
       for (int cls = 0; cls < 3; cls++) {
         std::vector<uint32_t> ids;
         for (uint32_t i2 = 0; i2 < nd; i2++) if (fill_class(order[i2]) == cls) ids.push_back(i2);
-        std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return loc[a] < loc[b]; });
+        // order: round-robin over the 8 bank-group residues of the scratch slots, so that the 8 lanes of a quarter-warp
+        // write (and the fill loop reads) different bank groups
+        {
+          std::vector<std::vector<uint32_t>> by_res(8);
+          std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return loc[a] < loc[b]; });
+          for (uint32_t i2 : ids) by_res[loc[i2] % 8].push_back(i2);
+          std::vector<uint32_t> inter;
+          for (size_t round = 0; inter.size() < ids.size(); round++)
+            for (int r = 0; r < 8; r++)
+              if (round < by_res[r].size()) inter.push_back(by_res[r][round]);
+          ids.swap(inter);
+        }
         for (uint32_t i2 : ids) {
           const Sym& sy = order[i2];
           if (resident[i2]) continue;
