@@ -955,11 +955,20 @@ class Builder {
       for (int kind = 0; kind < 3; kind++) {
         std::vector<uint32_t> seq;
         for (auto& pc : cur) if (pc.kind == kind) seq.push_back(index.at(sym_key(pc.s)));
-        for (size_t q = 0; q < seq.size(); q += 8) {
-          size_t qe = std::min(seq.size(), q + 8);
-          for (size_t a = q; a < qe; a++)
-            for (size_t b = a + 1; b < qe; b++)
-              if (seq[a] != seq[b]) { adj[seq[a]][seq[b]]++; adj[seq[b]][seq[a]]++; }
+        // the gate copy loop aligns its lanes to the output lines at run time (shift 0..3 cells), so which 8 cells share
+        // a quarter-warp is not fixed: weight a pair at distance d < 8 by the number of alignments (out of 8) that put
+        // both in one quarter.  Lookup / limb loops start at cell 0: fixed quarters.
+        if (kind == EV_GATE) {
+          for (size_t a = 0; a < seq.size(); a++)
+            for (size_t b = a + 1; b < std::min(seq.size(), a + 8); b++)
+              if (seq[a] != seq[b]) { uint32_t wgt = (uint32_t)(8 - (b - a)); adj[seq[a]][seq[b]] += wgt; adj[seq[b]][seq[a]] += wgt; }
+        } else {
+          for (size_t q = 0; q < seq.size(); q += 8) {
+            size_t qe = std::min(seq.size(), q + 8);
+            for (size_t a = q; a < qe; a++)
+              for (size_t b = a + 1; b < qe; b++)
+                if (seq[a] != seq[b]) { adj[seq[a]][seq[b]] += 8; adj[seq[b]][seq[a]] += 8; }
+          }
         }
       }
       const uint32_t n_res = (uint32_t)P.resident.size();
