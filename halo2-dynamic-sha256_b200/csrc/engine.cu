@@ -707,10 +707,11 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       if (ch.gate_len) {
         const CellEntry* cells = s_cells + ch.gate_off;
         if (!straddle) {
-          // warp stores are aligned to the 128-byte lines of the output: iteration k covers the 32 cells starting at
-          // (pos0 - shift) + 32 k, shift = pos0 mod 4 cells, so only the first iteration has idle lanes
+          // warp stores are aligned to 256-byte groups of the output: iteration k covers the 32 cells starting at
+          // (pos0 - shift) + 32 k, shift = pos0 mod 8 cells, so only the first iteration has idle lanes and the
+          // quarter-warp grouping is the one the planner coloured the scratch slots for
           const uint32_t pos0 = g_lo + off0 + ch.gate_dst_min;          // position of cells[0]
-          const int shift = (int)(pos0 & 3u);
+          const int shift = (int)(pos0 & 7u);
           uint32_t* out0 = gate_out + (uint64_t)(g_lo + off0) * 8;
           const int n = (int)ch.gate_len;
 #pragma unroll 4

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <array>
 #include <map>
+#include <set>
 #include <stdexcept>
 
 namespace h2sha {
@@ -913,6 +914,33 @@ class Builder {
   }
 
   // Cuts one unit's cell stream into chunks of at most cfg_.max_fill distinct values.
+  // (position of a unit's first gate cell inside its output column) mod 8, over every occurrence of the unit type in
+  // an instance: the copy loop aligns its lanes to 256-byte groups of the output, so these are the only ways the
+  // cells of a chunk can be grouped into quarter-warps.
+  std::map<std::string, std::set<uint32_t>> align_;
+  std::set<uint32_t> cur_align_;
+  void compute_alignments() {
+    Plan& P = *P_;
+    auto residue = [&](uint32_t gidx) {
+      size_t c = 0;
+      while (c + 1 < P.breaks.size() && P.breaks[c + 1] <= gidx) c++;
+      return (gidx - P.breaks[c]) & 7u;
+    };
+    for (size_t ci = 0; ci < class_recs_.size(); ci++) {
+      const ClassRec& c = class_recs_[ci];
+      std::vector<uint32_t> origins;
+      if (ci == 0) {
+        for (const DigestPlace& dp : P.digests)
+          for (uint32_t j = 0; j < dp.n_blocks; j++) origins.push_back(dp.blk_gate_base + j * dp.blk_gate_stride);
+      } else {
+        origins.push_back(0);
+      }
+      for (const GroupRec& g : c.groups)
+        for (uint32_t o : origins)
+          for (uint32_t u = 0; u < g.count; u++) align_[g.type].insert(residue(o + g.gate_base + u * g.gate_stride));
+    }
+  }
+
   void build_chunks(const UnitRec& u, UnitType* ut) {
     // pass 1: greedy, to learn how many chunks the distinct-value limit forces; pass 2: the same number of chunks with
     // balanced cell counts (multiples of 32 gate cells)
@@ -935,6 +963,18 @@ class Builder {
     uint32_t n_gate = 0, n_lk = 0, n_limb = 0, gate_in_chunk = 0;
     auto flush = [&]() {
       if (cur.empty()) return;
+      // spread-column cells: group them by output column (dense_0.., spread_0..) so that consecutive lanes store to
+      // consecutive rows of one column (the limb entries keep their slots in `cur`, only their order changes)
+      {
+        const uint32_t nc = cfg_.spread_cols;
+        std::vector<size_t> where;
+        std::vector<Pending> limbs;
+        for (size_t i2 = 0; i2 < cur.size(); i2++) if (cur[i2].kind == EV_LIMB) { where.push_back(i2); limbs.push_back(cur[i2]); }
+        std::stable_sort(limbs.begin(), limbs.end(), [&](const Pending& a, const Pending& b) {
+          return (a.dst & 1u) * nc + (a.dst >> 1) % nc < (b.dst & 1u) * nc + (b.dst >> 1) % nc;
+        });
+        for (size_t i2 = 0; i2 < where.size(); i2++) cur[where[i2]] = limbs[i2];
+      }
       // order the distinct values: TABLE | GENERIC32 | GENERIC64, stable by first use
       std::vector<Sym> order;
       std::map<uint64_t, uint32_t> index;
@@ -955,19 +995,24 @@ class Builder {
       for (int kind = 0; kind < 3; kind++) {
         std::vector<uint32_t> seq;
         for (auto& pc : cur) if (pc.kind == kind) seq.push_back(index.at(sym_key(pc.s)));
-        // the gate copy loop aligns its lanes to the output lines at run time (shift 0..3 cells), so which 8 cells share
-        // a quarter-warp is not fixed: weight a pair at distance d < 8 by the number of alignments (out of 8) that put
-        // both in one quarter.  Lookup / limb loops start at cell 0: fixed quarters.
+        // the gate copy loop aligns its lanes to 256-byte groups of the output at run time, so a quarter-warp holds the
+        // cells whose (position mod 32) lie in the same group of 8: enumerate the possible alignments of this chunk.
+        // Lookup / limb loops start at cell 0: fixed quarters.
         if (kind == EV_GATE) {
-          for (size_t a = 0; a < seq.size(); a++)
-            for (size_t b = a + 1; b < std::min(seq.size(), a + 8); b++)
-              if (seq[a] != seq[b]) { uint32_t wgt = (uint32_t)(8 - (b - a)); adj[seq[a]][seq[b]] += wgt; adj[seq[b]][seq[a]] += wgt; }
+          uint32_t first_dst = 0xffffffffu;
+          for (auto& pc : cur) if (pc.kind == EV_GATE) first_dst = std::min(first_dst, pc.dst);
+          for (uint32_t a : cur_align_) {
+            const uint32_t r = (a + first_dst) & 7u;   // position mod 8 of seq[0]
+            for (size_t i0 = 0; i0 < seq.size(); i0++)
+              for (size_t i1 = i0 + 1; i1 < seq.size() && (i1 + r) / 8 == (i0 + r) / 8; i1++)
+                if (seq[i0] != seq[i1]) { adj[seq[i0]][seq[i1]]++; adj[seq[i1]][seq[i0]]++; }
+          }
         } else {
           for (size_t q = 0; q < seq.size(); q += 8) {
             size_t qe = std::min(seq.size(), q + 8);
             for (size_t a = q; a < qe; a++)
               for (size_t b = a + 1; b < qe; b++)
-                if (seq[a] != seq[b]) { adj[seq[a]][seq[b]] += 8; adj[seq[b]][seq[a]] += 8; }
+                if (seq[a] != seq[b]) { adj[seq[a]][seq[b]] += (uint32_t)cur_align_.size(); adj[seq[b]][seq[a]] += (uint32_t)cur_align_.size(); }
           }
         }
       }
@@ -1199,11 +1244,14 @@ class Builder {
       const uint32_t nres = std::min<uint32_t>({cfg_.resident_consts, (uint32_t)byuse.size(), cfg_.max_fill / 2});
       for (uint32_t i = 0; i < nres; i++) { resident_slot_[byuse[i].second] = i; P.resident.push_back(byuse[i].second); }
     }
+    compute_alignments();
     // ---- unit types ----
     for (auto& kv : type_idx_) { if (P.type_names.size() <= kv.second) P.type_names.resize(kv.second + 1); P.type_names[kv.second] = kv.first; }
     for (size_t t = 0; t < type_recs_.size(); t++) {
       const UnitRec& u = type_recs_[t];
       UnitType ut{};
+      cur_align_ = align_[P.type_names[t]];
+      if (cur_align_.empty()) cur_align_.insert(0);
       ut.n_in = (uint32_t)u.in.size(); ut.n_slots = u.n_slots;
       ut.prog_off = (uint32_t)P.prog.size(); ut.prog_len = (uint32_t)u.prog.size();
       P.prog.insert(P.prog.end(), u.prog.begin(), u.prog.end());
@@ -1258,17 +1306,17 @@ class Builder {
       add_class(gs, P.digests[ci - 1].trace_words);
     }
     // ---- layout ----
-    auto up4 = [](uint32_t x) { return (x + 3u) & ~3u; };
+    auto up8 = [](uint32_t x) { return (x + 7u) & ~7u; };   // column strides are multiples of 8 cells (256 B)
     P.n_gate_cols = (uint32_t)P.breaks.size();
     uint32_t rows = 0;
     for (size_t c = 0; c < P.breaks.size(); c++) {
       uint32_t e = (c + 1 < P.breaks.size()) ? P.breaks[c + 1] : n_gate_;
       rows = std::max(rows, e - P.breaks[c]);
     }
-    P.gate_col_rows = up4(rows);
+    P.gate_col_rows = up8(rows);
     P.n_lookup_cols = std::max(1u, (n_lk_ + cfg_.max_rows - 1) / cfg_.max_rows);
-    P.lookup_col_rows = up4(std::min(n_lk_, cfg_.max_rows));
-    P.spread_rows = up4((n_limb_ + cfg_.spread_cols - 1) / cfg_.spread_cols);
+    P.lookup_col_rows = up8(std::min(n_lk_, cfg_.max_rows));
+    P.spread_rows = up8((n_limb_ + cfg_.spread_cols - 1) / cfg_.spread_cols);
     compute_zero_ranges(P_);
   }
 };

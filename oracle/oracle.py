@@ -153,7 +153,7 @@ class Region:
     def n_gate(self):
         return self.gate.shape[0]
 
-    def layout(self, align: int = 4) -> Layout:
+    def layout(self, align: int = 8) -> Layout:
         ends = list(self.breaks[1:]) + [self.n_gate]
         rows = max(int(e) - int(s) for s, e in zip(self.breaks, ends))
         rows = (rows + align - 1) // align * align
