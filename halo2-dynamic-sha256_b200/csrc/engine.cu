@@ -293,6 +293,8 @@ struct TraceArgs {
   uint8_t* digests;           // may be null
   const DevDigest* digests_plan;
   uint32_t blocks_per_inst, dtrace_words_per_inst;
+  unsigned long long* job_counter;   // zeroed here for the expansion kernel that follows (saves two memset nodes)
+  unsigned long long* cks;           // [n_inst][4] or null, zeroed here
 };
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
@@ -319,9 +321,11 @@ __device__ __forceinline__ uint32_t padded_word(const uint8_t* msg, uint32_t len
 
 __global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
   uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0 && A.job_counter) *A.job_counter = 0ull;
   if (m >= A.n_msgs) return;
   const uint32_t d = (uint32_t)(m % A.n_digests);
   const uint64_t inst = m / A.n_digests;
+  if (d == 0 && A.cks) { A.cks[inst * 4 + 0] = 0; A.cks[inst * 4 + 1] = 0; A.cks[inst * 4 + 2] = 0; A.cks[inst * 4 + 3] = 0; }
   const DevDigest dd = A.digests_plan[d];
   const uint32_t R = dd.dp.n_blocks;
   const uint8_t* msg = A.msgs + A.offsets[m];
@@ -1194,14 +1198,15 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   ta.pre_lens = has_pre ? e->d_pre : nullptr;
   ta.btrace = e->d_btrace; ta.dtrace = e->d_dtrace; ta.digests = dig_dev; ta.digests_plan = e->d_digests;
   ta.blocks_per_inst = e->blocks_per_inst; ta.dtrace_words_per_inst = e->dtrace_words_per_inst;
+  const bool expand = b->gate || b->lookup || b->spread || cks_dev;
+  ta.job_counter = expand ? e->d_counter : nullptr;
+  ta.cks = cks_dev;
   if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[0], st));
   k_trace<<<(unsigned)((n_msgs + 127) / 128), 128, 0, st>>>(ta);
   launches++;
   CUDA_TRY(cudaGetLastError());
   if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[1], st));
-  if (b->gate || b->lookup || b->spread || cks_dev) {
-    CUDA_TRY(cudaMemsetAsync(e->d_counter, 0, 8, st));
-    if (cks_dev) CUDA_TRY(cudaMemsetAsync(cks_dev, 0, b->n_instances * 32, st));
+  if (expand) {
     JobArgs ja{};
     ja.n_inst = b->n_instances; ja.btrace = e->d_btrace; ja.dtrace = e->d_dtrace;
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
