@@ -59,6 +59,7 @@ struct DevPlan {
   // dynamic shared memory layout after the blob
   uint32_t off_trace, off_scratch, off_misc, smem_bytes;
   uint32_t stage_bytes, stage_off_slots, stage_off_desc;   // per producer warp: trace | slots | StageDesc
+  uint32_t cons_sleep;                                     // consumers poll their full barrier with back-off
   uint32_t max_fill, scratch_bytes, n_resident;            // per consumer warp: lo[max_fill] | hi[max_fill]
   // layout
   int32_t spread_cols_shift;   // log2(spread_cols) when it is a power of two, else -1
@@ -319,7 +320,10 @@ __device__ __forceinline__ uint32_t padded_word(const uint8_t* msg, uint32_t len
   return x;
 }
 
-__global__ void __launch_bounds__(128) k_trace(TraceArgs A) {
+__global__ void __launch_bounds__(64) k_trace(TraceArgs A) {
+  // programmatic dependent launch: the expansion kernel may be scheduled now; it waits (griddepcontrol.wait) for this
+  // grid to complete before it touches the traces, the job counter or the checksums
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m == 0 && A.job_counter) *A.job_counter = 0ull;
   if (m >= A.n_msgs) return;
@@ -431,6 +435,24 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// polling wait with back-off for warps that are expected to wait long (producers waiting for a free stage): keeps
+// their retries out of the issue slots of the working warps
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -572,6 +594,8 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // blob + barriers visible; the only CTA-wide barrier
+  // everything above is independent of the trace kernel; from here on its outputs are read
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst * P.n_block_parts;
   const uint64_t n_jobs = n_block_jobs + A.n_inst * P.n_digests;
@@ -585,7 +609,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     StageDesc* desc = reinterpret_cast<StageDesc*>(stage + P.stage_off_desc);
     for (int i = lane; i < 64; i += 32) s_trace[TR_K + i] = c_K[i];
     for (uint32_t k = 0;; k++) {
-      mbar_wait(&s_empty[st], (k & 1u) ^ 1u);   // consumers are done with this stage's previous job
+      mbar_wait_relaxed(&s_empty[st], (k & 1u) ^ 1u);   // consumers are done with this stage's previous job
       unsigned long long job = 0;
       if (lane == 0) job = atomicAdd(A.job_counter, 1ULL);
       job = __shfl_sync(0xffffffffu, job, 0);
@@ -659,7 +683,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     const int st = k % NPROD;
     const uint32_t round = k / NPROD;
     if (finished & (1u << st)) continue;
-    mbar_wait(&s_full[st], round & 1u);
+    if (P.cons_sleep) mbar_wait_relaxed(&s_full[st], round & 1u); else mbar_wait(&s_full[st], round & 1u);
     const uint8_t* stage = smem + P.off_trace + (size_t)st * P.stage_bytes;
     const uint64_t* s_slots = reinterpret_cast<const uint64_t*>(stage + P.stage_off_slots);
     const StageDesc* desc = reinterpret_cast<const StageDesc*>(stage + P.stage_off_desc);
@@ -834,7 +858,8 @@ template <int NC, int NP>
 ExpandVariant make_variant() { return ExpandVariant{NC, NP, (const void*)k_expand<NC, NP>}; }
 const ExpandVariant* expand_variants(int* n) {
   static const ExpandVariant v[] = {make_variant<16, 4>(), make_variant<12, 4>(), make_variant<20, 4>(), make_variant<24, 4>(), make_variant<16, 2>(),
-                                    make_variant<20, 2>(), make_variant<24, 6>(), make_variant<8, 2>(), make_variant<8, 4>()};
+                                    make_variant<20, 2>(), make_variant<24, 6>(), make_variant<8, 2>(), make_variant<8, 4>(), make_variant<18, 6>(),
+                                    make_variant<16, 6>(), make_variant<20, 5>(), make_variant<20, 6>(), make_variant<16, 8>()};
   *n = (int)(sizeof v / sizeof v[0]);
   return v;
 }
@@ -1020,6 +1045,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.n_breaks = (uint32_t)P.breaks.size();
   D.n_digests = (uint32_t)P.digests.size();
   D.n_block_parts = P.n_block_parts;
+  D.cons_sleep = (uint32_t)tune_value("csleep", 0);
   D.off_trace = D.blob_bytes;
   D.stage_off_slots = align_up(4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
   D.stage_off_desc = align_up(D.stage_off_slots + 8 * (P.max_slots + 1), 16);
@@ -1202,7 +1228,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   ta.job_counter = expand ? e->d_counter : nullptr;
   ta.cks = cks_dev;
   if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[0], st));
-  k_trace<<<(unsigned)((n_msgs + 127) / 128), 128, 0, st>>>(ta);
+  k_trace<<<(unsigned)((n_msgs + 63) / 64), 64, 0, st>>>(ta);
   launches++;
   CUDA_TRY(cudaGetLastError());
   if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[1], st));
@@ -1215,8 +1241,16 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     {
+      // programmatic dependent launch: prologue (plan -> shared memory) overlaps the trace kernel
       void* args[2] = {(void*)&e->dplan, (void*)&ja};
-      CUDA_TRY(cudaLaunchKernel(e->variant.fn, dim3(grid), dim3((e->variant.ncons + e->variant.nprod) * 32), args, e->dplan.smem_bytes, st));
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3(grid); lc.blockDim = dim3((e->variant.ncons + e->variant.nprod) * 32);
+      lc.dynamicSmemBytes = e->dplan.smem_bytes; lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = e->timed ? 0 : 1;   // plain serialisation when kernels are timed individually
+      lc.attrs = at; lc.numAttrs = 1;
+      CUDA_TRY(cudaLaunchKernelExC(&lc, e->variant.fn, args));
     }
     launches++;
     CUDA_TRY(cudaGetLastError());
