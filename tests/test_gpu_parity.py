@@ -232,3 +232,43 @@ def test_config4_sample_properties_at_full_shape(pkg):
     assert (first[sample] == ref["checksums"]).all()
     assert int(first[sample, 3].sum()) == int(ref["checksums"][:, 3].sum())
     cfg.close()
+
+
+def test_config5_shape_33_blocks_18_columns(pkg):
+    """BASELINE configs[4] shape (max 2112 = 33 blocks, 18 gate columns at k = 17): column wraps inside units, lookup
+    column wrap, long digest traces.  Edge lengths 1, 2047, 2048, max-9 and a random one."""
+    rng = np.random.default_rng(55)
+    lens = [1, 2047, 2048, 2103, int(rng.integers(1, 2049))]
+    instances = [[bytes(rng.integers(0, 256, n, dtype=np.uint8))] for n in lens]
+    res, _ = _compare(pkg, dict(max_variable_byte_sizes=(2112,)), instances)
+    for inst, d in zip(instances, res.digests):
+        assert hashlib.sha256(inst[0]).digest() == bytes(d)
+
+
+def test_checksum_only_device_inputs_and_input_reuse(pkg):
+    """The other entry modes of h2sha_digest_batch: no cell buffers (checksums only), message bytes already on the
+    device, and reuse_inputs (inputs of the previous call still resident in HBM)."""
+    import torch
+    kw = dict(max_variable_byte_sizes=(128,))
+    cfg = _engine(pkg, kw)
+    rng = np.random.default_rng(77)
+    instances = [[bytes(rng.integers(0, 256, int(n), dtype=np.uint8))] for n in rng.integers(0, 120, size=64)]
+    full = cfg.digest_batch(instances)
+    only = cfg.digest_batch(instances, want_cells=False)
+    assert (only.checksums == full.checksums).all() and (only.digests == full.digests).all()
+    blob, offs, lens = pkg.pack_messages(instances)
+    d_blob = torch.from_numpy(np.concatenate([blob, np.zeros(16, np.uint8)])).cuda()
+    dig = np.zeros((64, 32), np.uint8); cks = np.zeros((64, 4), np.uint64)
+    st = torch.cuda.current_stream().cuda_stream
+    cfg.digest_batch_raw(64, d_blob.data_ptr(), True, int(blob.size), offs, lens, None, digests_host_ptr=dig.ctypes.data,
+                         checksums_host_ptr=cks.ctypes.data, stream=st)
+    torch.cuda.synchronize()
+    assert (cks == full.checksums).all() and (dig == full.digests).all()
+    dig[:] = 0; cks[:] = 0
+    cfg.digest_batch_raw(64, 0, True, 0, offs, lens, None, digests_host_ptr=dig.ctypes.data, checksums_host_ptr=cks.ctypes.data, stream=st,
+                         reuse_inputs=True)
+    torch.cuda.synchronize()
+    assert (cks == full.checksums).all() and (dig == full.digests).all()
+    with pytest.raises(pkg.EngineError):   # more instances than are resident
+        cfg.digest_batch_raw(65, 0, True, 0, offs, lens, None, reuse_inputs=True)
+    cfg.close()
