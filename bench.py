@@ -284,6 +284,14 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        traffic = None   # dram__bytes_read + dram__bytes_write of one k_expand launch, from the committed ncu capture of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "k_expand_traffic.json")) as f:
+                tj = json.load(f)
+            if tj["workload"] == w.name and tj["instances_per_launch"] == per_gpu:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         alg_bytes = per_gpu * lay.cells_per_instance * 32
         achieved = alg_bytes / (expand_ms * 1e-3) / 1e9
         line = {
@@ -300,7 +308,7 @@ def main():
                     "note": "host message buffers -> h2sha_digest_batch -> digests+checksums on host; the witness stays in HBM for the prover"},
             "gpu_launches": 2 * args.steps,
             "kernels_ms": {"k_trace": trace_ms, "k_expand": expand_ms},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_expand", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "verified_instances_vs_oracle": verified, "job_checksum": job_ck,
