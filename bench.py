@@ -266,6 +266,7 @@ def main():
         m = bytes(blob[int(offs[i]):int(offs[i]) + int(lens[i])])
         assert hashlib.sha256(m).digest() == bytes(dig[i]), f"digest mismatch at instance {first + i}"
     verified = 0
+    mock_prover_instances = 0
     if args.verify:
         from oracle import oracle as O
         ocfg = O.OracleConfig(max_variable_byte_sizes=tuple(w.max_variable_byte_sizes))
@@ -278,6 +279,25 @@ def main():
         assert (spread[:nv].cpu().numpy().view(np.uint64) == ref["spread"]).all(), "spread cells differ from oracle"
         assert (h_cks.numpy().view(np.uint64)[:nv] == ref["checksums"]).all(), "checksums differ from oracle"
         verified = nv
+        # MockProver-style pass on one sampled instance of the GPU output with the product's own shape plan:
+        # every gate, copy constraint, range / spread lookup, and the digest bytes (reference lib.rs:525-526)
+        from oracle import mock_prover as MP
+        shp_cfg = pkg.Sha256DynamicConfig.configure(list(w.max_variable_byte_sizes), device=-1, build_shape=True)
+        sh, brk = shp_cfg.shape(), shp_cfg.breaks()
+        i0 = nv - 1
+        g = gate[i0].cpu().numpy().view(np.uint64); lk = lookup[i0].cpu().numpy().view(np.uint64); sp = spread[i0].cpu().numpy().view(np.uint64)
+        ends = list(brk[1:]) + [lay.n_gate_cells]
+        stream_cells = np.concatenate([g[c, : int(e_) - int(s_)] for c, (s_, e_) in enumerate(zip(brk, ends))])
+        nc = lay.n_spread_cols // 2
+        nl = np.arange(lay.n_spread_limbs)
+        consts_mont = np.array([O.int_to_mont(int(a) | int(b_) << 64 | int(c) << 128 | int(d_) << 192) for a, b_, c, d_ in sh.fixed], dtype=np.uint64)
+        msg0 = bytes(blob[int(offs[i0]):int(offs[i0]) + int(lens[i0])])
+        MP.verify(gate=stream_cells, selectors=sh.selectors, breaks=brk, lookup_idx=sh.lookup_src, dense=sp[nl % nc, nl // nc],
+                  spread=sp[nc + nl % nc, nl // nc], limb_gate_dense=sh.limb_dense_src, limb_gate_spread=sh.limb_spread_src, copies=sh.copies,
+                  consts=consts_mont, lookup_bits=16, limb_bits=8, max_rows=(1 << 17) - 9, output_bytes_idx=[shp_cfg.handles(0).output_bytes],
+                  expected_digests=[hashlib.sha256(msg0).digest()])
+        assert (np.concatenate([lk[c] for c in range(lay.n_lookup_cols)])[: lay.n_lookup_cells] == stream_cells[sh.lookup_src]).all()
+        mock_prover_instances = 1
     # the only collective: gather digests + checksums (64 B / instance) after the hot path
     sh = ge.load_package_module("sharding")
     _, _, job_ck = sh.gather_results(d_digests, d_cks, world)
@@ -311,7 +331,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_expand", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
-            "verified_instances_vs_oracle": verified, "job_checksum": job_ck,
+            "verified_instances_vs_oracle": verified, "mock_prover_instances": mock_prover_instances, "job_checksum": job_ck,
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1
