@@ -1,12 +1,13 @@
 // h2sha_defs.h -- data structures shared by the host planner and the sm_100a kernels.
 //
-// The engine is a two-phase, template-driven expander:
+// The engine is a two-phase, plan-driven expander:
 //   phase 1 ("slots"):  per unit instance (one SHA-256 round, one schedule step, ...) a tiny
 //                       straight-line VM program turns a few u32 trace words into <= 255 raw u64 "slots";
-//   phase 2 ("cells"):  a static per-unit-type template maps every advice / lookup / spread-column cell to
-//                       (slot, shift, width) or a constant; the kernel converts to BN254 Fr Montgomery form
-//                       and stores the cell at its final (column,row).
-// Both the VM programs and the templates are produced once per configuration by the host planner
+//   phase 2 ("cells"):  per chunk of a unit, every distinct value ((slot >> sh) & mask, a table lookup of it, a
+//                       constant, ...) is converted once to BN254 Fr Montgomery form in a per-warp scratch table
+//                       (fill), then every advice / lookup / spread-column cell is a 32-byte copy from that table
+//                       to its final (column,row).
+// The VM programs, fill lists and cell lists are produced once per configuration by the host planner
 // (planner.cc), which walks the reference's call order (lib.rs:71-349 -> compression.rs:19-213 ->
 // spread.rs:76-233) symbolically.
 #pragma once
@@ -15,7 +16,7 @@
 namespace h2sha {
 
 // ---------------------------------------------------------------------------------------------
-// Template entry: one output cell.  8 bytes.
+// Value descriptor ("template entry"): how one Fr value derives from the unit's slots.  8 bytes.
 //   lo: dst (16)  | tbl (16)
 //   hi: slot (8) | sh (6) | w (7) | shl (5) | kind (2) | neg (1)
 // value(raw)  = ((slots[slot] >> sh) & mask(w)) << shl          (w == 0 -> 0, w == 64 -> all bits)
