@@ -1,0 +1,34 @@
+"""Builds and runs the C++ host-side parity test (tests/cpp/test_reference_vectors.cc) that mirrors the reference's own
+test_sha256_correct1..4 over the C-ABI: no Python between the test and libh2sha_b200.so."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(pkg):
+    from oracle import oracle as O
+    O.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_reference_vectors")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "test_reference_vectors.cc")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O1", "-o", exe, src, "-L" + libdir, "-lh2sha_b200", "-ldl",
+                           "-Xlinker", "-rpath," + libdir, "-cudart", "shared"])
+    return exe
+
+
+def test_cpp_host_test_compiles_and_links(pkg):
+    """CPU part: the C++ host API (csrc/host_api.hpp) compiles against include/h2sha_b200.h and links the library."""
+    assert os.path.exists(_build(pkg))
+
+
+@pytest.mark.gpu
+def test_reference_tests_through_cpp_host_api(pkg):
+    exe = _build(pkg)
+    out = subprocess.run([exe, os.path.join(ROOT, "oracle", "_build", "libh2sha_oracle.so")], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok ") == 5
