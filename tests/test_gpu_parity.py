@@ -272,3 +272,15 @@ def test_checksum_only_device_inputs_and_input_reuse(pkg):
     with pytest.raises(pkg.EngineError):   # more instances than are resident
         cfg.digest_batch_raw(65, 0, True, 0, offs, lens, None, reuse_inputs=True)
     cfg.close()
+
+
+def test_random_configurations_cells_property(pkg):
+    """Property test (seeded): random chip configurations and random messages, every cell against the oracle."""
+    rng = np.random.default_rng(4242)
+    for _ in range(6):
+        kw = dict(max_variable_byte_sizes=tuple(int(64 * rng.integers(1, 4)) for _ in range(int(rng.integers(1, 3)))),
+                  lookup_bits=int(rng.choice([8, 9, 10, 11, 12, 13, 14, 16, 17, 18, 19, 20])), limb_bits=int(rng.choice([2, 4, 8])), spread_cols=int(rng.integers(1, 4)),
+                  is_input_range_check=bool(rng.integers(0, 2)), max_rows=int(rng.integers(3000, 200000)))
+        instances = [[bytes(rng.integers(0, 256, int(rng.integers(0, m - 8)), dtype=np.uint8)) for m in kw["max_variable_byte_sizes"]]
+                     for _ in range(3)]
+        _compare(pkg, kw, instances)

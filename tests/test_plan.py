@@ -81,3 +81,23 @@ def test_wider_column_strides(pkg):
     assert lay.gate_bytes == (1 << 17) * 32 and lay.spread_bytes == 4 * (1 << 17) * 32
     with pytest.raises(pkg.EngineError):
         _engine(pkg, dict(max_variable_byte_sizes=(64,)), gate_col_rows=1000)
+
+
+def test_random_configurations_shape_property(pkg):
+    """Property test (seeded): for random chip configurations the planner's shape equals the oracle's."""
+    rng = np.random.default_rng(2024)
+    for _ in range(12):
+        kw = dict(max_variable_byte_sizes=tuple(int(64 * rng.integers(1, 4)) for _ in range(int(rng.integers(1, 3)))),
+                  lookup_bits=int(rng.choice([8, 9, 10, 11, 12, 13, 14, 16, 17, 18, 19, 20])), limb_bits=int(rng.choice([1, 2, 4, 8])), spread_cols=int(rng.integers(1, 5)),
+                  is_input_range_check=bool(rng.integers(0, 2)), max_rows=int(rng.integers(3000, 200000)))
+        cfg = _engine(pkg, kw)
+        sh, lay = cfg.shape(), cfg.layout
+        D = len(kw["max_variable_byte_sizes"])
+        msgs = [bytes(rng.integers(0, 256, int(rng.integers(0, m - 8)), dtype=np.uint8)) for m in kw["max_variable_byte_sizes"]]
+        reg = O.synthesize(O.OracleConfig(**kw), msgs)
+        assert (lay.n_gate_cells, lay.n_lookup_cells, lay.n_spread_limbs) == (reg.n_gate, len(reg.lookup_idx), reg.dense.shape[0]), kw
+        assert (cfg.breaks() == reg.breaks).all(), kw
+        assert (sh.selectors == reg.selectors).all() and (sh.copies == reg.copies).all(), kw
+        assert (sh.lookup_src == reg.lookup_idx).all(), kw
+        assert [int(a) | int(b) << 64 | int(c) << 128 | int(d) << 192 for a, b, c, d in sh.fixed] == [O.mont_to_int(c) for c in reg.consts], kw
+        cfg.close()
