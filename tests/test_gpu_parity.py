@@ -284,3 +284,38 @@ def test_random_configurations_cells_property(pkg):
         instances = [[bytes(rng.integers(0, 256, int(rng.integers(0, m - 8)), dtype=np.uint8)) for m in kw["max_variable_byte_sizes"]]
                      for _ in range(3)]
         _compare(pkg, kw, instances)
+
+
+def test_no_out_of_bounds_writes_guard_bands(pkg):
+    """compute-sanitizer is closed on this pool, so bound the writes ourselves: every output buffer sits between two
+    sentinel bands that must stay intact, for a multi-column configuration and a batch larger than the CTA count."""
+    import torch
+    kw = dict(max_variable_byte_sizes=(128,), max_rows=20011)
+    cfg = _engine(pkg, kw)
+    lay = cfg.layout
+    n, band = 200, 4096
+    rng = np.random.default_rng(99)
+    instances = [[bytes(rng.integers(0, 256, int(rng.integers(0, 120)), dtype=np.uint8))] for _ in range(n)]
+    blob, offs, lens = pkg.pack_messages(instances)
+    sentinel = 0x5A5A5A5A5A5A5A5A
+    bufs = []
+    for nbytes in (lay.gate_bytes, lay.lookup_bytes, lay.spread_bytes):
+        t = torch.full((band + n * nbytes // 8 + band,), sentinel, dtype=torch.int64, device="cuda")
+        bufs.append(t)
+    dig = np.zeros((n, 32), np.uint8); cks = np.zeros((n, 4), np.uint64)
+    cfg.digest_batch_raw(n, blob.ctypes.data, False, int(blob.size), offs, lens, None, gate_ptr=bufs[0].data_ptr() + band * 8,
+                         lookup_ptr=bufs[1].data_ptr() + band * 8, spread_ptr=bufs[2].data_ptr() + band * 8, digests_host_ptr=dig.ctypes.data,
+                         checksums_host_ptr=cks.ctypes.data, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for t in bufs:
+        assert (t[:band] == sentinel).all() and (t[-band:] == sentinel).all(), "write outside the output buffer"
+    olay = O.Layout(lay.n_gate_cols, lay.gate_col_rows, lay.n_lookup_cols, lay.lookup_col_rows, lay.spread_rows)
+    ref = O.batch(_oracle_cfg(kw), olay, instances, None, want_cells=False, n_threads=NCPU)
+    assert (cks == ref["checksums"]).all() and (dig == ref["digests"]).all()
+    # assigned cells differ from the sentinel; everything unassigned still holds it
+    g = bufs[0][band:-band].view(n, lay.n_gate_cols, lay.gate_col_rows, 4)
+    brk = list(cfg.breaks()) + [lay.n_gate_cells]
+    for c in range(lay.n_gate_cols):
+        used = int(brk[c + 1]) - int(brk[c])
+        assert (g[:, c, used:] == sentinel).all(), "unassigned gate rows were written"
+    cfg.close()
