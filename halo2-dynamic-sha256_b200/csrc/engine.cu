@@ -423,9 +423,10 @@ struct WarpScratch {   // runtime-sized: lo[max_fill] | hi[max_fill]; slots [0, 
 };
 // job descriptor a producer warp leaves in its stage
 struct StageDesc {
-  unsigned long long inst;
+  unsigned long long inst;      // first circuit instance of the job
   uint32_t cls, gate0, lk0, limb0;
-  uint32_t valid, pad;
+  uint32_t valid;               // 0: the producer has run out of jobs
+  uint32_t n_inst;              // circuit instances the job covers (digest jobs are batched)
 };
 
 // ---- mbarrier helpers (shared::cta) ----
@@ -473,12 +474,13 @@ __device__ __forceinline__ uint64_t vm_operand(uint32_t o, const uint64_t* slots
   return extract(slots[(o >> 1) & 0xfffu], (o >> 13) & 63u, (o >> 19) & 127u);
 }
 
-// phase 1: run the slot program of group `g` for unit instance `u` (one lane)
-__device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitType& ut, uint32_t u, const VmIns* prog, const uint64_t* raw,
+// phase 1: run the slot program of group `g` for unit instance `u` (one lane); `trace` is the trace of the circuit
+// instance the unit belongs to and `uu` the unit's index inside that instance
+__device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitType& ut, uint32_t uu, const VmIns* prog, const uint64_t* raw,
                                                  const uint32_t* trace, uint64_t* slots) {
   for (uint32_t k = 0; k < ut.n_in; k++) {
     int32_t base = g.in[k].base;
-    slots[k] = (base < 0) ? (uint64_t)(g.in[k].stride + (int32_t)u) : (uint64_t)trace[base + g.in[k].stride * (int32_t)u];
+    slots[k] = (base < 0) ? (uint64_t)(g.in[k].stride + (int32_t)uu) : (uint64_t)trace[base + g.in[k].stride * (int32_t)uu];
   }
   const VmIns* ins = prog + ut.prog_off;
   for (uint32_t pc = 0; pc < ut.prog_len; pc++) {
@@ -558,6 +560,23 @@ __device__ __forceinline__ void store_cell2(uint32_t* p, const uint4& lo, const 
                : "memory");
 }
 
+// warp-reduce the three checksum accumulators and add them to the instance's totals (gate, lookup, spread, all)
+__device__ __forceinline__ void flush_checksums(unsigned long long* cks, uint64_t inst, unsigned long long ck_g, unsigned long long ck_l,
+                                                unsigned long long ck_s, int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ck_g += __shfl_xor_sync(0xffffffffu, ck_g, o);
+    ck_l += __shfl_xor_sync(0xffffffffu, ck_l, o);
+    ck_s += __shfl_xor_sync(0xffffffffu, ck_s, o);
+  }
+  if (lane == 0) {
+    if (ck_g) atomicAdd(&cks[inst * 4 + 0], ck_g);
+    if (ck_l) atomicAdd(&cks[inst * 4 + 1], ck_l);
+    if (ck_s) atomicAdd(&cks[inst * 4 + 2], ck_s);
+    atomicAdd(&cks[inst * 4 + 3], ck_g + ck_l + ck_s);
+  }
+}
+
 // Warp-specialised persistent kernel: NPROD producer warps run phase 1 (job fetch, trace load, slot programs) into
 // their own stage buffer; NCONS consumer warps run phase 2 (fill + copy) stage after stage.  Stages are handed over
 // with mbarriers, so no warp ever waits at a CTA-wide barrier inside the job loop.
@@ -597,8 +616,13 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
   // everything above is independent of the trace kernel; from here on its outputs are read
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
+  // jobs: all block-job parts first, then per digest the batched prologue/epilogue jobs
   const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst * P.n_block_parts;
-  const uint64_t n_jobs = n_block_jobs + A.n_inst * P.n_digests;
+  uint64_t n_jobs = n_block_jobs;
+  for (uint32_t d = 0; d < P.n_digests; d++) {
+    const uint32_t batch = s_classes[s_digests[d].dp.job_class].batch;
+    n_jobs += (A.n_inst + batch - 1) / batch;
+  }
 
   if (warp >= NCONS) {
     // =========================== producer warp: owns stage `st` ===========================
@@ -620,7 +644,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         break;
       }
       // ---- decode job ----
-      uint64_t inst, tr_stride; uint32_t cls, gate0, lk0, limb0; const uint32_t* tr_src; uint32_t tr_words;
+      uint64_t inst; uint32_t cls, gate0, lk0, limb0, n_valid = 1, tr_words;
       if (job < n_block_jobs) {
         const uint64_t blk = job / P.n_block_parts;          // global block index = inst * blocks_per_inst + r
         cls = (uint32_t)(job - blk * P.n_block_parts);        // part of the block job
@@ -633,33 +657,46 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
         lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
         limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
-        tr_src = A.btrace + (uint64_t)r * A.n_inst + inst;
-        tr_stride = (uint64_t)P.blocks_per_inst * A.n_inst;
+        const uint32_t* tr_src = A.btrace + (uint64_t)r * A.n_inst + inst;
+        const uint64_t tr_stride = (uint64_t)P.blocks_per_inst * A.n_inst;
         tr_words = TR_BLOCK_WORDS;
+        for (uint32_t i = lane; i < tr_words; i += 32) s_trace[i] = tr_src[(uint64_t)i * tr_stride];
       } else {
         uint64_t kk = job - n_block_jobs;
-        inst = kk / P.n_digests;
-        uint32_t d = (uint32_t)(kk - inst * P.n_digests);
+        uint32_t d = 0, batch = s_classes[s_digests[0].dp.job_class].batch;
+        for (;;) {
+          const uint64_t nb = (A.n_inst + batch - 1) / batch;
+          if (kk < nb) break;
+          kk -= nb; d++;
+          batch = s_classes[s_digests[d].dp.job_class].batch;
+        }
         const DevDigest& dd = s_digests[d];
         cls = dd.dp.job_class;
+        inst = kk * batch;
+        n_valid = (uint32_t)min((uint64_t)batch, A.n_inst - inst);
         gate0 = 0; lk0 = 0; limb0 = 0;
-        tr_src = A.dtrace + (uint64_t)dd.dtrace_off * A.n_inst + inst;
-        tr_stride = A.n_inst;
         tr_words = dd.dp.trace_words;
+        // word-major global layout: consecutive instances are adjacent, so lanes run over the instances of the batch
+        const uint32_t* tr_src = A.dtrace + (uint64_t)dd.dtrace_off * A.n_inst + inst;
+        for (uint32_t idx = lane; idx < tr_words * n_valid; idx += 32) {
+          const uint32_t k2 = idx / n_valid, i2 = idx - k2 * n_valid;
+          s_trace[i2 * tr_words + k2] = tr_src[(uint64_t)k2 * A.n_inst + i2];
+        }
       }
       const JobClass jc = s_classes[cls];
-      for (uint32_t i = lane; i < tr_words; i += 32) s_trace[i] = tr_src[(uint64_t)i * tr_stride];
-      if (lane == 0) { desc->inst = inst; desc->cls = cls; desc->gate0 = gate0; desc->lk0 = lk0; desc->limb0 = limb0; desc->valid = 1; }
+      if (lane == 0) { desc->inst = inst; desc->cls = cls; desc->gate0 = gate0; desc->lk0 = lk0; desc->limb0 = limb0; desc->valid = 1; desc->n_inst = n_valid; }
       __syncwarp();
       // ---- phase 1: slot programs, lanes = unit instances ----
       for (uint32_t t = 0; t < jc.n_tasks; t++) {
         const WarpTask wt = s_tasks[jc.task_off + t];
         const UnitGroup& g = s_groups[jc.group_off + wt.group];
         const UnitType& ut = s_types[g.type];
-        uint32_t u = wt.first + lane;
-        if (u < g.count) run_unit_program(g, ut, u, s_prog, s_raw, s_trace, s_slots + g.slot_base + u * (ut.n_slots | 1u));
+        const uint32_t u = wt.first + lane;
+        const uint32_t ii = u / g.per_inst, uu = u - ii * g.per_inst;   // circuit instance inside the job, unit inside the instance
+        if (u < g.count && ii < n_valid)
+          run_unit_program(g, ut, uu, s_prog, s_raw, s_trace + ii * tr_words, s_slots + g.slot_base + u * (ut.n_slots | 1u));
       }
-      if (tr_words > TR_K) {  // a long digest trace overwrote the round constants kept at TR_K for block jobs: restore them
+      if (tr_words * n_valid > TR_K) {  // a digest trace overwrote the round constants kept at TR_K for block jobs: restore them
         __syncwarp();
         for (int i = lane; i < 64; i += 32) s_trace[TR_K + i] = c_K[i];
       }
@@ -688,18 +725,21 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     const uint64_t* s_slots = reinterpret_cast<const uint64_t*>(stage + P.stage_off_slots);
     const StageDesc* desc = reinterpret_cast<const StageDesc*>(stage + P.stage_off_desc);
     if (!desc->valid) { finished |= 1u << st; continue; }   // this producer has run out of jobs and exited
-    const uint64_t inst = desc->inst;
-    const uint32_t gate0 = desc->gate0, lk0 = desc->lk0, limb0 = desc->limb0;
+    const uint64_t inst0 = desc->inst;
+    const uint32_t gate0 = desc->gate0, lk0 = desc->lk0, limb0 = desc->limb0, n_valid = desc->n_inst;
     const JobClass jc = s_classes[desc->cls];
     unsigned long long ck_g = 0, ck_l = 0, ck_s = 0;
-    uint32_t* gate_out = A.gate ? A.gate + inst * P.gate_inst_cells * 8 : nullptr;
-    uint32_t* lk_out = A.lookup ? A.lookup + inst * P.lookup_inst_cells * 8 : nullptr;
-    uint32_t* sp_out = A.spread ? A.spread + inst * P.spread_inst_cells * 8 : nullptr;
     // static item -> warp assignment, rotated per job so that the heavier leading items do not always hit the same warps
     for (uint32_t it = (uint32_t)(warp + k) % NCONS; it < jc.n_items; it += NCONS) {
       const ItemDesc item = s_items[jc.item_off + it];
-      const Chunk ch = s_chunks[item.slot_chunk >> 16];
-      const uint64_t* slots = s_slots + (item.slot_chunk & 0xffffu);
+      const uint32_t inst_off = H2SHA_ITEM_INST(item.slot_chunk);
+      if (inst_off >= n_valid) continue;   // partial last batch of digest jobs (warp-uniform)
+      const uint64_t inst = inst0 + inst_off;
+      uint32_t* gate_out = A.gate ? A.gate + inst * P.gate_inst_cells * 8 : nullptr;
+      uint32_t* lk_out = A.lookup ? A.lookup + inst * P.lookup_inst_cells * 8 : nullptr;
+      uint32_t* sp_out = A.spread ? A.spread + inst * P.spread_inst_cells * 8 : nullptr;
+      const Chunk ch = s_chunks[H2SHA_ITEM_CHUNK(item.slot_chunk)];
+      const uint64_t* slots = s_slots + H2SHA_ITEM_SLOT(item.slot_chunk);
       // ---- positions of the chunk's gate cells; a column break inside the chunk (rare) takes the per-cell path ----
       const uint32_t g_lo = gate0 + item.gate_rel;   // instance-relative gate-stream index of the unit's first cell
       uint32_t c0 = 0;
@@ -800,25 +840,16 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           ck_s += (unsigned long long)hash8(lo, hi) * (unsigned long long)(2u * pos + 1u);
         }
       }
+      if (A.cks && jc.batch > 1) {   // batched digest jobs: the items of a warp belong to different instances
+        flush_checksums(A.cks, inst, ck_g, ck_l, ck_s, lane);
+        ck_g = 0; ck_l = 0; ck_s = 0;
+      }
       __syncwarp();  // scratch is overwritten by the next item's fill
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[st]);   // this warp no longer reads the stage
-    // ---- checksums: warp reduce, one global atomic per kind and warp ----
-    if (A.cks) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ck_g += __shfl_xor_sync(0xffffffffu, ck_g, o);
-        ck_l += __shfl_xor_sync(0xffffffffu, ck_l, o);
-        ck_s += __shfl_xor_sync(0xffffffffu, ck_s, o);
-      }
-      if (lane == 0) {
-        if (ck_g) atomicAdd(&A.cks[inst * 4 + 0], ck_g);
-        if (ck_l) atomicAdd(&A.cks[inst * 4 + 1], ck_l);
-        if (ck_s) atomicAdd(&A.cks[inst * 4 + 2], ck_s);
-        atomicAdd(&A.cks[inst * 4 + 3], ck_g + ck_l + ck_s);
-      }
-    }
+    // ---- checksums: warp reduce, one global atomic per kind and warp (block jobs: one instance per job) ----
+    if (A.cks && jc.batch == 1) flush_checksums(A.cks, inst0, ck_g, ck_l, ck_s, lane);
   }
 }
 
@@ -971,6 +1002,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   pc.block_parts = (uint32_t)tune_value("parts", (int)pc.block_parts);
   pc.max_fill = (uint32_t)tune_value("fill", (int)pc.max_fill);
   pc.resident_consts = (uint32_t)tune_value("res", (int)pc.resident_consts);
+  pc.digest_batch = (uint32_t)tune_value("dbatch", (int)pc.digest_batch);
   h2sha_engine* e = new h2sha_engine();
   std::string err;
   if (!build_plan(pc, &e->plan, &err)) { delete e; return set_err(H2SHA_EINVAL, err); }
@@ -1237,7 +1269,11 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     ja.n_inst = b->n_instances; ja.btrace = e->d_btrace; ja.dtrace = e->d_dtrace;
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
     ja.cks = cks_dev; ja.job_counter = e->d_counter;
-    uint64_t n_jobs = b->n_instances * ((uint64_t)e->blocks_per_inst * P.n_block_parts + D);
+    uint64_t n_jobs = b->n_instances * (uint64_t)e->blocks_per_inst * P.n_block_parts;
+    for (uint32_t d = 0; d < D; d++) {
+      const uint32_t batch = P.classes[P.digests[d].job_class].batch;
+      n_jobs += (b->n_instances + batch - 1) / batch;
+    }
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     {

@@ -122,7 +122,8 @@ enum { MAX_UNIT_INPUTS = 20 };
 // A group = `count` consecutive instances of one unit type inside a job.
 struct UnitGroup {
   uint32_t type;
-  uint32_t count;
+  uint32_t count;                // unit instances in the job = per_inst * (instances the job covers)
+  uint32_t per_inst;             // unit instances per circuit instance (== count for block jobs, which cover one instance)
   uint32_t slot_base;            // offset (in u64) of instance 0's slots in the job's slot area
   uint32_t gate_base, gate_stride;   // gate-stream index of instance 0 relative to the job's gate base, and per-instance stride
   uint32_t lk_base, lk_stride;       // same for the lookup stream
@@ -140,8 +141,13 @@ struct alignas(16) ItemDesc {
   uint32_t gate_rel;   // gate-stream index of the unit's first cell, relative to the job's gate base
   uint32_t lk_rel;     // same for the lookup stream
   uint32_t limb_rel;   // same for spread limbs
-  uint32_t slot_chunk; // slot_off (16: offset in u64 units of the unit instance's slots in the job's slot area) | Chunk index (16)
+  uint32_t slot_chunk; // slot_off (16: offset in u64 units of the unit's slots in the job's slot area) | Chunk index (11) |
+                       // inst_off (5: which of the job's circuit instances the unit belongs to)
 };
+#define H2SHA_ITEM_SLOT(x) ((x) & 0xffffu)
+#define H2SHA_ITEM_CHUNK(x) (((x) >> 16) & 0x7ffu)
+#define H2SHA_ITEM_INST(x) ((x) >> 27)
+enum { H2SHA_MAX_JOB_BATCH = 32 };
 
 // A job class: (a part of) the block job (one sha256_compression) or the per-digest prologue/epilogue job.
 struct JobClass {
@@ -149,7 +155,10 @@ struct JobClass {
   uint32_t task_off, n_tasks;    // WarpTask (phase 1)
   uint32_t item_off, n_items;    // phase-2 work items, heaviest first
   uint32_t n_slots_total;        // u64 slots needed in shared memory
-  uint32_t n_trace_words;        // u32 words of trace the job loads
+  uint32_t n_trace_words;        // u32 words of trace the job loads, per circuit instance
+  uint32_t batch;                // circuit instances one job covers (1 for block jobs; digest jobs are batched so that the
+                                 // lanes of the slot VM are filled and its latency is amortised)
+  uint32_t pad;
 };
 
 // Trace layout of a block job (u32 words), written by the trace kernel:

@@ -1145,13 +1145,20 @@ class Builder {
   }
 
   // appends a JobClass made of `groups` (already with final counts / bases / input maps)
-  void add_class(const std::vector<UnitGroup>& groups, uint32_t n_trace_words) {
+  // appends a JobClass made of `groups` (final per-instance counts / bases / input maps); one job covers `batch`
+  // consecutive circuit instances: unit instance u' of a group belongs to instance u' / per_inst
+  void add_class(const std::vector<UnitGroup>& groups_in, uint32_t n_trace_words, uint32_t batch) {
     Plan& P = *P_;
     JobClass jc{};
-    jc.group_off = (uint32_t)P.groups.size(); jc.n_groups = (uint32_t)groups.size();
-    if (groups.size() > 255) fail("too many groups in a job class");
+    jc.group_off = (uint32_t)P.groups.size(); jc.n_groups = (uint32_t)groups_in.size();
+    jc.batch = batch;
+    if (groups_in.size() > 255) fail("too many groups in a job class");
+    if (batch == 0 || batch > H2SHA_MAX_JOB_BATCH) fail("bad job batch");
+    std::vector<UnitGroup> groups = groups_in;
     uint32_t slot_base = 0;
-    for (UnitGroup g : groups) {
+    for (UnitGroup& g : groups) {
+      g.per_inst = g.count;
+      g.count = g.per_inst * batch;
       g.slot_base = slot_base;
       slot_base += g.count * (P.types[g.type].n_slots | 1u);
       P.groups.push_back(g);
@@ -1170,17 +1177,18 @@ class Builder {
     jc.item_off = (uint32_t)P.items.size();
     std::vector<std::pair<uint32_t, ItemDesc>> its;
     for (uint32_t gi = 0; gi < groups.size(); gi++) {
-      const UnitGroup& g = P.groups[jc.group_off + gi];
+      const UnitGroup& g = groups[gi];
       const UnitType& ut = P.types[g.type];
       for (uint32_t u = 0; u < g.count; u++)
         for (uint32_t c = 0; c < ut.n_chunks; c++) {
           ItemDesc d{};
           const uint32_t slot_off = g.slot_base + u * (ut.n_slots | 1u);
-          if (slot_off > 0xffff || ut.chunk_off + c > 0xffff) fail("item descriptor overflow (job class too large)");
-          d.gate_rel = g.gate_base + u * g.gate_stride;
-          d.lk_rel = g.lk_base + u * g.lk_stride;
-          d.limb_rel = g.limb_base + u * g.limb_stride;
-          d.slot_chunk = slot_off | ((ut.chunk_off + c) << 16);
+          const uint32_t inst_off = u / g.per_inst, uu = u % g.per_inst;
+          if (slot_off > 0xffff || ut.chunk_off + c > 0x7ff || inst_off > 31) fail("item descriptor overflow (job class too large)");
+          d.gate_rel = g.gate_base + uu * g.gate_stride;
+          d.lk_rel = g.lk_base + uu * g.lk_stride;
+          d.limb_rel = g.limb_base + uu * g.limb_stride;
+          d.slot_chunk = slot_off | ((ut.chunk_off + c) << 16) | (inst_off << 27);
           its.push_back({chunk_cost(P.chunks[ut.chunk_off + c]), d});
         }
     }
@@ -1188,7 +1196,7 @@ class Builder {
     for (auto& it : its) P.items.push_back(it.second);
     jc.n_items = (uint32_t)its.size();
     jc.n_trace_words = n_trace_words;
-    P.max_trace_words = std::max(P.max_trace_words, n_trace_words);
+    P.max_trace_words = std::max(P.max_trace_words, n_trace_words * batch);
     P.classes.push_back(jc);
   }
 
@@ -1297,13 +1305,22 @@ class Builder {
       }
       while (!part_groups.empty() && part_groups.back().empty()) part_groups.pop_back();
       P.n_block_parts = (uint32_t)part_groups.size();
-      for (auto& pg : part_groups) add_class(pg, (uint32_t)TR_BLOCK_WORDS_WITH_K);
+      for (auto& pg : part_groups) add_class(pg, (uint32_t)TR_BLOCK_WORDS_WITH_K, 1);
     }
+    const uint32_t block_slots = P.max_slots;
     for (size_t ci = 1; ci < class_recs_.size(); ci++) {
       std::vector<UnitGroup> gs;
-      for (const GroupRec& g : class_recs_[ci].groups) gs.push_back(make_group(g, 0, g.count));
+      uint32_t slots_one = 0;
+      for (const GroupRec& g : class_recs_[ci].groups) {
+        gs.push_back(make_group(g, 0, g.count));
+        slots_one += g.count * (P.types[gs.back().type].n_slots | 1u);
+      }
+      // batch as many instances per digest job as fit in the stage a block job needs anyway (slots and item encoding)
+      uint32_t batch = cfg_.digest_batch ? cfg_.digest_batch : H2SHA_MAX_JOB_BATCH;
+      batch = std::min<uint32_t>(batch, H2SHA_MAX_JOB_BATCH);
+      while (batch > 1 && (slots_one * batch > std::max(block_slots, slots_one) || slots_one * batch > 0xffff)) batch--;
       P.digests[ci - 1].job_class = (uint32_t)P.classes.size();
-      add_class(gs, P.digests[ci - 1].trace_words);
+      add_class(gs, P.digests[ci - 1].trace_words, batch);
     }
     // ---- layout ----
     auto up8 = [](uint32_t x) { return (x + 7u) & ~7u; };   // column strides are multiples of 8 cells (256 B)

@@ -25,6 +25,7 @@ struct Config {
   uint32_t record_shape = 1;                      // also build selectors / copy constraints / fixed column
   uint32_t block_parts = 3;                       // engine tuning: jobs per sha256_compression (load balance vs. overhead)
   uint32_t max_fill = 144;                        // engine tuning: distinct values per chunk (size of a warp's scratch table)
+  uint32_t digest_batch = 0;                      // engine tuning: instances per digest job (0 = as many as fit, <= 32)
   uint32_t resident_consts = 16;                  // engine tuning: most-used constants kept permanently in every warp's scratch
 };
 
