@@ -29,7 +29,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape",
-    "h2sha_digest_batch", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
+    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library():
     L.h2sha_get_handles.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.h2sha_get_shape.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
+    L.h2sha_export_instance.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]
     L.h2sha_zero_outputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.h2sha_debug_mont_from_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.h2sha_debug_mont_from_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -307,6 +308,19 @@ class Sha256DynamicConfig:
             raise EngineError(H2SHA_EINVAL, "digest() needs a single-digest configuration; use digest_batch")
         res = self.digest_batch([[input]], [[precomputed_input_len or 0]] if precomputed_input_len is not None else None)
         return self.handles(0), res
+
+    def export_instance(self, res: "BatchResult", instance: int, rows_per_column: int) -> np.ndarray:
+        """Prover hand-off: the advice columns of one instance as a host array [n_columns, rows_per_column, 4] u64
+        (gate columns, lookup column(s), dense_0.., spread_0..), zero-padded like halo2's witness vectors."""
+        import torch
+        lay = self.layout
+        n_cols = lay.n_gate_cols + lay.n_lookup_cols + lay.n_spread_cols
+        out = np.zeros((n_cols, rows_per_column, 4), dtype=np.uint64)
+        ptrs = (C.c_void_p * n_cols)(*[out[c].ctypes.data for c in range(n_cols)])
+        _check(load_library().h2sha_export_instance(self._h, instance, res.gate.data_ptr(), res.lookup.data_ptr(), res.spread.data_ptr(), ptrs,
+                                                    rows_per_column, torch.cuda.current_stream(self.device).cuda_stream))
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
 
     def launches_last_batch(self) -> int:
         return int(load_library().h2sha_last_launch_count(self._h))

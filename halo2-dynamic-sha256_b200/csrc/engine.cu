@@ -890,7 +890,8 @@ ExpandVariant make_variant() { return ExpandVariant{NC, NP, (const void*)k_expan
 const ExpandVariant* expand_variants(int* n) {
   static const ExpandVariant v[] = {make_variant<16, 4>(), make_variant<12, 4>(), make_variant<20, 4>(), make_variant<24, 4>(), make_variant<16, 2>(),
                                     make_variant<20, 2>(), make_variant<24, 6>(), make_variant<8, 2>(), make_variant<8, 4>(), make_variant<18, 6>(),
-                                    make_variant<16, 6>(), make_variant<20, 5>(), make_variant<20, 6>(), make_variant<16, 8>()};
+                                    make_variant<16, 6>(), make_variant<20, 5>(), make_variant<20, 6>(), make_variant<16, 8>(), make_variant<21, 4>(),
+                                    make_variant<22, 4>(), make_variant<18, 4>(), make_variant<22, 3>(), make_variant<21, 3>(), make_variant<16, 3>()};
   *n = (int)(sizeof v / sizeof v[0]);
   return v;
 }
@@ -1299,6 +1300,39 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     CUDA_TRY(cudaEventSynchronize(copied));
     cudaEventDestroy(copied);
   }
+  return H2SHA_OK;
+}
+
+int h2sha_export_instance(h2sha_engine_t* e, uint64_t instance, const void* gate, const void* lookup, const void* spread,
+                          uint64_t* const* host_columns, uint32_t rows_per_column, void* stream) {
+  if (!e || !host_columns) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine");
+  const Plan& P = e->plan;
+  const uint32_t col_rows[3] = {P.gate_col_rows, P.lookup_col_rows, P.spread_rows};
+  const uint32_t n_cols[3] = {P.n_gate_cols, P.n_lookup_cols, 2 * P.cfg.spread_cols};
+  const void* bufs[3] = {gate, lookup, spread};
+  const uint64_t inst_cells[3] = {e->dplan.gate_inst_cells, e->dplan.lookup_inst_cells, e->dplan.spread_inst_cells};
+  for (int b = 0; b < 3; b++)
+    if (col_rows[b] > rows_per_column && bufs[b]) {
+      // only the assigned prefix of a column has to fit: the stride may exceed rows_per_column through alignment padding
+      uint32_t used = (b == 0) ? 0 : (b == 1 ? std::min(P.n_lookup, P.cfg.max_rows) : (P.n_limb + P.cfg.spread_cols - 1) / P.cfg.spread_cols);
+      if (b == 0)
+        for (size_t c = 0; c < P.breaks.size(); c++) used = std::max(used, ((c + 1 < P.breaks.size()) ? P.breaks[c + 1] : P.n_gate) - P.breaks[c]);
+      if (used > rows_per_column) return set_err(H2SHA_EINVAL, "rows_per_column is smaller than the assigned rows of a column");
+    }
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t k = 0;
+  for (int b = 0; b < 3; b++)
+    for (uint32_t c = 0; c < n_cols[b]; c++, k++) {
+      if (!bufs[b]) continue;
+      uint64_t* dst = host_columns[k];
+      if (!dst) return set_err(H2SHA_EINVAL, "null host column");
+      const uint32_t rows = std::min(col_rows[b], rows_per_column);
+      const uint8_t* src = (const uint8_t*)bufs[b] + ((instance * inst_cells[b] + (uint64_t)c * col_rows[b]) * 32);
+      CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)rows * 32, cudaMemcpyDeviceToHost, st));
+      if (rows < rows_per_column) memset(dst + (size_t)rows * 4, 0, (size_t)(rows_per_column - rows) * 32);
+    }
   return H2SHA_OK;
 }
 

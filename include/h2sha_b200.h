@@ -122,6 +122,15 @@ typedef struct {
  * batch->stream; host arrays `offsets/lens/precomputed_lens` are consumed before the call returns. */
 int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* batch);
 
+/* Prover hand-off: copy ONE instance's advice columns from the batch buffers to host memory, one vector per advice
+ * column, `rows_per_column` (normally 2^k) Fr each, zero-padded -- the layout halo2's witness collection / MockProver
+ * hold (`advice[column][row]`).  Column order = allocation order of the reference's configure (lib.rs:409-428,
+ * spread.rs:39-52): gate advice columns, lookup advice column(s), SpreadConfig denses[0..], spreads[0..].
+ * `host_columns` has n_gate_cols + n_lookup_cols + n_spread_cols pointers.  Asynchronous on `stream` when the host
+ * memory is pinned; any of the device buffers may be NULL (its columns are skipped). */
+int h2sha_export_instance(h2sha_engine_t* e, uint64_t instance, const void* gate, const void* lookup, const void* spread,
+                          uint64_t* const* host_columns, uint32_t rows_per_column, void* stream);
+
 /* Zero-fill output buffers (or just the never-assigned ranges when only_unassigned != 0). */
 int h2sha_zero_outputs(h2sha_engine_t* e, uint64_t n_instances, void* gate, void* lookup, void* spread, int only_unassigned, void* stream);
 

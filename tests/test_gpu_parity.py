@@ -319,3 +319,23 @@ def test_no_out_of_bounds_writes_guard_bands(pkg):
         used = int(brk[c + 1]) - int(brk[c])
         assert (g[:, c, used:] == sentinel).all(), "unassigned gate rows were written"
     cfg.close()
+
+
+def test_export_instance_matches_halo2_witness_layout(pkg):
+    """Prover hand-off (h2sha_export_instance): one instance's advice columns as zero-padded 2^k-row vectors in the
+    reference's column order -- compared with the oracle's column-major output."""
+    kw = dict(max_variable_byte_sizes=(128, 128))
+    cfg = _engine(pkg, kw)
+    lay = cfg.layout
+    instances = [[b"abc", b""], [b"\x01" * 56, b"\x00\x00\x00"]]
+    res = cfg.digest_batch(instances)
+    cols = cfg.export_instance(res, 1, 1 << 17)
+    assert cols.shape == (3 + 1 + 4, 1 << 17, 4)
+    olay = O.Layout(lay.n_gate_cols, lay.gate_col_rows, lay.n_lookup_cols, lay.lookup_col_rows, lay.spread_rows)
+    ref = O.batch(_oracle_cfg(kw), olay, instances, None, want_cells=True)
+    assert (cols[0:3, : lay.gate_col_rows] == ref["gate"][1]).all() and not cols[0:3, lay.gate_col_rows:].any()
+    assert (cols[3, : lay.lookup_col_rows] == ref["lookup"][1][0]).all() and not cols[3, lay.lookup_col_rows:].any()
+    assert (cols[4:8, : lay.spread_rows] == ref["spread"][1]).all() and not cols[4:8, lay.spread_rows:].any()
+    with pytest.raises(pkg.EngineError):
+        cfg.export_instance(res, 0, 1024)   # fewer rows than a column has assigned
+    cfg.close()
