@@ -814,7 +814,13 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           loff0 = col0 * (P.lookup_col_rows - P.max_rows);
           loff1 = (col0 + 1) * (P.lookup_col_rows - P.max_rows);
         }
-        for (uint32_t i = lane; i < ch.lk_len; i += 32) {
+        // lanes aligned to the 256-byte groups of the output, like the gate loop (a misaligned warp store costs ~1.7x the
+        // LSU wavefronts: tools/stg_wave_probe.cu)
+        const uint32_t lpos0 = l_lo + ((l_lo >= wrap) ? loff1 : loff0);
+        const int lshift = (int)(lpos0 & 7u);
+        const int ln = (int)ch.lk_len;
+        for (int i = (int)lane - lshift; i < ln; i += 32) {
+          if (i < 0) continue;
           const CellEntry ce = s_cells[ch.lk_off + i];
           const uint32_t src = H2SHA_CE_SRC(ce);
           const uint4 lo = ws.lo[src], hi = ws.hi[src];

@@ -10,6 +10,8 @@
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace h2sha {
 namespace {
@@ -919,6 +921,7 @@ class Builder {
   // cells of a chunk can be grouped into quarter-warps.
   std::map<std::string, std::set<uint32_t>> align_;
   std::set<uint32_t> cur_align_;
+  uint64_t stat_cost_greedy_ = 0, stat_cost_final_ = 0, stat_cost_ideal_ = 0, stat_norm_ = 1;   // shared-memory wavefronts of the unit type being chunked
   void compute_alignments() {
     Plan& P = *P_;
     auto residue = [&](uint32_t gidx) {
@@ -1023,6 +1026,8 @@ class Builder {
       // free slots per residue class: all slots >= n_res
       std::vector<std::vector<uint32_t>> free_slots(8);
       for (uint32_t sl = cfg_.max_fill; sl-- > n_res;) free_slots[sl % 8].push_back(sl);   // back() = smallest free slot
+      uint32_t cap_left[8];
+      for (int r = 0; r < 8; r++) cap_left[r] = (uint32_t)free_slots[r].size();
       uint32_t n_dyn = 0;
       for (uint32_t i2 = 0; i2 < nd; i2++) {
         if (is_resident(order[i2])) { resident[i2] = 1; loc[i2] = resident_slot_.at(table_index(order[i2])); residue[i2] = (int)(loc[i2] % 8); }
@@ -1038,11 +1043,124 @@ class Builder {
         for (auto& kv : adj[vi]) if (residue[kv.first] >= 0) cost[residue[kv.first]] += kv.second;
         int best = -1;
         for (int r = 0; r < 8; r++)
-          if (!free_slots[r].empty() && (best < 0 || cost[r] < cost[best] || (cost[r] == cost[best] && free_slots[r].size() > free_slots[best].size()))) best = r;
+          if (cap_left[r] && (best < 0 || cost[r] < cost[best] || (cost[r] == cost[best] && cap_left[r] > cap_left[best]))) best = r;
         if (best < 0) fail("scratch colouring out of space");
         residue[vi] = best;
-        loc[vi] = free_slots[best].back();
-        free_slots[best].pop_back();
+        cap_left[best]--;
+      }
+      // ---- local search on the exact cost: shared-memory wavefronts of one execution of the chunk ----
+      // A quarter-warp access costs max over the 8 bank groups of the number of DISTINCT slots it touches there
+      // (tools/lsu_probe.cu: conflicts inside a quarter serialise even when the warp as a whole is balanced).  Reads:
+      // every quarter of the three copy loops (per possible alignment of the chunk in its output column).  Writes: the
+      // fill loops store 8 consecutive fill entries per quarter; with the round-robin order emitted below a class of n
+      // values costs max(ceil(n / 8), largest residue class), so the classes are balanced here as well.
+      {
+        struct Quarter { std::vector<uint32_t> vs; uint32_t w; };
+        std::vector<Quarter> quarters;
+        auto add_quarter = [&](std::vector<uint32_t> vs, uint32_t w) {
+          std::sort(vs.begin(), vs.end());
+          vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
+          if (vs.size() > 1) quarters.push_back(Quarter{vs, w});
+        };
+        const uint32_t n_al = (uint32_t)cur_align_.size();
+        for (int kind = 0; kind < 3; kind++) {
+          std::vector<uint32_t> seq;
+          uint32_t first_dst = 0xffffffffu;
+          for (auto& pc : cur) if (pc.kind == kind) { seq.push_back(index.at(sym_key(pc.s))); first_dst = std::min(first_dst, pc.dst); }
+          if (seq.empty()) continue;
+          // every copy loop aligns its lanes to the 256-byte groups of the output at run time: a quarter holds the cells
+          // whose position falls into the same group of 8; enumerate the alignments this chunk can have
+          std::map<uint32_t, uint32_t> shifts;   // shift -> number of alignments that produce it
+          if (kind == EV_GATE) for (uint32_t a : cur_align_) shifts[(a + first_dst) & 7u]++;
+          else if (kind == EV_LK) for (uint32_t sh = 0; sh < 8; sh++) shifts[sh] = n_al;   // lookup stream: any alignment, equally likely
+          else shifts[0] = n_al * 8u;                                                       // limb loop: lanes start at cell 0
+          for (auto& sw : shifts) {
+            std::vector<uint32_t> q;
+            for (size_t i0 = 0; i0 < seq.size(); i0++) {
+              if (i0 && (i0 + sw.first) % 8 == 0) { add_quarter(q, sw.second * (kind == EV_GATE ? 8u : 1u)); q.clear(); }
+              q.push_back(seq[i0]);
+            }
+            add_quarter(q, sw.second * (kind == EV_GATE ? 8u : 1u));
+          }
+        }
+        std::vector<std::vector<uint32_t>> memb(nd);
+        for (uint32_t q = 0; q < quarters.size(); q++) for (uint32_t v : quarters[q].vs) memb[v].push_back(q);
+        auto qcost = [&](const Quarter& q) {
+          uint32_t c8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, m = 0;
+          for (uint32_t v : q.vs) m = std::max(m, ++c8[residue[v]]);
+          return m * q.w;
+        };
+        // fill classes for the write cost: 0 = table copies, 1 = Barrett (32- and 64-bit entries share one loop)
+        auto wclass = [&](uint32_t v) { return fill_class(order[v]) == 0 ? 0 : 1; };
+        uint32_t ccount[2][8] = {{0}}, ctotal[2] = {0, 0};
+        for (uint32_t v = 0; v < nd; v++) if (!resident[v]) { ccount[wclass(v)][residue[v]]++; ctotal[wclass(v)]++; }
+        auto fcost = [&]() {
+          uint32_t t = 0;
+          for (int c = 0; c < 2; c++) {
+            uint32_t m = (ctotal[c] + 7) / 8;
+            for (int r = 0; r < 8; r++) m = std::max(m, ccount[c][r]);
+            t += m;
+          }
+          return t * n_al * 8u;
+        };
+        auto local_cost = [&](uint32_t v, uint32_t u) {   // cost of the quarters touching v (and u, if any), each counted once
+          uint64_t t = fcost();
+          for (uint32_t q : memb[v]) t += qcost(quarters[q]);
+          if (u != ~0u)
+            for (uint32_t q : memb[u]) if (!std::binary_search(quarters[q].vs.begin(), quarters[q].vs.end(), v)) t += qcost(quarters[q]);
+          return t;
+        };
+        uint64_t total0 = fcost();
+        for (auto& q : quarters) total0 += qcost(q);
+        uint64_t total = total0;
+        std::vector<uint32_t> dyn;
+        for (uint32_t v = 0; v < nd; v++) if (!resident[v]) dyn.push_back(v);
+        for (int sweep = 0; sweep < 12; sweep++) {
+          bool improved = false;
+          for (uint32_t v : dyn) {
+            const int r0 = residue[v];
+            const int cv = wclass(v);
+            int64_t best_gain = 0; int best_r = -1; uint32_t best_u = ~0u;
+            for (int r = 0; r < 8; r++) {
+              if (r == r0 || !cap_left[r]) continue;
+              const uint64_t before = local_cost(v, ~0u);
+              residue[v] = r; ccount[cv][r0]--; ccount[cv][r]++;
+              const uint64_t after = local_cost(v, ~0u);
+              residue[v] = r0; ccount[cv][r0]++; ccount[cv][r]--;
+              const int64_t gain = (int64_t)before - (int64_t)after;
+              if (gain > best_gain) { best_gain = gain; best_r = r; best_u = ~0u; }
+            }
+            for (uint32_t u : dyn) {
+              const int r = residue[u];
+              if (r == r0) continue;
+              const int cu = wclass(u);
+              const uint64_t before = local_cost(v, u);
+              residue[v] = r; residue[u] = r0; ccount[cv][r0]--; ccount[cv][r]++; ccount[cu][r]--; ccount[cu][r0]++;
+              const uint64_t after = local_cost(v, u);
+              residue[v] = r0; residue[u] = r; ccount[cv][r0]++; ccount[cv][r]--; ccount[cu][r]++; ccount[cu][r0]--;
+              const int64_t gain = (int64_t)before - (int64_t)after;
+              if (gain > best_gain) { best_gain = gain; best_r = r; best_u = u; }
+            }
+            if (best_r >= 0) {
+              if (best_u == ~0u) { cap_left[r0]++; cap_left[best_r]--; }
+              else { residue[best_u] = r0; const int cu = wclass(best_u); ccount[cu][best_r]--; ccount[cu][r0]++; }
+              residue[v] = best_r; ccount[cv][r0]--; ccount[cv][best_r]++;
+              total -= (uint64_t)best_gain;
+              improved = true;
+            }
+          }
+          if (!improved) break;
+        }
+        uint64_t ideal = 0;
+        for (auto& q : quarters) ideal += q.w;
+        ideal += (uint64_t)n_al * 8u * ((ctotal[0] + 7) / 8 + (ctotal[1] + 7) / 8);
+        stat_cost_greedy_ += total0; stat_cost_final_ += total; stat_cost_ideal_ += ideal; stat_norm_ = n_al * 8u;
+      }
+      for (uint32_t vi = 0; vi < nd; vi++) {
+        if (resident[vi]) continue;
+        if (free_slots[residue[vi]].empty()) fail("scratch colouring out of space");
+        loc[vi] = free_slots[residue[vi]].back();
+        free_slots[residue[vi]].pop_back();
       }
       // gate-checksum weights of every distinct value
       std::vector<uint32_t> cnt(nd, 0), sumdst(nd, 0);
@@ -1263,7 +1381,12 @@ class Builder {
       ut.n_in = (uint32_t)u.in.size(); ut.n_slots = u.n_slots;
       ut.prog_off = (uint32_t)P.prog.size(); ut.prog_len = (uint32_t)u.prog.size();
       P.prog.insert(P.prog.end(), u.prog.begin(), u.prog.end());
+      stat_cost_greedy_ = stat_cost_final_ = stat_cost_ideal_ = 0;
       build_chunks(u, &ut);
+      if (getenv("H2SHA_PLAN_STATS"))   // multi-chunk types run the chunking twice (see build_chunks): their numbers are doubled
+        fprintf(stderr, "[plan] %-8s chunks %2u gate %4u lk %3u limb %3u | quarter-warp scratch accesses per unit: conflict-free %.1f greedy %.1f searched %.1f\n",
+                P.type_names[t].c_str(), ut.n_chunks, ut.gate_len, ut.lk_len, ut.limb_len, (double)stat_cost_ideal_ / stat_norm_,
+                (double)stat_cost_greedy_ / stat_norm_, (double)stat_cost_final_ / stat_norm_);
       P.types.push_back(ut);
     }
     // ---- job classes: the block job is split into `block_parts` parts of roughly equal cell count ----

@@ -11,6 +11,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 pkg = ge.load_package()
+if os.environ.get("TUNE_LIB"):   # A/B runs: time another build of the engine (e.g. tools/ab/libh2sha_base.so) with the same harness
+    pkg.LIB_PATH = os.path.abspath(os.environ["TUNE_LIB"])
 S = ge.load_package_module("synthetic")
 
 
