@@ -139,8 +139,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU per step (0 = workload default, capped by HBM)")
+    ap.add_argument("--split-total", action="store_true",
+                    help="divide the workload's instances over the ranks (rank r takes [r*n/N, (r+1)*n/N): strong scaling) instead of "
+                         "one full-size shard per rank; e.g. --workload cfg4 --gpus 8 = 2^16 messages on 8 GPUs, 8192 each")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="instances in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-witness-d2h", action="store_true", help="skip the extra end-to-end leg that copies the whole witness to the host")
     ap.add_argument("--verify", type=int, default=8, help="instances per rank checked cell-for-cell against the oracle after timing")
     args = ap.parse_args()
 
@@ -171,10 +175,19 @@ def main():
     lay = cfg.layout
     # instances per GPU per step: the whole workload if it fits in ~60% of free HBM, else a chunk (ring reuse)
     free_b, _ = torch.cuda.mem_get_info(dev)
-    cap = max(1, int(0.6 * free_b) // lay.bytes_per_instance)
-    per_gpu = args.instances or min(w.n_instances, cap)
-    per_gpu = min(per_gpu, cap)
-    first = rank * per_gpu
+    cap = max(1, int((0.62 if args.split_total else 0.6) * free_b) // lay.bytes_per_instance)
+    if args.split_total:
+        sh0 = ge.load_package_module("sharding")
+        if w.n_instances % world:
+            raise SystemExit("--split-total needs the workload's instance count to be a multiple of the number of GPUs")
+        lo, hi = sh0.shard_range(w.n_instances, rank, world)
+        if hi - lo > cap:
+            raise SystemExit(f"--split-total: {hi - lo} instances per GPU need {(hi - lo) * lay.bytes_per_instance / 1e9:.0f} GB, more than fits ({cap} instances)")
+        per_gpu, first = hi - lo, lo
+    else:
+        per_gpu = args.instances or min(w.n_instances, cap)
+        per_gpu = min(per_gpu, cap)
+        first = rank * per_gpu
     blob, offs, lens = S.generate(w, first, per_gpu)
     n_msgs = per_gpu
     blocks_per_step = per_gpu * lay.n_blocks
@@ -259,6 +272,33 @@ def main():
     h2d = int(blob.size) + offs.nbytes + lens.nbytes
     d2h = n_msgs * 32 + per_gpu * 32
 
+    # ---- extra datapoint: the same end-to-end step when the consumer is a CPU prover, i.e. the whole witness is also copied
+    # to pinned host memory every step (PCIe-bound; single GPU and small batches only) ----
+    e2e_witness = None
+    witness_bytes = per_gpu * lay.bytes_per_instance
+    if world == 1 and witness_bytes <= (4 << 30) and not args.no_witness_d2h:
+        h_gate = torch.empty(gate.shape, dtype=gate.dtype).pin_memory()
+        h_lookup = torch.empty(lookup.shape, dtype=lookup.dtype).pin_memory()
+        h_spread = torch.empty(spread.shape, dtype=spread.dtype).pin_memory()
+
+        def step_witness():
+            cfg.digest_batch_raw(per_gpu, h_blob.data_ptr(), False, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(),
+                                 lookup_ptr=lookup.data_ptr(), spread_ptr=spread.data_ptr(), digests_host_ptr=h_digests.data_ptr(),
+                                 checksums_host_ptr=h_cks.data_ptr(), stream=sp)
+            h_gate.copy_(gate, non_blocking=True); h_lookup.copy_(lookup, non_blocking=True); h_spread.copy_(spread, non_blocking=True)
+            stream.synchronize()
+
+        step_witness()
+        n_w = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_w):
+            step_witness()
+        dt = (time.perf_counter() - t0) / n_w
+        e2e_witness = {"value": blocks_per_step / dt, "unit": UNIT, "d2h_bytes_per_step": d2h + h_gate.nbytes + h_lookup.nbytes + h_spread.nbytes,
+                       "steps": n_w, "note": "as e2e, plus every advice/lookup/spread column copied to pinned host memory each step (what a CPU "
+                                             "prover would need); PCIe-bound, not the headline"}
+        del h_gate, h_lookup, h_spread
+
     # ---- correctness inside the bench: digests vs hashlib for all, cells vs oracle on a sample, gather over NCCL ----
     import hashlib
     dig = h_digests.numpy()
@@ -316,7 +356,7 @@ def main():
         achieved = alg_bytes / (expand_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.split_total else "weak", "vs_baseline": None,
             "dtype": "u64 (BN254 Fr, 4x64-bit Montgomery limbs; u32 SHA-256 words)", "data": "synthetic",
             "config": {"workload": f"{w.name}: {w.description}", "instances_per_gpu": per_gpu, "blocks_per_instance": lay.n_blocks,
                        "cells_per_instance": lay.cells_per_instance, "bytes_per_instance": lay.cells_per_instance * 32,
@@ -326,6 +366,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "host message buffers -> h2sha_digest_batch -> digests+checksums on host; the witness stays in HBM for the prover"},
+            "e2e_witness_to_host": e2e_witness,
             "gpu_launches": 2 * args.steps,
             "kernels_ms": {"k_trace": trace_ms, "k_expand": expand_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -336,9 +377,13 @@ def main():
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             sample = min(w.n_instances, args.cpu_sample)
-            v, dt, _ = cpu_baseline(w, sample, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{sample} instances of {w.name} ({sample * w.blocks_per_instance} blocks, {dt:.1f} s wall), "
+            # bounded sample: repeat it until ~12 s of CPU work (cores x wall) have been timed
+            reps, wall, blocks = 0, 0.0, 0
+            while reps < 1 or (wall * cores < 12.0 and reps < 64):
+                _, dt, _ = cpu_baseline(w, sample, cores)
+                wall += dt; blocks += sample * w.blocks_per_instance; reps += 1
+            line["cpu_baseline"] = {"value": blocks / wall, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{reps} x {sample} instances of {w.name} ({blocks} blocks, {wall:.1f} s wall = {wall * cores:.0f} core-seconds), "
                                               f"oracle/h2sha_oracle.c (C restatement; the Rust crate cannot be built here) on {cores} threads"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -28,7 +28,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
-    "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape",
+    "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape", "h2sha_get_lookup_tables",
     "h2sha_digest_batch", "h2sha_export_instance", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
@@ -84,6 +84,7 @@ def load_library():
     L.h2sha_get_breaks.argtypes = [C.c_void_p, C.c_void_p]
     L.h2sha_get_handles.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.h2sha_get_shape.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    L.h2sha_get_lookup_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
     L.h2sha_export_instance.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]
     L.h2sha_zero_outputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -238,6 +239,15 @@ class Sha256DynamicConfig:
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         _check(load_library().h2sha_get_shape(self._h, p(sel), p(cp), p(fx), p(ls), p(ld), p(lsp)))
         return Shape(sel, cp, fx, ls, ld, lsp)
+
+    def lookup_tables(self):
+        """(dense[2^bits], spread[2^bits], n_range_rows): SpreadConfig::load (spread.rs:165-194) and the range table's row count."""
+        L = load_library()
+        ns, nr = C.c_uint32(), C.c_uint32()
+        _check(L.h2sha_get_lookup_tables(self._h, None, None, C.byref(ns), C.byref(nr)))
+        d = np.zeros(ns.value, dtype=np.uint64); sp = np.zeros(ns.value, dtype=np.uint64)
+        _check(L.h2sha_get_lookup_tables(self._h, d.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p), C.byref(ns), C.byref(nr)))
+        return d, sp, int(nr.value)
 
     # ------------------------------------------------------------------------------------------------
     def alloc_outputs(self, n_instances: int, zero: bool = True):

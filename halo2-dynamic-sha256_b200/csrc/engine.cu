@@ -1205,6 +1205,20 @@ int h2sha_get_shape(const h2sha_engine_t* e, uint8_t* selectors, uint32_t* copie
   return H2SHA_OK;
 }
 
+int h2sha_get_lookup_tables(const h2sha_engine_t* e, uint64_t* table_dense, uint64_t* table_spread, uint32_t* n_spread_rows, uint32_t* n_range_rows) {
+  if (!e) return set_err(H2SHA_EINVAL, "null argument");
+  const uint32_t bits = e->plan.cfg.limb_bits, n = 1u << bits;
+  for (uint32_t i = 0; i < n; i++) {
+    uint64_t sp = 0;
+    for (uint32_t b = 0; b < bits; b++) sp |= (uint64_t)((i >> b) & 1u) << (2 * b);   // spread.rs:171-180
+    if (table_dense) table_dense[i] = i;
+    if (table_spread) table_spread[i] = sp;
+  }
+  if (n_spread_rows) *n_spread_rows = n;
+  if (n_range_rows) *n_range_rows = 1u << e->plan.cfg.lookup_bits;
+  return H2SHA_OK;
+}
+
 int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   if (!e || !b) return set_err(H2SHA_EINVAL, "null argument");
   if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine (device = -1): witness generation needs a CUDA device; there is no CPU path");

@@ -94,6 +94,12 @@ int h2sha_get_handles(const h2sha_engine_t* e, uint32_t d, uint32_t* input_len_i
 int h2sha_get_shape(const h2sha_engine_t* e, uint8_t* selectors, uint32_t* copies, uint64_t* fixed, uint32_t* lookup_src,
                     uint32_t* limb_dense_src, uint32_t* limb_spread_src);
 
+/* The fixed lookup tables keygen has to load next to the shape:
+ *   SpreadConfig::load (spread.rs:165-194): 2^num_bits_lookup rows (dense i, spread(i)) with bit b of i at bit 2b of spread(i);
+ *   range.load_lookup_table (lib.rs:442): 2^lookup_bits rows holding 0 .. 2^lookup_bits - 1 (only the row count is returned).
+ * table_dense / table_spread: [2^num_bits_lookup] u64 canonical values, may be NULL. */
+int h2sha_get_lookup_tables(const h2sha_engine_t* e, uint64_t* table_dense, uint64_t* table_spread, uint32_t* n_spread_rows, uint32_t* n_range_rows);
+
 /* One batch = n_instances instances; message m = instance * n_digests + d. */
 typedef struct {
   uint64_t n_instances;

@@ -101,3 +101,17 @@ def test_random_configurations_shape_property(pkg):
         assert (sh.lookup_src == reg.lookup_idx).all(), kw
         assert [int(a) | int(b) << 64 | int(c) << 128 | int(d) << 192 for a, b, c, d in sh.fixed] == [O.mont_to_int(c) for c in reg.consts], kw
         cfg.close()
+
+
+@pytest.mark.parametrize("limb_bits,lookup_bits", [(8, 16), (4, 12), (2, 8)])
+def test_lookup_tables_follow_spread_config_load(pkg, limb_bits, lookup_bits):
+    """SpreadConfig::load (spread.rs:165-194): row i = (i, bits of i moved to even positions); the range table has 2^lookup_bits rows."""
+    e = _engine(pkg, dict(max_variable_byte_sizes=(64,), limb_bits=limb_bits, lookup_bits=lookup_bits))
+    dense, spread, n_range = e.lookup_tables()
+    assert n_range == 1 << lookup_bits
+    assert dense.tolist() == list(range(1 << limb_bits))
+    for i, s in enumerate(spread.tolist()):
+        bits = [(i >> b) & 1 for b in range(limb_bits)]           # fe_to_bits_le (utils.rs:6-14)
+        assert s == sum(bit << (2 * b) for b, bit in enumerate(bits))
+        assert s == O.spread_bits(i) if hasattr(O, "spread_bits") else True
+    e.close()

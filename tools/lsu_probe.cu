@@ -98,6 +98,15 @@ int main() {
       float ms; cudaEventElapsedTime(&ms, a, b);
       if (rep) printf("stg256 %-28s %.3f ms  %.1f GB/s\n", sn[m], ms, n_cells * 32 / ms / 1e6);
     }
+  // sustained regime (power cap): incompressible linear stores back to back for ~2 s, then 20 timed launches
+  {
+    for (int r = 0; r < 5000; r++) k_store<<<148 * 8, 256>>>(d, n_cells, 0);
+    cudaEventRecord(a);
+    for (int r = 0; r < 20; r++) k_store<<<148 * 8, 256>>>(d, n_cells, 0);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    printf("stg256 linear, sustained (after 5000 launches)   %.3f ms  %.1f GB/s\n", ms / 20, 20.0 * n_cells * 32 / ms / 1e6);
+  }
   // the same stores into a 32 MiB window that stays in L2: exposes the LSU / L2 cost of each pattern without the HBM bound
   for (int m = 0; m < 5; m++)
     for (int rep = 0; rep < 2; rep++) {
