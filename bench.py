@@ -175,7 +175,7 @@ def main():
     lay = cfg.layout
     # instances per GPU per step: the whole workload if it fits in ~60% of free HBM, else a chunk (ring reuse)
     free_b, _ = torch.cuda.mem_get_info(dev)
-    cap = max(1, int((0.62 if args.split_total else 0.6) * free_b) // lay.bytes_per_instance)
+    cap = max(1, int((0.75 if args.split_total else 0.6) * free_b) // lay.bytes_per_instance)
     if args.split_total:
         sh0 = ge.load_package_module("sharding")
         if w.n_instances % world:
