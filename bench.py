@@ -325,15 +325,15 @@ def main():
         shp_cfg = pkg.Sha256DynamicConfig.configure(list(w.max_variable_byte_sizes), device=-1, build_shape=True)
         sh, brk = shp_cfg.shape(), shp_cfg.breaks()
         i0 = nv - 1
-        g = gate[i0].cpu().numpy().view(np.uint64); lk = lookup[i0].cpu().numpy().view(np.uint64); sp = spread[i0].cpu().numpy().view(np.uint64)
+        g = gate[i0].cpu().numpy().view(np.uint64); lk = lookup[i0].cpu().numpy().view(np.uint64); spc = spread[i0].cpu().numpy().view(np.uint64)
         ends = list(brk[1:]) + [lay.n_gate_cells]
         stream_cells = np.concatenate([g[c, : int(e_) - int(s_)] for c, (s_, e_) in enumerate(zip(brk, ends))])
         nc = lay.n_spread_cols // 2
         nl = np.arange(lay.n_spread_limbs)
         consts_mont = np.array([O.int_to_mont(int(a) | int(b_) << 64 | int(c) << 128 | int(d_) << 192) for a, b_, c, d_ in sh.fixed], dtype=np.uint64)
         msg0 = bytes(blob[int(offs[i0]):int(offs[i0]) + int(lens[i0])])
-        MP.verify(gate=stream_cells, selectors=sh.selectors, breaks=brk, lookup_idx=sh.lookup_src, dense=sp[nl % nc, nl // nc],
-                  spread=sp[nc + nl % nc, nl // nc], limb_gate_dense=sh.limb_dense_src, limb_gate_spread=sh.limb_spread_src, copies=sh.copies,
+        MP.verify(gate=stream_cells, selectors=sh.selectors, breaks=brk, lookup_idx=sh.lookup_src, dense=spc[nl % nc, nl // nc],
+                  spread=spc[nc + nl % nc, nl // nc], limb_gate_dense=sh.limb_dense_src, limb_gate_spread=sh.limb_spread_src, copies=sh.copies,
                   consts=consts_mont, lookup_bits=16, limb_bits=8, max_rows=(1 << 17) - 9, output_bytes_idx=[shp_cfg.handles(0).output_bytes],
                   expected_digests=[hashlib.sha256(msg0).digest()])
         assert (np.concatenate([lk[c] for c in range(lay.n_lookup_cols)])[: lay.n_lookup_cells] == stream_cells[sh.lookup_src]).all()
@@ -341,6 +341,34 @@ def main():
     # the only collective: gather digests + checksums (64 B / instance) after the hot path
     sh = ge.load_package_module("sharding")
     _, _, job_ck = sh.gather_results(d_digests, d_cks, world)
+
+    # ---- reference points for the roofline, measured live on this GPU (rank 0): (a) the plainest writer of incompressible
+    # cells (coalesced 256-bit stores, nothing else) over a buffer larger than L2, (b) k_expand timed alone after an idle
+    # gap (burst clocks; the figures above are from back-to-back launches under the power cap) ----
+    store_ceiling = None
+    burst_ms = None
+    if rank == 0:
+        try:
+            free_now, _ = torch.cuda.mem_get_info(dev)
+            pb = int(min(4 << 30, free_now // 2)) // 4096 * 4096
+            probe = torch.empty(pb, dtype=torch.uint8, device=dev)
+            ts = []
+            for _ in range(6):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(stream); cfg.store_probe(probe.data_ptr(), pb, sp); b_.record(stream); b_.synchronize()
+                ts.append(a_.elapsed_time(b_))
+            store_ceiling = {"gbs": pb / (min(ts[1:]) * 1e-3) / 1e9, "bytes": pb,
+                             "how": "k_store_probe: coalesced st.global.v8.b32 of incompressible 32-byte cells, best of 5"}
+            del probe
+            time.sleep(0.5)
+            bm = []
+            for _ in range(3):
+                step_resident(timed=True)
+                bm.append(cfg.last_kernel_ms()[1])
+                time.sleep(0.2)
+            burst_ms = min(bm)
+        except Exception as ex:   # measurement extras must not take the bench line down
+            store_ceiling = {"error": str(ex)}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -371,7 +399,11 @@ def main():
             "kernels_ms": {"k_trace": trace_ms, "k_expand": expand_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_expand", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "store_ceiling": store_ceiling,
+                         "frac_of_store_ceiling": (achieved / store_ceiling["gbs"]) if store_ceiling and "gbs" in store_ceiling else None,
+                         "k_expand_burst_ms": burst_ms,
+                         "achieved_burst": (alg_bytes / (burst_ms * 1e-3) / 1e9) if burst_ms else None},
             "verified_instances_vs_oracle": verified, "mock_prover_instances": mock_prover_instances, "job_checksum": job_ck,
         }
         if not args.no_cpu:

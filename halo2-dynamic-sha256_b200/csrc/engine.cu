@@ -875,6 +875,18 @@ __global__ void k_mont_debug32(const uint64_t* vals, uint64_t* out, uint64_t n) 
   for (int k = 0; k < 4; k++) out[4 * i + k] = (uint64_t)x[2 * k] | ((uint64_t)x[2 * k + 1] << 32);
 }
 
+// reference point for the roofline: the plainest possible writer of incompressible 32-byte cells (one 256-bit store per lane,
+// consecutive lanes -> consecutive cells), no shared memory, no arithmetic
+__global__ void k_store_probe(uint32_t* out, uint64_t n_cells, uint32_t salt) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += stride) {
+    const uint32_t v = (uint32_t)i * 2654435761u + salt;
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + i * 8), "r"(v), "r"(v ^ 0x9E3779B1u), "r"(v + 0x85EBCA77u),
+                 "r"(v ^ 0xC2B2AE3Du), "r"(v + 0x27D4EB2Fu), "r"(v ^ 0x165667B1u), "r"(v + 0xD3A2646Du), "r"(v ^ 0xFD7046C5u)
+                 : "memory");
+  }
+}
+
 __global__ void k_zero_ranges(uint4* buf, uint64_t inst_cells, uint64_t n_inst, const uint32_t* ranges /*pos,count pairs*/, uint32_t n_ranges) {
   // grid.y = instance, grid.x strides over the cells of all ranges
   uint64_t inst = blockIdx.y;
@@ -1390,6 +1402,16 @@ int h2sha_debug_mont_from_u32(h2sha_engine_t* e, const uint64_t* vals_dev, uint6
   CUDA_TRY(cudaSetDevice(e->device));
   if (n == 0) return H2SHA_OK;
   k_mont_debug32<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals_dev, out_dev, n);
+  CUDA_TRY(cudaGetLastError());
+  return H2SHA_OK;
+}
+
+int h2sha_debug_store_probe(h2sha_engine_t* e, void* buf_dev, uint64_t bytes, void* stream) {
+  if (!e || !buf_dev) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (bytes < 32) return H2SHA_OK;
+  k_store_probe<<<(unsigned)(e->n_sms * 8), 256, 0, (cudaStream_t)stream>>>((uint32_t*)buf_dev, bytes / 32, (uint32_t)bytes);
   CUDA_TRY(cudaGetLastError());
   return H2SHA_OK;
 }

@@ -151,6 +151,10 @@ int h2sha_debug_mont_from_u64(h2sha_engine_t* e, const uint64_t* vals_dev, uint6
 /* Same for the 32-bit fast path (the low 32 bits of each value are converted). */
 int h2sha_debug_mont_from_u32(h2sha_engine_t* e, const uint64_t* vals_dev, uint64_t* out_dev, uint64_t n, void* stream);
 
+/* Measurement hook: overwrite `bytes` of device memory with incompressible 32-byte cells by plain coalesced 256-bit stores
+ * (no shared memory, no arithmetic) -- the write-bandwidth ceiling bench.py reports next to the expansion kernel. */
+int h2sha_debug_store_probe(h2sha_engine_t* e, void* buf_dev, uint64_t bytes, void* stream);
+
 /* Kernel launch statistics of the last h2sha_digest_batch (for bench.py's gpu_launches). */
 int h2sha_last_launch_count(const h2sha_engine_t* e);
 /* Device time of the two kernels of the last batch run with time_kernels = 1; synchronises on the recorded events. */
