@@ -29,7 +29,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape", "h2sha_get_lookup_tables",
-    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
+    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
 
@@ -65,6 +65,11 @@ class _Batch(C.Structure):
                 ("checksums_host", C.c_void_p), ("stream", C.c_void_p), ("reuse_inputs", C.c_int32), ("time_kernels", C.c_int32)]
 
 
+class _LookupInfo(C.Structure):
+    _fields_ = [("n_range_lookups", C.c_uint32), ("n_spread_lookups", C.c_uint32), ("range_table_rows", C.c_uint32),
+                ("spread_table_rows", C.c_uint32), ("min_usable_rows", C.c_uint32), ("mult_words_per_instance", C.c_uint64)]
+
+
 _lib = None
 
 
@@ -87,6 +92,9 @@ def load_library():
     L.h2sha_get_lookup_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
     L.h2sha_export_instance.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]
+    L.h2sha_get_lookup_info.argtypes = [C.c_void_p, C.POINTER(_LookupInfo)]
+    L.h2sha_lookup_multiplicities.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.h2sha_permute_lookup.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.h2sha_zero_outputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.h2sha_debug_mont_from_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.h2sha_debug_mont_from_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -336,6 +344,42 @@ class Sha256DynamicConfig:
                                                     rows_per_column, torch.cuda.current_stream(self.device).cuda_stream))
         torch.cuda.current_stream(self.device).synchronize()
         return out
+
+    # ---- lookup-argument pre-work (halo2 lookup prover `permute_expression_pair`; spread.rs:53-62, lib.rs:409-418,469) ----
+    def lookup_info(self) -> dict:
+        li = _LookupInfo()
+        _check(load_library().h2sha_get_lookup_info(self._h, C.byref(li)))
+        return {f[0]: int(getattr(li, f[0])) for f in _LookupInfo._fields_}
+
+    def lookup_multiplicities(self, res: "BatchResult", usable_rows: int):
+        """(mult [n_inst, mult_words_per_instance] int32 device tensor, cells that are no table row) of a batch's witness."""
+        import torch
+        n = res.lookup.shape[0]
+        info = self.lookup_info()
+        dev = torch.device("cuda", self.device)
+        mult = torch.empty((n, info["mult_words_per_instance"]), dtype=torch.int32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        _check(load_library().h2sha_lookup_multiplicities(self._h, n, res.lookup.data_ptr(), res.spread.data_ptr(), usable_rows, mult.data_ptr(),
+                                                          bad.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        return mult, int(bad.item())
+
+    def permute_lookup(self, mult, lookup_idx: int, usable_rows: int, theta_mont: Optional[np.ndarray] = None):
+        """(A', S') of lookup `lookup_idx` for every instance: device tensors [n_inst, usable_rows, 4] int64 (Montgomery Fr)."""
+        import torch
+        n = mult.shape[0]
+        dev = torch.device("cuda", self.device)
+        a = torch.empty((n, usable_rows, 4), dtype=torch.int64, device=dev)
+        s = torch.empty((n, usable_rows, 4), dtype=torch.int64, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        th = None
+        if theta_mont is not None:
+            th = np.ascontiguousarray(theta_mont, dtype=np.uint64)
+            assert th.shape == (4,)
+        _check(load_library().h2sha_permute_lookup(self._h, n, lookup_idx, mult.data_ptr(), usable_rows, th.ctypes.data if th is not None else None,
+                                                   a.data_ptr(), s.data_ptr(), err.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        if int(err.item()):
+            raise EngineError(H2SHA_EINVAL, f"{int(err.item())} instance(s) whose multiplicities do not cover usable_rows")
+        return a, s
 
     def launches_last_batch(self) -> int:
         return int(load_library().h2sha_last_launch_count(self._h))

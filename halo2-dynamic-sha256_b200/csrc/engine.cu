@@ -957,6 +957,11 @@ struct h2sha_engine {
   const uint8_t* resident_msgs = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // trace start/stop, expand start/stop
   bool timed = false;
+  // lookup-argument pre-work (lookup_prework.cuh)
+  bool lookup_consts_ready = false;
+  uint32_t* d_lk_ws = nullptr;    // scans of the permutation kernels
+  uint64_t lk_ws_bytes = 0;
+  uint32_t* d_lk_tab = nullptr;   // compressed spread table in sorted order
 };
 
 namespace {
@@ -1165,6 +1170,7 @@ void h2sha_destroy(h2sha_engine_t* e) {
   for (int b = 0; b < 3; b++) cudaFree(e->d_zero_ranges[b]);
   cudaFree(e->d_msgs); cudaFree(e->d_offsets); cudaFree(e->d_lens); cudaFree(e->d_pre); cudaFree(e->d_btrace); cudaFree(e->d_dtrace);
   cudaFree(e->d_digests_out); cudaFree(e->d_cks);
+  cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab);
   delete e;
 }
 
@@ -1427,3 +1433,5 @@ int h2sha_last_kernel_ms(h2sha_engine_t* e, float* trace_ms, float* expand_ms) {
 }
 
 }  // extern "C"
+
+#include "lookup_prework.cuh"

@@ -1,0 +1,396 @@
+// lookup_prework.cuh -- lookup-argument pre-work on the witness that is already in HBM.
+// Included at the end of engine.cu (one translation unit: it uses the engine struct, c_fr and mont_from_u32).
+//
+// What it replaces: the first step of halo2's lookup prover for the chip's two lookups --
+//   * "spread lookup" per column pair (reference src/spread.rs:53-62, table src/spread.rs:165-194),
+//   * the range lookup on the lookup advice column(s) filled by range.finalize (reference src/lib.rs:409-418, 469;
+//     halo2-base RangeConfig, dependency not vendored),
+// i.e. PSE halo2_proofs plonk/lookup/prover.rs `permute_expression_pair`: A' = the input column sorted, S' = the table
+// column permuted so that A'[i] == S'[i] or A'[i] == A'[i-1].  Both are functions of the table-row *multiplicities*
+// of the input, so the work is split into
+//   k_range_mult / k_spread_mult   cells (Montgomery Fr) -> canonical value (REDC) -> histogram over the table rows,
+//   k_permute_scan                 per (instance, lookup): exclusive scans over the table rows in sorted order,
+//   k_permute_fill                 one thread per row: binary search in the scans, 2 x 256-bit stores.
+// HBM-bound like the rest of the path: the fill writes 64 B per usable row and reads only the (L2-resident) scans.
+// oracle/lookup_prework.py is the CPU restatement the tests compare against.
+#pragma once
+
+namespace {
+
+__constant__ uint64_t c_fr_ninv;   // -p^-1 mod 2^64 (derived from p at first use)
+
+// Montgomery reduction: x * 2^-256 mod p, canonical (Montgomery form -> the integer the cell stands for)
+__device__ __forceinline__ void mont_reduce(const uint64_t x[4], uint64_t r[4]) {
+  typedef unsigned __int128 u128;
+  uint64_t t0 = x[0], t1 = x[1], t2 = x[2], t3 = x[3];
+  const uint64_t P0 = c_fr.p[0], P1 = c_fr.p[1], P2 = c_fr.p[2], P3 = c_fr.p[3];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint64_t m = t0 * c_fr_ninv;
+    u128 c = (u128)m * P0 + t0;            // low limb becomes 0
+    c = (u128)m * P1 + t1 + (uint64_t)(c >> 64); t0 = (uint64_t)c;
+    c = (u128)m * P2 + t2 + (uint64_t)(c >> 64); t1 = (uint64_t)c;
+    c = (u128)m * P3 + t3 + (uint64_t)(c >> 64); t2 = (uint64_t)c;
+    t3 = (uint64_t)(c >> 64);
+  }
+  // t < 2p: one conditional subtraction
+  uint64_t s0, s1, s2, s3, borrow;
+  asm("sub.cc.u64 %0, %5, %9;\n\t"
+      "subc.cc.u64 %1, %6, %10;\n\t"
+      "subc.cc.u64 %2, %7, %11;\n\t"
+      "subc.cc.u64 %3, %8, %12;\n\t"
+      "subc.u64 %4, 0, 0;"
+      : "=l"(s0), "=l"(s1), "=l"(s2), "=l"(s3), "=l"(borrow)
+      : "l"(t0), "l"(t1), "l"(t2), "l"(t3), "l"(P0), "l"(P1), "l"(P2), "l"(P3));
+  if (borrow == 0) { t0 = s0; t1 = s1; t2 = s2; t3 = s3; }
+  r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+
+__device__ __forceinline__ void load_cell(const uint64_t* p, uint64_t x[4]) {
+  const ulonglong2 a = reinterpret_cast<const ulonglong2*>(p)[0], b = reinterpret_cast<const ulonglong2*>(p)[1];
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+}
+
+struct LookupGeom {
+  uint64_t n_inst;
+  uint64_t lookup_inst_cells, spread_inst_cells;   // Fr per instance in the lookup / spread buffers
+  uint32_t n_lookup, max_rows, n_lookup_cols, lookup_col_rows, lookup_bits;
+  uint32_t n_limb, spread_cols, spread_rows, limb_bits;
+  uint32_t usable_rows;
+  uint64_t mult_words;   // u32 words per instance in the multiplicity buffer
+};
+
+// range lookup: one thread per assigned cell of the lookup advice column(s).  grid = (tiles, instances).
+__global__ void __launch_bounds__(256) k_range_mult(const LookupGeom G, const uint64_t* __restrict__ lookup, uint32_t* __restrict__ mult,
+                                                   uint32_t* __restrict__ bad) {
+  const uint64_t inst = blockIdx.y;
+  const uint64_t* base = lookup + inst * G.lookup_inst_cells * 4;
+  uint32_t* m_inst = mult + inst * G.mult_words;
+  const uint32_t n_vals = 1u << G.lookup_bits;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < G.n_lookup; i += gridDim.x * blockDim.x) {
+    const uint32_t col = i / G.max_rows, row = i - col * G.max_rows;   // range.finalize wraps at max_rows
+    uint64_t x[4], v[4];
+    load_cell(base + ((uint64_t)col * G.lookup_col_rows + row) * 4, x);
+    mont_reduce(x, v);
+    if ((v[1] | v[2] | v[3]) == 0 && v[0] < n_vals) atomicAdd(&m_inst[(uint64_t)col * n_vals + (uint32_t)v[0]], 1u);
+    else if (bad) atomicAdd(bad, 1u);
+  }
+  // never-assigned rows of a column hold 0
+  if (blockIdx.x == 0 && threadIdx.x < G.n_lookup_cols) {
+    const uint32_t col = threadIdx.x;
+    const uint32_t first = col * G.max_rows;
+    const uint32_t used = (G.n_lookup > first) ? min(G.max_rows, G.n_lookup - first) : 0u;
+    if (G.usable_rows > used) atomicAdd(&m_inst[(uint64_t)col * n_vals], G.usable_rows - used);
+  }
+}
+
+// spread lookups: limb n sits in column pair n % cols, row n / cols (spread.rs:202,228-231).  Block-local histograms in
+// shared memory, flushed with one global atomic per non-empty bin.  grid = (tiles, instances); dynamic smem = cols * 2^bits * 4.
+__global__ void __launch_bounds__(256) k_spread_mult(const LookupGeom G, const uint64_t* __restrict__ spread, uint32_t* __restrict__ mult,
+                                                    uint32_t* __restrict__ bad) {
+  extern __shared__ uint32_t s_hist[];
+  const uint32_t n_vals = 1u << G.limb_bits, n_bins = G.spread_cols * n_vals;
+  for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const uint64_t inst = blockIdx.y;
+  const uint64_t* base = spread + inst * G.spread_inst_cells * 4;
+  uint32_t* m_inst = mult + inst * G.mult_words + (uint64_t)G.n_lookup_cols * (1u << G.lookup_bits);
+  uint32_t n_bad = 0;
+  for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < G.n_limb; n += gridDim.x * blockDim.x) {
+    const uint32_t row = n / G.spread_cols, col = n - row * G.spread_cols;
+    uint64_t x[4], d[4], s[4];
+    load_cell(base + ((uint64_t)col * G.spread_rows + row) * 4, x);
+    mont_reduce(x, d);
+    load_cell(base + ((uint64_t)(G.spread_cols + col) * G.spread_rows + row) * 4, x);
+    mont_reduce(x, s);
+    bool ok = (d[1] | d[2] | d[3]) == 0 && d[0] < n_vals && (s[1] | s[2] | s[3]) == 0;
+    if (ok) ok = spread32(d[0]) == s[0];   // the pair has to be a table row, not just the dense half
+    if (ok) atomicAdd(&s_hist[col * n_vals + (uint32_t)d[0]], 1u); else n_bad++;
+  }
+  if (n_bad && bad) atomicAdd(bad, n_bad);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&m_inst[i], s_hist[i]);
+  if (blockIdx.x == 0 && threadIdx.x < G.spread_cols) {
+    const uint32_t col = threadIdx.x;
+    const uint32_t used = (G.n_limb > col) ? (G.n_limb - col + G.spread_cols - 1) / G.spread_cols : 0u;
+    if (G.usable_rows > used) atomicAdd(&m_inst[col * n_vals], G.usable_rows - used);
+  }
+}
+
+struct PermuteArgs {
+  const uint32_t* mult;        // this lookup's multiplicities of instance 0; instance i at + i * mult_stride
+  uint64_t mult_stride;
+  const uint32_t* order;       // sorted position -> table row, or null (identity: the range table is already sorted)
+  const uint32_t* vals;        // [n_vals][8]: Montgomery value at each sorted position, or null (value = position, range table)
+  uint32_t n_vals, usable_rows;
+  uint32_t* scan;              // workspace [n_inst][3][n_vals]: start | distinct-before | leftover-before   (+ [n_inst] totals after)
+  uint32_t* totals;            // [n_inst][2]: distinct inputs, sum of multiplicities
+  uint32_t* errors;            // may be null
+  uint64_t* out_input;         // [n_inst][usable_rows] Fr
+  uint64_t* out_table;
+};
+
+// one CTA per instance: exclusive scans, in sorted order, of m (-> first row of each value's run in A'), of [m > 0]
+// (-> how many runs start before it) and of the leftover table multiplicity t - [m > 0]
+// (t = 1 per table row; the row holding the padding value -- table row 0 -- also takes the usable_rows - n_vals padded rows)
+__global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
+  __shared__ uint32_t s_part[3][32];
+  __shared__ uint32_t s_base[3];
+  const uint32_t inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t* m = A.mult + (uint64_t)inst * A.mult_stride;
+  uint32_t* start = A.scan + (uint64_t)inst * 3 * A.n_vals;
+  uint32_t* dpre = start + A.n_vals;
+  uint32_t* lpre = dpre + A.n_vals;
+  if (tid < 3) s_base[tid] = 0;
+  __syncthreads();
+  const uint32_t pad = A.usable_rows - A.n_vals;
+  for (uint32_t k0 = 0; k0 < A.n_vals; k0 += 1024) {
+    const uint32_t k = k0 + tid;
+    uint32_t v[3] = {0, 0, 0};
+    if (k < A.n_vals) {
+      const uint32_t row = A.order ? A.order[k] : k;
+      const uint32_t mk = m[row];
+      v[0] = mk; v[1] = mk ? 1u : 0u;
+      v[2] = 1u + (row == 0 ? pad : 0u) - v[1];
+    }
+    uint32_t incl[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      uint32_t x = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
+      }
+      incl[q] = x;
+      if (lane == 31) s_part[q][warp] = x;
+    }
+    __syncthreads();
+    if (warp < 3) {
+      uint32_t x = s_part[warp][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
+      }
+      s_part[warp][lane] = x;   // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t ex[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) ex[q] = s_base[q] + (warp ? s_part[q][warp - 1] : 0u) + incl[q] - v[q];
+    if (k < A.n_vals) { start[k] = ex[0]; dpre[k] = ex[1]; lpre[k] = ex[2]; }
+    __syncthreads();
+    if (tid < 3) s_base[tid] += s_part[tid][31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    A.totals[2 * inst] = s_base[1];
+    A.totals[2 * inst + 1] = s_base[0];
+    if (s_base[0] != A.usable_rows && A.errors) atomicAdd(A.errors, 1u);   // multiplicities do not cover the usable rows
+  }
+}
+
+// last index k in [0, n) with a[k] <= x (a non-decreasing, a[0] = 0 <= x)
+__device__ __forceinline__ uint32_t last_leq(const uint32_t* __restrict__ a, uint32_t n, uint32_t x) {
+  uint32_t lo = 0, hi = n;   // invariant: a[lo] <= x, (hi == n or a[hi] > x)
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void permuted_value(const PermuteArgs& A, uint32_t k, uint32_t x[8]) {
+  if (A.vals) {
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(A.vals + (uint64_t)k * 8)), hi = __ldg(reinterpret_cast<const uint4*>(A.vals + (uint64_t)k * 8) + 1);
+    x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+  } else {
+    mont_from_u32(k, x);
+  }
+}
+
+// grid = (tiles, instances): thread per row of the permuted pair
+__global__ void __launch_bounds__(256) k_permute_fill(const PermuteArgs A) {
+  const uint32_t inst = blockIdx.y;
+  const uint32_t* start = A.scan + (uint64_t)inst * 3 * A.n_vals;
+  const uint32_t* dpre = start + A.n_vals;
+  const uint32_t* lpre = dpre + A.n_vals;
+  const uint32_t n_distinct = A.totals[2 * inst];
+  if (A.totals[2 * inst + 1] != A.usable_rows) return;   // inconsistent multiplicities: reported by the scan kernel
+  const uint32_t n_rep = A.usable_rows - n_distinct;
+  uint32_t* out_a = reinterpret_cast<uint32_t*>(A.out_input) + (uint64_t)inst * A.usable_rows * 8;
+  uint32_t* out_s = reinterpret_cast<uint32_t*>(A.out_table) + (uint64_t)inst * A.usable_rows * 8;
+  for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < A.usable_rows; row += gridDim.x * blockDim.x) {
+    const uint32_t k = last_leq(start, A.n_vals, row);
+    uint32_t x[8];
+    permuted_value(A, k, x);
+    store_cell2(out_a + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
+    if (row != __ldg(start + k)) {
+      // a repeated row: halo2 pops the repeated rows from the back while walking the leftover table elements upwards
+      const uint32_t rank = row - __ldg(dpre + k) - 1u;
+      const uint32_t j = n_rep - 1u - rank;
+      const uint32_t w = last_leq(lpre, A.n_vals, j);
+      permuted_value(A, w, x);
+    }
+    store_cell2(out_s + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
+  }
+}
+
+int ensure_lookup_consts(h2sha_engine* e) {
+  if (e->lookup_consts_ready) return H2SHA_OK;
+  uint64_t inv = 1;   // Newton: inv = p^-1 mod 2^64
+  for (int i = 0; i < 6; i++) inv *= 2 - fr::P[0] * inv;
+  const uint64_t ninv = 0 - inv;
+  CUDA_TRY(cudaMemcpyToSymbol(c_fr_ninv, &ninv, 8));
+  e->lookup_consts_ready = true;
+  return H2SHA_OK;
+}
+
+LookupGeom lookup_geom(const h2sha_engine* e, uint64_t n_inst, uint32_t usable_rows) {
+  const Plan& P = e->plan;
+  LookupGeom G{};
+  G.n_inst = n_inst;
+  G.lookup_inst_cells = e->dplan.lookup_inst_cells; G.spread_inst_cells = e->dplan.spread_inst_cells;
+  G.n_lookup = P.n_lookup; G.max_rows = P.cfg.max_rows; G.n_lookup_cols = P.n_lookup_cols; G.lookup_col_rows = P.lookup_col_rows;
+  G.lookup_bits = P.cfg.lookup_bits;
+  G.n_limb = P.n_limb; G.spread_cols = P.cfg.spread_cols; G.spread_rows = P.spread_rows; G.limb_bits = P.cfg.limb_bits;
+  G.usable_rows = usable_rows;
+  G.mult_words = (uint64_t)P.n_lookup_cols * (1u << P.cfg.lookup_bits) + (uint64_t)P.cfg.spread_cols * (1u << P.cfg.limb_bits);
+  return G;
+}
+
+// rows of the largest advice column the two lookups read
+uint32_t lookup_rows_needed(const Plan& P) {
+  const uint32_t lk = std::min(P.n_lookup, P.cfg.max_rows);
+  const uint32_t sp = (P.n_limb + P.cfg.spread_cols - 1) / P.cfg.spread_cols;
+  return std::max(std::max(lk, sp), std::max(1u << P.cfg.lookup_bits, 1u << P.cfg.limb_bits));
+}
+
+bool u256_less(const U256& a, const U256& b) {
+  for (int i = 3; i >= 0; i--)
+    if (a.l[i] != b.l[i]) return a.l[i] < b.l[i];
+  return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int h2sha_get_lookup_info(const h2sha_engine_t* e, h2sha_lookup_info_t* out) {
+  if (!e || !out) return set_err(H2SHA_EINVAL, "null argument");
+  const Plan& P = e->plan;
+  out->n_range_lookups = P.n_lookup_cols;
+  out->n_spread_lookups = P.cfg.spread_cols;
+  out->range_table_rows = 1u << P.cfg.lookup_bits;
+  out->spread_table_rows = 1u << P.cfg.limb_bits;
+  out->min_usable_rows = lookup_rows_needed(P);
+  out->mult_words_per_instance = (uint64_t)P.n_lookup_cols * (1u << P.cfg.lookup_bits) + (uint64_t)P.cfg.spread_cols * (1u << P.cfg.limb_bits);
+  return H2SHA_OK;
+}
+
+int h2sha_lookup_multiplicities(h2sha_engine_t* e, uint64_t n_instances, const void* lookup, const void* spread, uint32_t usable_rows,
+                                uint32_t* mult_dev, uint32_t* not_in_table_dev, void* stream) {
+  if (!e || !mult_dev) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine (device = -1): there is no CPU path");
+  if (!lookup && !spread) return set_err(H2SHA_EINVAL, "neither the lookup nor the spread buffer was given");
+  if (usable_rows < lookup_rows_needed(e->plan)) return set_err(H2SHA_EINVAL, "usable_rows is smaller than an assigned column or a lookup table");
+  if (n_instances == 0) return H2SHA_OK;
+  if (n_instances > 65535) return set_err(H2SHA_EINVAL, "at most 65535 instances per call");
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = ensure_lookup_consts(e);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const LookupGeom G = lookup_geom(e, n_instances, usable_rows);
+  const uint64_t range_words = (uint64_t)G.n_lookup_cols << G.lookup_bits;
+  // only the halves whose buffer was given are (re)computed
+  if (lookup && spread) {
+    CUDA_TRY(cudaMemsetAsync(mult_dev, 0, n_instances * G.mult_words * 4, st));
+  } else {
+    const uint64_t off = lookup ? 0 : range_words, cnt = lookup ? range_words : G.mult_words - range_words;
+    CUDA_TRY(cudaMemset2DAsync(mult_dev + off, G.mult_words * 4, 0, cnt * 4, n_instances, st));
+  }
+  if (not_in_table_dev) CUDA_TRY(cudaMemsetAsync(not_in_table_dev, 0, 4, st));
+  if (lookup) {
+    const unsigned tiles = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((G.n_lookup + 255) / 256, 64));
+    k_range_mult<<<dim3(tiles, (unsigned)n_instances), 256, 0, st>>>(G, (const uint64_t*)lookup, mult_dev, not_in_table_dev);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (spread) {
+    const unsigned tiles = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((G.n_limb + 1023) / 1024, 32));
+    const size_t smem = (size_t)G.spread_cols * (1u << G.limb_bits) * 4;
+    if (smem > 48 * 1024) return set_err(H2SHA_EINVAL, "spread histogram does not fit in shared memory");
+    k_spread_mult<<<dim3(tiles, (unsigned)n_instances), 256, smem, st>>>(G, (const uint64_t*)spread, mult_dev, not_in_table_dev);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return H2SHA_OK;
+}
+
+int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint32_t usable_rows,
+                         const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream) {
+  if (!e || !mult_dev || !permuted_input_dev || !permuted_table_dev) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine (device = -1): there is no CPU path");
+  const Plan& P = e->plan;
+  const uint32_t n_range = P.n_lookup_cols, n_spread = P.cfg.spread_cols;
+  if (lookup_idx >= n_range + n_spread) return set_err(H2SHA_EINVAL, "bad lookup index");
+  const bool is_range = lookup_idx < n_range;
+  if (!is_range && !theta_mont) return set_err(H2SHA_EINVAL, "a spread lookup has two expressions: theta is needed to compress them");
+  if (usable_rows < lookup_rows_needed(P)) return set_err(H2SHA_EINVAL, "usable_rows is smaller than an assigned column or a lookup table");
+  if (n_instances == 0) return H2SHA_OK;
+  if (n_instances > 65535) return set_err(H2SHA_EINVAL, "at most 65535 instances per call");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const LookupGeom G = lookup_geom(e, n_instances, usable_rows);
+  const uint32_t n_vals = is_range ? (1u << G.lookup_bits) : (1u << G.limb_bits);
+  // workspace: scans + totals, sorted order + compressed values of the spread table
+  const uint64_t need = n_instances * (3ull * n_vals + 2) * 4;
+  if (need > e->lk_ws_bytes) {
+    cudaFree(e->d_lk_ws); e->d_lk_ws = nullptr; e->lk_ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&e->d_lk_ws, need));
+    e->lk_ws_bytes = need;
+  }
+  PermuteArgs A{};
+  A.mult_stride = G.mult_words;
+  A.mult = mult_dev + (is_range ? (uint64_t)lookup_idx * n_vals : ((uint64_t)n_range << G.lookup_bits) + (uint64_t)(lookup_idx - n_range) * n_vals);
+  A.n_vals = n_vals; A.usable_rows = usable_rows;
+  A.scan = e->d_lk_ws; A.totals = e->d_lk_ws + n_instances * 3ull * n_vals;
+  A.errors = errors_dev;
+  A.out_input = (uint64_t*)permuted_input_dev; A.out_table = (uint64_t*)permuted_table_dev;
+  if (!is_range) {
+    // compressed table expression dense * theta + spread (halo2 `compress_expressions`), sorted by canonical value
+    // (`impl Ord for Fr`): 2^num_bits_lookup field multiplications, done on the host with the plan-time helpers
+    U256 th_m; memcpy(th_m.l, theta_mont, 32);
+    if (fr::geq_p(th_m.l)) return set_err(H2SHA_EINVAL, "theta is not a reduced field element");
+    static const U256 r_inv = fr::inv(fr::mont_r());
+    const U256 theta = fr::mul(th_m, r_inv);
+    struct Row { U256 c; uint32_t row; };
+    std::vector<Row> rows(n_vals);
+    for (uint32_t i = 0; i < n_vals; i++) {
+      uint64_t sp = 0;
+      for (uint32_t b = 0; b < G.limb_bits; b++) sp |= (uint64_t)((i >> b) & 1u) << (2 * b);   // spread.rs:171-180
+      rows[i].c = fr::add(fr::mul(theta, fr::from_u64(i)), fr::from_u64(sp));
+      rows[i].row = i;
+    }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return u256_less(a.c, b.c); });
+    for (uint32_t i = 0; i + 1 < n_vals; i++)
+      if (rows[i].c == rows[i + 1].c) return set_err(H2SHA_EINVAL, "theta makes two spread-table rows collide");
+    std::vector<uint32_t> host(n_vals * 9);   // values (16-byte aligned for the 128-bit loads), then the order
+    for (uint32_t i = 0; i < n_vals; i++) {
+      host[8 * n_vals + i] = rows[i].row;
+      const U256 m = fr::to_mont(rows[i].c);
+      memcpy(&host[8 * i], m.l, 32);
+    }
+    if (!e->d_lk_tab) CUDA_TRY(cudaMalloc(&e->d_lk_tab, (size_t)(1u << 8) * 9 * 4));
+    CUDA_TRY(cudaMemcpyAsync(e->d_lk_tab, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st));   // pageable: staged before return
+    A.vals = e->d_lk_tab; A.order = e->d_lk_tab + 8 * n_vals;
+  }
+  k_permute_scan<<<(unsigned)n_instances, 1024, 0, st>>>(A);
+  CUDA_TRY(cudaGetLastError());
+  const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, (uint64_t)e->n_sms * 8);
+  k_permute_fill<<<dim3(tiles, (unsigned)n_instances), 256, 0, st>>>(A);
+  CUDA_TRY(cudaGetLastError());
+  return H2SHA_OK;
+}
+
+}  // extern "C"

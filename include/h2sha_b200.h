@@ -137,6 +137,39 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* batch);
 int h2sha_export_instance(h2sha_engine_t* e, uint64_t instance, const void* gate, const void* lookup, const void* spread,
                           uint64_t* const* host_columns, uint32_t rows_per_column, void* stream);
 
+/* ---- Lookup-argument pre-work on the witness in HBM (the step after assignment in create_proof) --------------------
+ * The chip has two kinds of lookups, neither with a selector (every usable row is looked up):
+ *   range lookup l  (l < n_range_lookups = n_lookup_cols): lookup advice column l against the table 0 .. 2^lookup_bits - 1
+ *                   (halo2-base RangeConfig, lib.rs:409-418; filled by range.finalize, lib.rs:469);
+ *   spread lookup c (index n_range_lookups + c, c < num_advice_columns): (denses[c], spreads[c]) against
+ *                   (table_dense, table_spread) (spread.rs:53-62, 165-194).
+ * halo2's lookup prover (halo2_proofs plonk/lookup/prover.rs, `permute_expression_pair`) needs per lookup A' = the
+ * (compressed) input column sorted and S' = the table column permuted so that A'[i] == S'[i] or A'[i] == A'[i-1].
+ * Never-assigned advice rows hold 0; table columns are padded with their first row.  `usable_rows` = 2^k - (blinding
+ * factors + 1); the trailing blinding rows are random and stay with the prover. */
+typedef struct {
+  uint32_t n_range_lookups, n_spread_lookups;
+  uint32_t range_table_rows, spread_table_rows;   /* 2^lookup_bits, 2^num_bits_lookup                                    */
+  uint32_t min_usable_rows;                       /* largest assigned lookup / spread column or table                     */
+  uint64_t mult_words_per_instance;               /* n_range_lookups * range_table_rows + n_spread_lookups * spread_table_rows */
+} h2sha_lookup_info_t;
+int h2sha_get_lookup_info(const h2sha_engine_t* e, h2sha_lookup_info_t* out);
+
+/* Challenge-independent half: how often each table row is hit by the first `usable_rows` rows of each lookup's input.
+ *   mult_dev [n_instances][mult_words_per_instance] u32 (device): range lookups first ([l][2^lookup_bits]), then the spread
+ *   lookups ([c][2^num_bits_lookup]).  `lookup` / `spread` are the batch buffers of h2sha_digest_batch; one of them may be
+ *   NULL (its half of mult_dev is left untouched).  not_in_table_dev (device u32, may be NULL) counts cells that are no
+ *   table row (a witness the lookup argument would reject).  Asynchronous on `stream`. */
+int h2sha_lookup_multiplicities(h2sha_engine_t* e, uint64_t n_instances, const void* lookup, const void* spread, uint32_t usable_rows,
+                                uint32_t* mult_dev, uint32_t* not_in_table_dev, void* stream);
+
+/* Permuted pair of lookup `lookup_idx` for every instance: permuted_input_dev / permuted_table_dev [n_instances][usable_rows]
+ * Fr (Montgomery, device).  theta_mont (host, 4 x u64 Montgomery) compresses the two expressions of a spread lookup
+ * (dense * theta + spread); NULL for range lookups (one expression).  errors_dev (device u32, may be NULL) is incremented
+ * for every instance whose multiplicities do not sum to usable_rows (its rows are then not written). */
+int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint32_t usable_rows,
+                         const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream);
+
 /* Zero-fill output buffers (or just the never-assigned ranges when only_unassigned != 0). */
 int h2sha_zero_outputs(h2sha_engine_t* e, uint64_t n_instances, void* gate, void* lookup, void* spread, int only_unassigned, void* stream);
 
