@@ -370,6 +370,40 @@ def main():
         except Exception as ex:   # measurement extras must not take the bench line down
             store_ceiling = {"error": str(ex)}
 
+    # ---- extra datapoint: lookup-argument pre-work on the witness that is in HBM (not part of `value`): multiplicities of
+    # every instance of the step, permuted (A', S') pairs of a 64-instance slice (64 B written per usable row) ----
+    prework = None
+    if rank == 0:
+        try:
+            usable = (1 << 17) - 6
+            info = cfg.lookup_info()
+            res_view = pkg.BatchResult(None, None, gate, lookup, spread)
+            if usable >= info["min_usable_rows"]:
+                n_mult = min(per_gpu, 4096)
+                rv = pkg.BatchResult(None, None, gate[:n_mult], lookup[:n_mult], spread[:n_mult])
+                tm = []
+                for _ in range(4):
+                    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a_.record(stream); mult, bad = cfg.lookup_multiplicities(rv, usable); b_.record(stream); b_.synchronize()
+                    tm.append(a_.elapsed_time(b_))
+                assert bad == 0, "witness cells outside the lookup tables"
+                n_perm = min(n_mult, 64)
+                tp = []
+                for _ in range(4):
+                    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a_.record(stream); pa, ps = cfg.permute_lookup(mult[:n_perm], 0, usable); b_.record(stream); b_.synchronize()
+                    tp.append(a_.elapsed_time(b_))
+                read_b = n_mult * (lay.n_lookup_cells + 2 * lay.n_spread_limbs) * 32
+                prework = {"usable_rows": usable, "multiplicities_ms": min(tm[1:]), "multiplicities_instances": n_mult,
+                           "multiplicities_read_gbs": read_b / (min(tm[1:]) * 1e-3) / 1e9,
+                           "permute_range_lookup_ms": min(tp[1:]), "permute_instances": n_perm,
+                           "permute_write_gbs": n_perm * usable * 64 / (min(tp[1:]) * 1e-3) / 1e9,
+                           "note": "h2sha_lookup_multiplicities / h2sha_permute_lookup incl. their memsets, allocation of the outputs and one host sync"}
+                del mult, pa, ps
+            del res_view
+        except Exception as ex:
+            prework = {"error": str(ex)}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         traffic = None   # dram__bytes_read + dram__bytes_write of one k_expand launch, from the committed ncu capture of this workload
@@ -404,6 +438,7 @@ def main():
                          "frac_of_store_ceiling": (achieved / store_ceiling["gbs"]) if store_ceiling and "gbs" in store_ceiling else None,
                          "k_expand_burst_ms": burst_ms,
                          "achieved_burst": (alg_bytes / (burst_ms * 1e-3) / 1e9) if burst_ms else None},
+            "lookup_prework": prework,
             "verified_instances_vs_oracle": verified, "mock_prover_instances": mock_prover_instances, "job_checksum": job_ck,
         }
         if not args.no_cpu:

@@ -962,6 +962,7 @@ struct h2sha_engine {
   uint32_t* d_lk_ws = nullptr;    // scans of the permutation kernels
   uint64_t lk_ws_bytes = 0;
   uint32_t* d_lk_tab = nullptr;   // compressed spread table in sorted order
+  uint32_t* d_range_tab = nullptr;   // Montgomery form of the range table's values
 };
 
 namespace {
@@ -1170,7 +1171,7 @@ void h2sha_destroy(h2sha_engine_t* e) {
   for (int b = 0; b < 3; b++) cudaFree(e->d_zero_ranges[b]);
   cudaFree(e->d_msgs); cudaFree(e->d_offsets); cudaFree(e->d_lens); cudaFree(e->d_pre); cudaFree(e->d_btrace); cudaFree(e->d_dtrace);
   cudaFree(e->d_digests_out); cudaFree(e->d_cks);
-  cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab);
+  cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab); cudaFree(e->d_range_tab);
   delete e;
 }
 

@@ -88,6 +88,41 @@ inline U256 to_mont(const U256& a) {
   static const U256 R = mont_r();
   return mul(a, R);
 }
+// Montgomery product a * b * 2^-256 mod p (CIOS, 64-bit limbs) for a, b < p; -p^-1 mod 2^64 by Newton iteration
+inline uint64_t neg_p_inv64() {
+  uint64_t inv = 1;
+  for (int i = 0; i < 6; i++) inv *= 2 - P[0] * inv;
+  return 0 - inv;
+}
+inline U256 mont_mul(const U256& a, const U256& b) {
+  static const uint64_t ninv = neg_p_inv64();
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a.l[j] * b.l[i] + t[j];
+      t[j] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (uint64_t)c;
+    t[5] = (uint64_t)(c >> 64);
+    const uint64_t m = t[0] * ninv;
+    c = (u128)m * P[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * P[j] + t[j];
+      t[j - 1] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (uint64_t)c;
+    t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  U256 r = {{t[0], t[1], t[2], t[3]}};
+  if (t[4] != 0 || geq_p(r.l)) sub_p(r.l);
+  return r;
+}
 // canonical value of a signed small integer
 inline U256 from_i64(int64_t v) { return v >= 0 ? from_u64((uint64_t)v) : neg(from_u64((uint64_t)(-v))); }
 

@@ -10,7 +10,7 @@
 // of the input, so the work is split into
 //   k_range_mult / k_spread_mult   cells (Montgomery Fr) -> canonical value (REDC) -> histogram over the table rows,
 //   k_permute_scan                 per (instance, lookup): exclusive scans over the table rows in sorted order,
-//   k_permute_fill                 one thread per row: binary search in the scans, 2 x 256-bit stores.
+//   k_permute_fill                 one thread per row: two-level search in the scans, 2 x 256-bit stores.
 // HBM-bound like the rest of the path: the fill writes 64 B per usable row and reads only the (L2-resident) scans.
 // oracle/lookup_prework.py is the CPU restatement the tests compare against.
 #pragma once
@@ -135,25 +135,34 @@ struct PermuteArgs {
 // (-> how many runs start before it) and of the leftover table multiplicity t - [m > 0]
 // (t = 1 per table row; the row holding the padding value -- table row 0 -- also takes the usable_rows - n_vals padded rows)
 __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
-  __shared__ uint32_t s_part[3][32];
-  __shared__ uint32_t s_base[3];
+  __shared__ uint32_t s_part[2][3][32];   // double-buffered by round: two barriers per round
   const uint32_t inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* m = A.mult + (uint64_t)inst * A.mult_stride;
   uint32_t* start = A.scan + (uint64_t)inst * 3 * A.n_vals;
   uint32_t* dpre = start + A.n_vals;
   uint32_t* lpre = dpre + A.n_vals;
-  if (tid < 3) s_base[tid] = 0;
-  __syncthreads();
   const uint32_t pad = A.usable_rows - A.n_vals;
-  for (uint32_t k0 = 0; k0 < A.n_vals; k0 += 1024) {
-    const uint32_t k = k0 + tid;
-    uint32_t v[3] = {0, 0, 0};
-    if (k < A.n_vals) {
+  // rounds of 1024 threads x `per` consecutive sorted positions; 128-bit loads / stores when the order is the identity
+  const bool vec = A.order == nullptr && (A.n_vals & 4095u) == 0 && (A.mult_stride & 3u) == 0 && ((uintptr_t)A.mult & 15u) == 0;
+  const uint32_t per = vec ? 4u : 1u;
+  uint32_t base[3] = {0, 0, 0};
+  uint32_t round = 0;
+  for (uint32_t k0 = 0; k0 < A.n_vals; k0 += 1024u * per, round++) {
+    const uint32_t k = k0 + tid * per;
+    uint32_t mk[4] = {0, 0, 0, 0}, lf[4] = {0, 0, 0, 0};
+    if (vec) {
+      const uint4 q4 = *reinterpret_cast<const uint4*>(m + k);
+      mk[0] = q4.x; mk[1] = q4.y; mk[2] = q4.z; mk[3] = q4.w;
+#pragma unroll
+      for (int i = 0; i < 4; i++) lf[i] = 1u + ((k + i) == 0 ? pad : 0u) - (mk[i] ? 1u : 0u);
+    } else if (k < A.n_vals) {
       const uint32_t row = A.order ? A.order[k] : k;
-      const uint32_t mk = m[row];
-      v[0] = mk; v[1] = mk ? 1u : 0u;
-      v[2] = 1u + (row == 0 ? pad : 0u) - v[1];
+      mk[0] = m[row];
+      lf[0] = 1u + (row == 0 ? pad : 0u) - (mk[0] ? 1u : 0u);
     }
+    uint32_t v[3] = {mk[0] + mk[1] + mk[2] + mk[3], (mk[0] ? 1u : 0u) + (mk[1] ? 1u : 0u) + (mk[2] ? 1u : 0u) + (mk[3] ? 1u : 0u),
+                     lf[0] + lf[1] + lf[2] + lf[3]};
+    uint32_t (*part)[32] = s_part[round & 1u];
     uint32_t incl[3];
 #pragma unroll
     for (int q = 0; q < 3; q++) {
@@ -164,40 +173,47 @@ __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
         if ((int)lane >= o) x += y;
       }
       incl[q] = x;
-      if (lane == 31) s_part[q][warp] = x;
+      if (lane == 31) part[q][warp] = x;
     }
     __syncthreads();
     if (warp < 3) {
-      uint32_t x = s_part[warp][lane];
+      uint32_t x = part[warp][lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if ((int)lane >= o) x += y;
       }
-      s_part[warp][lane] = x;   // inclusive over warps
+      part[warp][lane] = x;   // inclusive over warps
     }
     __syncthreads();
     uint32_t ex[3];
 #pragma unroll
-    for (int q = 0; q < 3; q++) ex[q] = s_base[q] + (warp ? s_part[q][warp - 1] : 0u) + incl[q] - v[q];
-    if (k < A.n_vals) { start[k] = ex[0]; dpre[k] = ex[1]; lpre[k] = ex[2]; }
-    __syncthreads();
-    if (tid < 3) s_base[tid] += s_part[tid][31];
-    __syncthreads();
+    for (int q = 0; q < 3; q++) {
+      ex[q] = base[q] + (warp ? part[q][warp - 1] : 0u) + incl[q] - v[q];
+      base[q] += part[q][31];
+    }
+    if (vec) {
+      uint4 o0, o1, o2;
+      o0.x = ex[0]; o0.y = o0.x + mk[0]; o0.z = o0.y + mk[1]; o0.w = o0.z + mk[2];
+      o1.x = ex[1]; o1.y = o1.x + (mk[0] ? 1u : 0u); o1.z = o1.y + (mk[1] ? 1u : 0u); o1.w = o1.z + (mk[2] ? 1u : 0u);
+      o2.x = ex[2]; o2.y = o2.x + lf[0]; o2.z = o2.y + lf[1]; o2.w = o2.z + lf[2];
+      *reinterpret_cast<uint4*>(start + k) = o0; *reinterpret_cast<uint4*>(dpre + k) = o1; *reinterpret_cast<uint4*>(lpre + k) = o2;
+    } else if (k < A.n_vals) {
+      start[k] = ex[0]; dpre[k] = ex[1]; lpre[k] = ex[2];
+    }
   }
   if (tid == 0) {
-    A.totals[2 * inst] = s_base[1];
-    A.totals[2 * inst + 1] = s_base[0];
-    if (s_base[0] != A.usable_rows && A.errors) atomicAdd(A.errors, 1u);   // multiplicities do not cover the usable rows
+    A.totals[2 * inst] = base[1];
+    A.totals[2 * inst + 1] = base[0];
+    if (base[0] != A.usable_rows && A.errors) atomicAdd(A.errors, 1u);   // multiplicities do not cover the usable rows
   }
 }
 
-// last index k in [0, n) with a[k] <= x (a non-decreasing, a[0] = 0 <= x)
-__device__ __forceinline__ uint32_t last_leq(const uint32_t* __restrict__ a, uint32_t n, uint32_t x) {
-  uint32_t lo = 0, hi = n;   // invariant: a[lo] <= x, (hi == n or a[hi] > x)
-  while (hi - lo > 1) {
+// last index k in [lo, hi) with a[k] <= x (a non-decreasing, a[lo] <= x)
+__device__ __forceinline__ uint32_t last_leq(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t x) {
+  while (hi - lo > 1) {   // invariant: a[lo] <= x, (hi == end or a[hi] > x)
     const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(a + mid) <= x) lo = mid; else hi = mid;
+    if (a[mid] <= x) lo = mid; else hi = mid;
   }
   return lo;
 }
@@ -211,8 +227,12 @@ __device__ __forceinline__ void permuted_value(const PermuteArgs& A, uint32_t k,
   }
 }
 
-// grid = (tiles, instances): thread per row of the permuted pair
+// grid = (tiles, instances), one thread per row.  The two searches (run of the row in A'; leftover table element of a
+// repeated row) are two-level: a <= 256-entry sample of each scan sits in shared memory, so only log2(n_vals / 256)
+// dependent global loads remain per search (8 for the range table, none for the spread table) and neighbouring rows
+// touch the same few cache lines.
 __global__ void __launch_bounds__(256) k_permute_fill(const PermuteArgs A) {
+  __shared__ uint32_t s_start[256], s_lpre[256];
   const uint32_t inst = blockIdx.y;
   const uint32_t* start = A.scan + (uint64_t)inst * 3 * A.n_vals;
   const uint32_t* dpre = start + A.n_vals;
@@ -220,22 +240,37 @@ __global__ void __launch_bounds__(256) k_permute_fill(const PermuteArgs A) {
   const uint32_t n_distinct = A.totals[2 * inst];
   if (A.totals[2 * inst + 1] != A.usable_rows) return;   // inconsistent multiplicities: reported by the scan kernel
   const uint32_t n_rep = A.usable_rows - n_distinct;
+  const uint32_t stride = max(1u, A.n_vals >> 8), n_coarse = A.n_vals / stride;
+  for (uint32_t i = threadIdx.x; i < n_coarse; i += 256) { s_start[i] = __ldg(start + i * stride); s_lpre[i] = __ldg(lpre + i * stride); }
+  __syncthreads();
   uint32_t* out_a = reinterpret_cast<uint32_t*>(A.out_input) + (uint64_t)inst * A.usable_rows * 8;
   uint32_t* out_s = reinterpret_cast<uint32_t*>(A.out_table) + (uint64_t)inst * A.usable_rows * 8;
-  for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < A.usable_rows; row += gridDim.x * blockDim.x) {
-    const uint32_t k = last_leq(start, A.n_vals, row);
+  for (uint32_t row = blockIdx.x * 256u + threadIdx.x; row < A.usable_rows; row += gridDim.x * 256u) {
+    const uint32_t c = last_leq(s_start, 0, n_coarse, row) * stride;
+    const uint32_t k = last_leq(start, c, c + stride, row);
     uint32_t x[8];
     permuted_value(A, k, x);
     store_cell2(out_a + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
     if (row != __ldg(start + k)) {
-      // a repeated row: halo2 pops the repeated rows from the back while walking the leftover table elements upwards
+      // a repeated row: halo2 pops the repeated rows from the back while walking the leftover table elements upwards.
+      // rows <= row: row + 1, first occurrences among them: dpre[k] + 1 -> zero-based rank among the repeated rows
       const uint32_t rank = row - __ldg(dpre + k) - 1u;
       const uint32_t j = n_rep - 1u - rank;
-      const uint32_t w = last_leq(lpre, A.n_vals, j);
+      const uint32_t c2 = last_leq(s_lpre, 0, n_coarse, j) * stride;
+      const uint32_t w = last_leq(lpre, c2, c2 + stride, j);
       permuted_value(A, w, x);
     }
     store_cell2(out_s + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
   }
+}
+
+// Montgomery form of 0 .. n-1: the range table's values, kept in HBM (2 MB for 16 bits, L2-resident while the fill runs)
+__global__ void k_range_table(uint32_t* tab, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x[8];
+  mont_from_u32(i, x);
+  store_cell2(tab + (uint64_t)i * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
 }
 
 int ensure_lookup_consts(h2sha_engine* e) {
@@ -357,19 +392,26 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   A.scan = e->d_lk_ws; A.totals = e->d_lk_ws + n_instances * 3ull * n_vals;
   A.errors = errors_dev;
   A.out_input = (uint64_t*)permuted_input_dev; A.out_table = (uint64_t*)permuted_table_dev;
-  if (!is_range) {
+  if (is_range) {
+    if (!e->d_range_tab) {
+      CUDA_TRY(cudaMalloc(&e->d_range_tab, (size_t)n_vals * 32));
+      k_range_table<<<(n_vals + 255) / 256, 256, 0, st>>>(e->d_range_tab, n_vals);
+      CUDA_TRY(cudaGetLastError());
+    }
+    A.vals = e->d_range_tab;
+  } else {
     // compressed table expression dense * theta + spread (halo2 `compress_expressions`), sorted by canonical value
     // (`impl Ord for Fr`): 2^num_bits_lookup field multiplications, done on the host with the plan-time helpers
     U256 th_m; memcpy(th_m.l, theta_mont, 32);
     if (fr::geq_p(th_m.l)) return set_err(H2SHA_EINVAL, "theta is not a reduced field element");
-    static const U256 r_inv = fr::inv(fr::mont_r());
-    const U256 theta = fr::mul(th_m, r_inv);
-    struct Row { U256 c; uint32_t row; };
+    static const U256 r2 = fr::to_mont(fr::mont_r());   // R^2 mod p: mont_mul(v, r2) = Montgomery form of v
+    struct Row { U256 c, cm; uint32_t row; };
     std::vector<Row> rows(n_vals);
     for (uint32_t i = 0; i < n_vals; i++) {
       uint64_t sp = 0;
       for (uint32_t b = 0; b < G.limb_bits; b++) sp |= (uint64_t)((i >> b) & 1u) << (2 * b);   // spread.rs:171-180
-      rows[i].c = fr::add(fr::mul(theta, fr::from_u64(i)), fr::from_u64(sp));
+      rows[i].cm = fr::add(fr::mont_mul(th_m, fr::mont_mul(fr::from_u64(i), r2)), fr::mont_mul(fr::from_u64(sp), r2));
+      rows[i].c = fr::mont_mul(rows[i].cm, fr::from_u64(1));   // canonical value: what `Ord` compares
       rows[i].row = i;
     }
     std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return u256_less(a.c, b.c); });
@@ -378,8 +420,7 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
     std::vector<uint32_t> host(n_vals * 9);   // values (16-byte aligned for the 128-bit loads), then the order
     for (uint32_t i = 0; i < n_vals; i++) {
       host[8 * n_vals + i] = rows[i].row;
-      const U256 m = fr::to_mont(rows[i].c);
-      memcpy(&host[8 * i], m.l, 32);
+      memcpy(&host[8 * i], rows[i].cm.l, 32);
     }
     if (!e->d_lk_tab) CUDA_TRY(cudaMalloc(&e->d_lk_tab, (size_t)(1u << 8) * 9 * 4));
     CUDA_TRY(cudaMemcpyAsync(e->d_lk_tab, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st));   // pageable: staged before return
@@ -387,7 +428,7 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   }
   k_permute_scan<<<(unsigned)n_instances, 1024, 0, st>>>(A);
   CUDA_TRY(cudaGetLastError());
-  const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, (uint64_t)e->n_sms * 8);
+  const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, std::max<uint64_t>(16, ((uint64_t)e->n_sms * 16 + n_instances - 1) / n_instances));
   k_permute_fill<<<dim3(tiles, (unsigned)n_instances), 256, 0, st>>>(A);
   CUDA_TRY(cudaGetLastError());
   return H2SHA_OK;

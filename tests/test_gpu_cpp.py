@@ -32,3 +32,13 @@ def test_reference_tests_through_cpp_host_api(pkg):
     print(out.stdout, out.stderr)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok ") == 5
+
+
+def test_host_field_helpers():
+    """csrc/fr_host.h: the CIOS Montgomery product (spread-table compression of h2sha_permute_lookup) against the
+    double-and-add product; plain g++, no GPU."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_fr_host")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_fr_host.cc")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
