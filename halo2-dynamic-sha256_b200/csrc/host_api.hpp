@@ -70,6 +70,23 @@ class Sha256DynamicConfig {
     check(h2sha_get_breaks(engine_, b.data()));
     return b;
   }
+  // ---- lookup-argument pre-work on the witness in HBM (halo2 lookup prover `permute_expression_pair`) ----
+  h2sha_lookup_info_t lookup_info() const {
+    h2sha_lookup_info_t li{};
+    check(h2sha_get_lookup_info(engine_, &li));
+    return li;
+  }
+  // table-row multiplicities of every lookup (spread.rs:53-62; range lookup of lib.rs:409-418,469); all pointers are device memory
+  void lookup_multiplicities(uint64_t n_instances, const void* lookup, const void* spread, uint32_t usable_rows, uint32_t* mult_dev,
+                             uint32_t* not_in_table_dev, void* stream) {
+    check(h2sha_lookup_multiplicities(engine_, n_instances, lookup, spread, usable_rows, mult_dev, not_in_table_dev, stream));
+  }
+  // permuted (A', S') columns of one lookup for every instance; theta_mont only for spread lookups
+  void permute_lookup(uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint32_t usable_rows, const uint64_t* theta_mont,
+                      void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream) {
+    check(h2sha_permute_lookup(engine_, n_instances, lookup_idx, mult_dev, usable_rows, theta_mont, permuted_input_dev, permuted_table_dev,
+                               errors_dev, stream));
+  }
   h2sha_engine_t* raw() const { return engine_; }
 
  private:

@@ -142,6 +142,35 @@ impl Sha256DynamicConfig {
     }
 
     pub fn layout(&self) -> &h2sha_layout_t { &self.layout }
+
+    /// Lookup-argument pre-work on the batch that is in HBM: table-row multiplicities of the range lookup(s)
+    /// (halo2-base RangeConfig, lib.rs:409-418,469) and the spread lookups (spread.rs:53-62).  `mult` is a device
+    /// buffer of `n * lookup_info().mult_words_per_instance` u32; `not_in_table` a device u32 (or 0).
+    pub fn lookup_multiplicities(&mut self, n: usize, lookup: u64, spread: u64, usable_rows: u32, mult: u64, not_in_table: u64,
+                                 stream: *mut std::ffi::c_void) -> Result<(), Error> {
+        check(unsafe {
+            h2sha_lookup_multiplicities(self.engine, n as u64, lookup as *const _, spread as *const _, usable_rows, mult as *mut u32,
+                                        not_in_table as *mut u32, stream)
+        })
+    }
+
+    /// The permuted pair (A', S') halo2's `permute_expression_pair` would build for lookup `lookup_idx` of every
+    /// instance (`theta`: the transcript challenge in Montgomery limbs, only for the two-expression spread lookups).
+    /// Outputs: device buffers of `n * usable_rows` Fr each; the blinding rows stay with the prover.
+    pub fn permute_lookup(&mut self, n: usize, lookup_idx: u32, mult: u64, usable_rows: u32, theta: Option<&[u64; 4]>, permuted_input: u64,
+                          permuted_table: u64, errors: u64, stream: *mut std::ffi::c_void) -> Result<(), Error> {
+        check(unsafe {
+            h2sha_permute_lookup(self.engine, n as u64, lookup_idx, mult as *const u32, usable_rows,
+                                 theta.map(|t| t.as_ptr()).unwrap_or(std::ptr::null()), permuted_input as *mut _, permuted_table as *mut _,
+                                 errors as *mut u32, stream)
+        })
+    }
+
+    pub fn lookup_info(&self) -> Result<h2sha_lookup_info_t, Error> {
+        let mut li: h2sha_lookup_info_t = unsafe { std::mem::zeroed() };
+        check(unsafe { h2sha_get_lookup_info(self.engine, &mut li) })?;
+        Ok(li)
+    }
 }
 
 impl Drop for Sha256DynamicConfig {
