@@ -346,6 +346,7 @@ def main():
     # cells (coalesced 256-bit stores, nothing else) over a buffer larger than L2, (b) k_expand timed alone after an idle
     # gap (burst clocks; the figures above are from back-to-back launches under the power cap) ----
     store_ceiling = None
+    int_ceiling = None
     burst_ms = None
     if rank == 0:
         try:
@@ -360,6 +361,14 @@ def main():
             store_ceiling = {"gbs": pb / (min(ts[1:]) * 1e-3) / 1e9, "bytes": pb,
                              "how": "k_store_probe: coalesced st.global.v8.b32 of incompressible 32-byte cells, best of 5"}
             del probe
+            # (a') integer-ALU ceiling: IMAD/LOP3 dependency chains, no memory traffic
+            scratch = torch.zeros(148 * 8 * 256 * 2, dtype=torch.int32, device=dev)
+            ti = []
+            for _ in range(4):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(stream); n_int = cfg.int_probe(scratch.data_ptr(), 1 << 14, sp); b_.record(stream); b_.synchronize()
+                ti.append(a_.elapsed_time(b_))
+            int_ceiling = {"ginst_s": n_int / (min(ti[1:]) * 1e-3) / 1e9, "how": "k_int_probe: 8 independent IMAD+LOP3 chains per thread, 8 CTAs x 256 threads per SM, best of 3"}
             time.sleep(0.5)
             bm = []
             for _ in range(3):
@@ -407,13 +416,21 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         traffic = None   # dram__bytes_read + dram__bytes_write of one k_expand launch, from the committed ncu capture of this workload
+        int_insts = None  # thread-level integer instructions of one k_expand launch, same capture
         try:
             with open(os.path.join(ROOT, "profiles", "k_expand_traffic.json")) as f:
                 tj = json.load(f)
             if tj["workload"] == w.name and tj["instances_per_launch"] == per_gpu:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                int_insts = tj.get("int_thread_insts")
         except Exception:
             pass
+        int_roof = None
+        if int_insts and int_ceiling and "ginst_s" in int_ceiling:
+            ach = int_insts / (expand_ms * 1e-3) / 1e9
+            int_roof = {"achieved": ach, "peak": int_ceiling["ginst_s"], "unit": "Ginst/s (thread-level integer instructions)", "frac": ach / int_ceiling["ginst_s"],
+                        "instructions_per_launch": int_insts, "peak_source": int_ceiling["how"],
+                        "note": "the other roofline the north star names; HBM write is the slower (binding) one"}
         alg_bytes = per_gpu * lay.cells_per_instance * 32
         achieved = alg_bytes / (expand_ms * 1e-3) / 1e9
         line = {
@@ -436,6 +453,7 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "store_ceiling": store_ceiling,
                          "frac_of_store_ceiling": (achieved / store_ceiling["gbs"]) if store_ceiling and "gbs" in store_ceiling else None,
+                         "int_alu": int_roof,
                          "k_expand_burst_ms": burst_ms,
                          "achieved_burst": (alg_bytes / (burst_ms * 1e-3) / 1e9) if burst_ms else None},
             "lookup_prework": prework,

@@ -29,7 +29,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape", "h2sha_get_lookup_tables",
-    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
+    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_debug_int_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
 
@@ -99,6 +99,7 @@ def load_library():
     L.h2sha_debug_mont_from_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.h2sha_debug_mont_from_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.h2sha_debug_store_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.h2sha_debug_int_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p]
     L.h2sha_last_launch_count.argtypes = [C.c_void_p]
     L.h2sha_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L
@@ -252,6 +253,12 @@ class Sha256DynamicConfig:
     def store_probe(self, buf_ptr: int, nbytes: int, stream: int = 0):
         """Measurement hook: plain coalesced 256-bit stores of incompressible cells over [buf_ptr, buf_ptr + nbytes)."""
         _check(load_library().h2sha_debug_store_probe(self._h, C.c_void_p(buf_ptr), C.c_uint64(nbytes), C.c_void_p(stream)))
+
+    def int_probe(self, scratch_ptr: int, iters: int, stream: int = 0) -> int:
+        """Measurement hook: IMAD/LOP3 dependency chains, no memory traffic; returns the integer instructions the launch executes."""
+        n = C.c_uint64()
+        _check(load_library().h2sha_debug_int_probe(self._h, C.c_void_p(scratch_ptr), C.c_uint32(iters), C.byref(n), C.c_void_p(stream)))
+        return int(n.value)
 
     def lookup_tables(self):
         """(dense[2^bits], spread[2^bits], n_range_rows): SpreadConfig::load (spread.rs:165-194) and the range table's row count."""

@@ -887,6 +887,27 @@ __global__ void k_store_probe(uint32_t* out, uint64_t n_cells, uint32_t salt) {
   }
 }
 
+// second reference point (the north star names two rooflines): integer ALU throughput of this GPU for the instruction mix the
+// expansion kernel is made of -- 32-bit multiply-adds (IMAD: Barrett / Montgomery limbs, checksum hashes) and 3-input logic ops
+// (LOP3: extracts, spreads) -- from 8 independent dependency chains per thread, no memory traffic
+__global__ void __launch_bounds__(256) k_int_probe(uint32_t* out, uint32_t iters, uint32_t seed) {
+  uint32_t a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = seed + threadIdx.x * 8u + i + blockIdx.x;
+  const uint32_t m = seed | 1u, x = seed * 2654435761u;
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      a[i] = a[i] * m + x;                                   // IMAD
+      a[i] = (a[i] ^ (a[(i + 1) & 7] & x));                  // LOP3
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r ^= a[i];
+  if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;   // keeps the chains alive, (almost) never stores
+}
+
 __global__ void k_zero_ranges(uint4* buf, uint64_t inst_cells, uint64_t n_inst, const uint32_t* ranges /*pos,count pairs*/, uint32_t n_ranges) {
   // grid.y = instance, grid.x strides over the cells of all ranges
   uint64_t inst = blockIdx.y;
@@ -1420,6 +1441,17 @@ int h2sha_debug_store_probe(h2sha_engine_t* e, void* buf_dev, uint64_t bytes, vo
   if (bytes < 32) return H2SHA_OK;
   k_store_probe<<<(unsigned)(e->n_sms * 8), 256, 0, (cudaStream_t)stream>>>((uint32_t*)buf_dev, bytes / 32, (uint32_t)bytes);
   CUDA_TRY(cudaGetLastError());
+  return H2SHA_OK;
+}
+
+int h2sha_debug_int_probe(h2sha_engine_t* e, uint32_t* scratch_dev, uint32_t iters, uint64_t* thread_instructions, void* stream) {
+  if (!e || !scratch_dev) return set_err(H2SHA_EINVAL, "null argument");
+  if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const unsigned ctas = (unsigned)e->n_sms * 8u;
+  k_int_probe<<<ctas, 256, 0, (cudaStream_t)stream>>>(scratch_dev, iters, 0x9E3779B9u);
+  CUDA_TRY(cudaGetLastError());
+  if (thread_instructions) *thread_instructions = (uint64_t)ctas * 256u * iters * 16u;
   return H2SHA_OK;
 }
 

@@ -188,6 +188,11 @@ int h2sha_debug_mont_from_u32(h2sha_engine_t* e, const uint64_t* vals_dev, uint6
  * (no shared memory, no arithmetic) -- the write-bandwidth ceiling bench.py reports next to the expansion kernel. */
 int h2sha_debug_store_probe(h2sha_engine_t* e, void* buf_dev, uint64_t bytes, void* stream);
 
+/* Measurement hook for the other roofline the path could hit: `iters` x 16 dependent-chain integer instructions (8 IMAD +
+ * 8 LOP3 over 8 independent chains) per thread on n_sms * 8 CTAs of 256 threads, no memory traffic.  scratch_dev: device
+ * buffer of n_sms * 8 * 256 u32 (practically never written).  *thread_instructions = integer instructions the launch executes. */
+int h2sha_debug_int_probe(h2sha_engine_t* e, uint32_t* scratch_dev, uint32_t iters, uint64_t* thread_instructions, void* stream);
+
 /* Kernel launch statistics of the last h2sha_digest_batch (for bench.py's gpu_launches). */
 int h2sha_last_launch_count(const h2sha_engine_t* e);
 /* Device time of the two kernels of the last batch run with time_kernels = 1; synchronises on the recorded events. */
