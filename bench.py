@@ -358,8 +358,20 @@ def main():
                 a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a_.record(stream); cfg.store_probe(probe.data_ptr(), pb, sp); b_.record(stream); b_.synchronize()
                 ts.append(a_.elapsed_time(b_))
-            store_ceiling = {"gbs": pb / (min(ts[1:]) * 1e-3) / 1e9, "bytes": pb,
-                             "how": "k_store_probe: coalesced st.global.v8.b32 of incompressible 32-byte cells, best of 5"}
+            # the same writer back to back for ~1.5 s (the power-capped regime the timed steps run in), then 10 timed launches
+            t_s = time.perf_counter()
+            while time.perf_counter() - t_s < 1.5:
+                for _ in range(20):
+                    cfg.store_probe(probe.data_ptr(), pb, sp)
+                stream.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            for _ in range(10):
+                cfg.store_probe(probe.data_ptr(), pb, sp)
+            b_.record(stream); b_.synchronize()
+            store_ceiling = {"gbs": pb / (min(ts[1:]) * 1e-3) / 1e9, "gbs_sustained": 10 * pb / (a_.elapsed_time(b_) * 1e-3) / 1e9, "bytes": pb,
+                             "how": "k_store_probe: coalesced st.global.v8.b32 of incompressible 32-byte cells; gbs = best of 5 single launches, "
+                                    "gbs_sustained = 10 launches after 1.5 s of back-to-back launches"}
             del probe
             # (a') integer-ALU ceiling: IMAD/LOP3 dependency chains, no memory traffic
             scratch = torch.zeros(148 * 8 * 256 * 2, dtype=torch.int32, device=dev)
@@ -453,6 +465,7 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "store_ceiling": store_ceiling,
                          "frac_of_store_ceiling": (achieved / store_ceiling["gbs"]) if store_ceiling and "gbs" in store_ceiling else None,
+                         "frac_of_sustained_store_ceiling": (achieved / store_ceiling["gbs_sustained"]) if store_ceiling and "gbs_sustained" in store_ceiling else None,
                          "int_alu": int_roof,
                          "k_expand_burst_ms": burst_ms,
                          "achieved_burst": (alg_bytes / (burst_ms * 1e-3) / 1e9) if burst_ms else None},

@@ -59,7 +59,7 @@ struct DevPlan {
   // dynamic shared memory layout after the blob
   uint32_t off_trace, off_scratch, off_misc, smem_bytes;
   uint32_t stage_bytes, stage_off_slots, stage_off_desc;   // per producer warp: trace | slots | StageDesc
-  uint32_t cons_sleep;                                     // consumers poll their full barrier with back-off
+  uint32_t cons_sleep, prod_sleep;                         // back-off (ns) between polls of the full / empty barrier; cons_sleep 0 = tight spin
   uint32_t max_fill, scratch_bytes, n_resident;            // per consumer warp: lo[max_fill] | hi[max_fill]
   // layout
   int32_t spread_cols_shift;   // log2(spread_cols) when it is a power of two, else -1
@@ -439,7 +439,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // polling wait with back-off for warps that are expected to wait long (producers waiting for a free stage): keeps
 // their retries out of the issue slots of the working warps
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
   uint32_t done = 0;
   for (;;) {
     asm volatile(
@@ -452,7 +452,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(256);
+    __nanosleep(ns);
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -613,8 +613,14 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // blob + barriers visible; the only CTA-wide barrier
+#ifdef H2SHA_DEBUG_TIMING
+  unsigned long long dbg_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
+#endif
   // everything above is independent of the trace kernel; from here on its outputs are read
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef H2SHA_DEBUG_TIMING
+  unsigned long long dbg_t2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t2));
+#endif
 
   // jobs: all block-job parts first, then per digest the batched prologue/epilogue jobs
   const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst * P.n_block_parts;
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     StageDesc* desc = reinterpret_cast<StageDesc*>(stage + P.stage_off_desc);
     for (int i = lane; i < 64; i += 32) s_trace[TR_K + i] = c_K[i];
     for (uint32_t k = 0;; k++) {
-      mbar_wait_relaxed(&s_empty[st], (k & 1u) ^ 1u);   // consumers are done with this stage's previous job
+      mbar_wait_relaxed(&s_empty[st], (k & 1u) ^ 1u, P.prod_sleep);   // consumers are done with this stage's previous job
       unsigned long long job = 0;
       if (lane == 0) job = atomicAdd(A.job_counter, 1ULL);
       job = __shfl_sync(0xffffffffu, job, 0);
@@ -702,6 +708,12 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_full[st]);
+#ifdef H2SHA_DEBUG_TIMING
+      if (lane == 0 && k < 3 && (blockIdx.x % 37) == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        printf("P cta %3d prod %d job# %u cls %u: blob %llu ns, wait_trace %llu ns, full at +%llu ns\n", blockIdx.x, st, k, cls, dbg_t1 - 0, dbg_t2 - dbg_t1, t - dbg_t2);
+      }
+#endif
     }
     return;
   }
@@ -716,11 +728,25 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     __syncwarp();
   }
   uint32_t finished = 0;   // bit st: producer st has run out of jobs
+#ifdef H2SHA_DEBUG_TIMING
+  unsigned long long dbg_wait = 0; uint32_t dbg_nwait = 0;
+#endif
   for (uint32_t k = 0; finished != (1u << NPROD) - 1u; k++) {
     const int st = k % NPROD;
     const uint32_t round = k / NPROD;
     if (finished & (1u << st)) continue;
-    if (P.cons_sleep) mbar_wait_relaxed(&s_full[st], round & 1u); else mbar_wait(&s_full[st], round & 1u);
+#ifdef H2SHA_DEBUG_TIMING
+    unsigned long long dbg_w0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_w0));
+#endif
+    if (P.cons_sleep) mbar_wait_relaxed(&s_full[st], round & 1u, P.cons_sleep); else mbar_wait(&s_full[st], round & 1u);
+#ifdef H2SHA_DEBUG_TIMING
+    {
+      unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg_wait += t - dbg_w0; dbg_nwait++;
+      if (lane == 0 && (blockIdx.x % 37) == 0 && (warp % 7) == 0 && (k < 6 || t - dbg_w0 > 3000))
+        printf("C cta %3d warp %2d k %3u: waited %llu ns at +%llu ns\n", blockIdx.x, warp, k, t - dbg_w0, t - dbg_t2);
+    }
+#endif
     const uint8_t* stage = smem + P.off_trace + (size_t)st * P.stage_bytes;
     const uint64_t* s_slots = reinterpret_cast<const uint64_t*>(stage + P.stage_off_slots);
     const StageDesc* desc = reinterpret_cast<const StageDesc*>(stage + P.stage_off_desc);
@@ -857,6 +883,12 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     // ---- checksums: warp reduce, one global atomic per kind and warp (block jobs: one instance per job) ----
     if (A.cks && jc.batch == 1) flush_checksums(A.cks, inst0, ck_g, ck_l, ck_s, lane);
   }
+#ifdef H2SHA_DEBUG_TIMING
+  if (lane == 0 && (blockIdx.x % 37) == 0 && (warp % 7) == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    printf("E cta %3d warp %2d: done at +%llu ns, waited %llu ns in %u waits\n", blockIdx.x, warp, t - dbg_t2, dbg_wait, dbg_nwait);
+  }
+#endif
 }
 
 __global__ void k_mont_debug(const uint64_t* vals, uint64_t* out, uint64_t n) {
@@ -1124,6 +1156,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.n_digests = (uint32_t)P.digests.size();
   D.n_block_parts = P.n_block_parts;
   D.cons_sleep = (uint32_t)tune_value("csleep", 0);
+  D.prod_sleep = (uint32_t)tune_value("psleep", 256);
   D.off_trace = D.blob_bytes;
   D.stage_off_slots = align_up(4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
   D.stage_off_desc = align_up(D.stage_off_slots + 8 * (P.max_slots + 1), 16);

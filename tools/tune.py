@@ -70,4 +70,4 @@ if __name__ == "__main__":
     wl = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1].startswith("cfg") else "cfg2"
     tunes = [a for a in sys.argv[1:] if not a.startswith("cfg")] or ["parts=3,fill=128,cons=16,prod=4"]
     for t in tunes:
-        print(run(wl, t), flush=True)
+        print(run(wl, t, n_inst=int(os.environ.get("TUNE_N", "0")) or None), flush=True)
