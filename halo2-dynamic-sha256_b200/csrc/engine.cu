@@ -640,9 +640,15 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     for (int i = lane; i < 64; i += 32) s_trace[TR_K + i] = c_K[i];
     for (uint32_t k = 0;; k++) {
       mbar_wait_relaxed(&s_empty[st], (k & 1u) ^ 1u, P.prod_sleep);   // consumers are done with this stage's previous job
+#ifdef H2SHA_DEBUG_TIMING
+      unsigned long long dbg_p0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p0));
+#endif
       unsigned long long job = 0;
       if (lane == 0) job = atomicAdd(A.job_counter, 1ULL);
       job = __shfl_sync(0xffffffffu, job, 0);
+#ifdef H2SHA_DEBUG_TIMING
+      unsigned long long dbg_p1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p1));
+#endif
       if (job >= n_jobs) {
         if (lane == 0) { desc->valid = 0; }
         __syncwarp();
@@ -692,6 +698,9 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       const JobClass jc = s_classes[cls];
       if (lane == 0) { desc->inst = inst; desc->cls = cls; desc->gate0 = gate0; desc->lk0 = lk0; desc->limb0 = limb0; desc->valid = 1; desc->n_inst = n_valid; }
       __syncwarp();
+#ifdef H2SHA_DEBUG_TIMING
+      unsigned long long dbg_p2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p2));
+#endif
       // ---- phase 1: slot programs, lanes = unit instances ----
       for (uint32_t t = 0; t < jc.n_tasks; t++) {
         const WarpTask wt = s_tasks[jc.task_off + t];
@@ -711,7 +720,8 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
 #ifdef H2SHA_DEBUG_TIMING
       if (lane == 0 && k < 3 && (blockIdx.x % 37) == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        printf("P cta %3d prod %d job# %u cls %u: blob %llu ns, wait_trace %llu ns, full at +%llu ns\n", blockIdx.x, st, k, cls, dbg_t1 - 0, dbg_t2 - dbg_t1, t - dbg_t2);
+        printf("P cta %3d prod %d job# %u cls %u: wait_trace %llu | empty-wait done +%llu, job fetched +%llu, trace loaded +%llu, full +%llu ns\n", blockIdx.x, st, k, cls,
+               dbg_t2 - dbg_t1, dbg_p0 - dbg_t2, dbg_p1 - dbg_t2, dbg_p2 - dbg_t2, t - dbg_t2);
       }
 #endif
     }
