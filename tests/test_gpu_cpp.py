@@ -42,3 +42,30 @@ def test_host_field_helpers():
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_fr_host.cc")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+def _build_native_runner(pkg):
+    exe = os.path.join(ROOT, "tools", "native_runner")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-o", exe, os.path.join(ROOT, "tools", "native_runner.cc"),
+                           "-L" + libdir, "-lh2sha_b200", "-lnccl", "-Xlinker", "-rpath,$ORIGIN/../halo2-dynamic-sha256_b200", "-cudart", "shared"])
+    return exe
+
+
+def test_native_runner_compiles_and_links(pkg):
+    """The no-Python host program (one thread per GPU, NCCL gather) builds against the C-ABI; without a GPU it refuses to run."""
+    exe = _build_native_runner(pkg)
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe, "--gpus", "1"], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 3 and "no CPU path" in out.stderr
+
+
+@pytest.mark.gpu
+def test_native_runner_one_gpu(pkg):
+    import json
+    exe = _build_native_runner(pkg)
+    out = subprocess.run([exe, "--workload", "cfg3", "--instances", "64", "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["digest_mismatches"] == 0 and line["blocks_per_instance"] == 17 and line["value"] > 0
