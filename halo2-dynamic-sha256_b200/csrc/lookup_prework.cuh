@@ -332,7 +332,6 @@ int h2sha_lookup_multiplicities(h2sha_engine_t* e, uint64_t n_instances, const v
   if (!lookup && !spread) return set_err(H2SHA_EINVAL, "neither the lookup nor the spread buffer was given");
   if (usable_rows < lookup_rows_needed(e->plan)) return set_err(H2SHA_EINVAL, "usable_rows is smaller than an assigned column or a lookup table");
   if (n_instances == 0) return H2SHA_OK;
-  if (n_instances > 65535) return set_err(H2SHA_EINVAL, "at most 65535 instances per call");
   CUDA_TRY(cudaSetDevice(e->device));
   int rc = ensure_lookup_consts(e);
   if (rc) return rc;
@@ -347,17 +346,22 @@ int h2sha_lookup_multiplicities(h2sha_engine_t* e, uint64_t n_instances, const v
     CUDA_TRY(cudaMemset2DAsync(mult_dev + off, G.mult_words * 4, 0, cnt * 4, n_instances, st));
   }
   if (not_in_table_dev) CUDA_TRY(cudaMemsetAsync(not_in_table_dev, 0, 4, st));
-  if (lookup) {
-    const unsigned tiles = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((G.n_lookup + 255) / 256, 64));
-    k_range_mult<<<dim3(tiles, (unsigned)n_instances), 256, 0, st>>>(G, (const uint64_t*)lookup, mult_dev, not_in_table_dev);
-    CUDA_TRY(cudaGetLastError());
-  }
-  if (spread) {
-    const unsigned tiles = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((G.n_limb + 1023) / 1024, 32));
-    const size_t smem = (size_t)G.spread_cols * (1u << G.limb_bits) * 4;
-    if (smem > 48 * 1024) return set_err(H2SHA_EINVAL, "spread histogram does not fit in shared memory");
-    k_spread_mult<<<dim3(tiles, (unsigned)n_instances), 256, smem, st>>>(G, (const uint64_t*)spread, mult_dev, not_in_table_dev);
-    CUDA_TRY(cudaGetLastError());
+  // grid.y = instance: at most 65535 per launch
+  for (uint64_t i0 = 0; i0 < n_instances; i0 += 65535) {
+    const unsigned ni = (unsigned)std::min<uint64_t>(65535, n_instances - i0);
+    uint32_t* m0 = mult_dev + i0 * G.mult_words;
+    if (lookup) {
+      const unsigned tiles = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((G.n_lookup + 255) / 256, 64));
+      k_range_mult<<<dim3(tiles, ni), 256, 0, st>>>(G, (const uint64_t*)lookup + i0 * G.lookup_inst_cells * 4, m0, not_in_table_dev);
+      CUDA_TRY(cudaGetLastError());
+    }
+    if (spread) {
+      const unsigned tiles = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((G.n_limb + 1023) / 1024, 32));
+      const size_t smem = (size_t)G.spread_cols * (1u << G.limb_bits) * 4;
+      if (smem > 48 * 1024) return set_err(H2SHA_EINVAL, "spread histogram does not fit in shared memory");
+      k_spread_mult<<<dim3(tiles, ni), 256, smem, st>>>(G, (const uint64_t*)spread + i0 * G.spread_inst_cells * 4, m0, not_in_table_dev);
+      CUDA_TRY(cudaGetLastError());
+    }
   }
   return H2SHA_OK;
 }
@@ -373,13 +377,13 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   if (!is_range && !theta_mont) return set_err(H2SHA_EINVAL, "a spread lookup has two expressions: theta is needed to compress them");
   if (usable_rows < lookup_rows_needed(P)) return set_err(H2SHA_EINVAL, "usable_rows is smaller than an assigned column or a lookup table");
   if (n_instances == 0) return H2SHA_OK;
-  if (n_instances > 65535) return set_err(H2SHA_EINVAL, "at most 65535 instances per call");
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   const LookupGeom G = lookup_geom(e, n_instances, usable_rows);
   const uint32_t n_vals = is_range ? (1u << G.lookup_bits) : (1u << G.limb_bits);
-  // workspace: scans + totals, sorted order + compressed values of the spread table
-  const uint64_t need = n_instances * (3ull * n_vals + 2) * 4;
+  // workspace: scans + totals of one chunk of instances (the chunks run one after the other on `stream` and share it)
+  const uint64_t chunk = std::min<uint64_t>(n_instances, (uint64_t)std::max(1, tune_value("lkchunk", 256)));
+  const uint64_t need = chunk * (3ull * n_vals + 2) * 4;
   if (need > e->lk_ws_bytes) {
     cudaFree(e->d_lk_ws); e->d_lk_ws = nullptr; e->lk_ws_bytes = 0;
     CUDA_TRY(cudaMalloc(&e->d_lk_ws, need));
@@ -389,7 +393,7 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   A.mult_stride = G.mult_words;
   A.mult = mult_dev + (is_range ? (uint64_t)lookup_idx * n_vals : ((uint64_t)n_range << G.lookup_bits) + (uint64_t)(lookup_idx - n_range) * n_vals);
   A.n_vals = n_vals; A.usable_rows = usable_rows;
-  A.scan = e->d_lk_ws; A.totals = e->d_lk_ws + n_instances * 3ull * n_vals;
+  A.scan = e->d_lk_ws; A.totals = e->d_lk_ws + chunk * 3ull * n_vals;
   A.errors = errors_dev;
   A.out_input = (uint64_t*)permuted_input_dev; A.out_table = (uint64_t*)permuted_table_dev;
   if (is_range) {
@@ -426,11 +430,18 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
     CUDA_TRY(cudaMemcpyAsync(e->d_lk_tab, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st));   // pageable: staged before return
     A.vals = e->d_lk_tab; A.order = e->d_lk_tab + 8 * n_vals;
   }
-  k_permute_scan<<<(unsigned)n_instances, 1024, 0, st>>>(A);
-  CUDA_TRY(cudaGetLastError());
-  const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, std::max<uint64_t>(16, ((uint64_t)e->n_sms * 16 + n_instances - 1) / n_instances));
-  k_permute_fill<<<dim3(tiles, (unsigned)n_instances), 256, 0, st>>>(A);
-  CUDA_TRY(cudaGetLastError());
+  const uint32_t* mult0 = A.mult;
+  for (uint64_t i0 = 0; i0 < n_instances; i0 += chunk) {
+    const uint64_t ni = std::min<uint64_t>(chunk, n_instances - i0);
+    A.mult = mult0 + i0 * A.mult_stride;
+    A.out_input = (uint64_t*)permuted_input_dev + i0 * (uint64_t)usable_rows * 4;
+    A.out_table = (uint64_t*)permuted_table_dev + i0 * (uint64_t)usable_rows * 4;
+    k_permute_scan<<<(unsigned)ni, 1024, 0, st>>>(A);
+    CUDA_TRY(cudaGetLastError());
+    const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, std::max<uint64_t>(16, ((uint64_t)e->n_sms * 16 + ni - 1) / ni));
+    k_permute_fill<<<dim3(tiles, (unsigned)ni), 256, 0, st>>>(A);
+    CUDA_TRY(cudaGetLastError());
+  }
   return H2SHA_OK;
 }
 

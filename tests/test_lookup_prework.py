@@ -208,8 +208,15 @@ def test_permuted_pairs_at_batch_size_hold_the_lookup_rules(pkg):
     info = cfg.lookup_info()
     assert (mult.to(torch.int64).view(n, -1)[:, :65536 * info["n_range_lookups"]].view(n, info["n_range_lookups"], 65536).sum(-1) == usable).all()
     theta_m = O.int_to_mont(int.from_bytes(rng.bytes(32), "little") % P)
+    import os
     for l in range(info["n_range_lookups"] + info["n_spread_lookups"]):
-        a, s = cfg.permute_lookup(mult, l, usable, None if l < info["n_range_lookups"] else theta_m)
+        os.environ["H2SHA_TUNE"] = "lkchunk=24"          # three chunks of instances share the scan workspace
+        try:
+            a, s = cfg.permute_lookup(mult, l, usable, None if l < info["n_range_lookups"] else theta_m)
+        finally:
+            del os.environ["H2SHA_TUNE"]
+        a1, s1 = cfg.permute_lookup(mult[40:41], l, usable, None if l < info["n_range_lookups"] else theta_m)
+        assert bool((a1[0] == a[40]).all()) and bool((s1[0] == s[40]).all()), "chunked and single-instance results differ"
         same = (a == s).all(-1)
         prev = torch.zeros_like(same)
         prev[:, 1:] = (a[:, 1:] == a[:, :-1]).all(-1)
