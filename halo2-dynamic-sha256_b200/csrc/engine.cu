@@ -59,7 +59,7 @@ struct DevPlan {
   // dynamic shared memory layout after the blob
   uint32_t off_trace, off_scratch, off_misc, smem_bytes;
   uint32_t stage_bytes, stage_off_slots, stage_off_desc;   // per producer warp: trace | slots | StageDesc
-  uint32_t cons_sleep, prod_sleep;                         // back-off (ns) between polls of the full / empty barrier; cons_sleep 0 = tight spin
+  uint32_t cons_sleep, prod_sleep, wait_hint;                         // back-off (ns) between polls of the full / empty barrier; cons_sleep 0 = tight spin
   uint32_t max_fill, scratch_bytes, n_resident;            // per consumer warp: lo[max_fill] | hi[max_fill]
   // layout
   int32_t spread_cols_shift;   // log2(spread_cols) when it is a power of two, else -1
@@ -437,10 +437,26 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// polling wait with back-off for warps that are expected to wait long (producers waiting for a free stage): keeps
-// their retries out of the issue slots of the working warps
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+// wait with a suspend-time hint: the hardware parks the warp until the phase completes or `hint_ns` have passed, so a
+// waiting warp issues one instruction per `hint_ns` instead of polling (mode 1), or -- mode 0 -- polls with __nanosleep
+// back-off between tries (the round-1 behaviour)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns, uint32_t use_hint) {
   uint32_t done = 0;
+  if (use_hint) {
+    for (;;) {
+      asm volatile(
+          "{\n"
+          ".reg .pred P1;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+          "selp.u32 %0, 1, 0, P1;\n"
+          "}"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+          : "memory");
+      if (done) break;
+    }
+    return;
+  }
   for (;;) {
     asm volatile(
         "{\n"
@@ -639,7 +655,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     StageDesc* desc = reinterpret_cast<StageDesc*>(stage + P.stage_off_desc);
     for (int i = lane; i < 64; i += 32) s_trace[TR_K + i] = c_K[i];
     for (uint32_t k = 0;; k++) {
-      mbar_wait_relaxed(&s_empty[st], (k & 1u) ^ 1u, P.prod_sleep);   // consumers are done with this stage's previous job
+      mbar_wait_relaxed(&s_empty[st], (k & 1u) ^ 1u, P.prod_sleep, P.wait_hint);   // consumers are done with this stage's previous job
 #ifdef H2SHA_DEBUG_TIMING
       unsigned long long dbg_p0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p0));
 #endif
@@ -748,7 +764,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
 #ifdef H2SHA_DEBUG_TIMING
     unsigned long long dbg_w0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_w0));
 #endif
-    if (P.cons_sleep) mbar_wait_relaxed(&s_full[st], round & 1u, P.cons_sleep); else mbar_wait(&s_full[st], round & 1u);
+    if (P.cons_sleep) mbar_wait_relaxed(&s_full[st], round & 1u, P.cons_sleep, P.wait_hint); else mbar_wait(&s_full[st], round & 1u);
 #ifdef H2SHA_DEBUG_TIMING
     {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1167,6 +1183,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.n_block_parts = P.n_block_parts;
   D.cons_sleep = (uint32_t)tune_value("csleep", 0);
   D.prod_sleep = (uint32_t)tune_value("psleep", 256);
+  D.wait_hint = (uint32_t)tune_value("hint", 0);
   D.off_trace = D.blob_bytes;
   D.stage_off_slots = align_up(4 * std::max<uint32_t>(P.max_trace_words, TR_BLOCK_WORDS_WITH_K), 16);
   D.stage_off_desc = align_up(D.stage_off_slots + 8 * (P.max_slots + 1), 16);
