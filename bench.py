@@ -46,7 +46,7 @@ def measured_peak_gbs():
 class ClockSampler:
     """Samples clocks / throttle reasons with one `nvidia-smi -lms 100` process running across the timed region."""
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,clocks.mem"
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
@@ -68,17 +68,22 @@ class ClockSampler:
                 lines = out.strip().splitlines()
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, pw, mem = [], 0, set(), [], []
         for ln in lines:
             s = [x.strip() for x in ln.split(",")]
             try:
                 sm.append(float(s[0])); mx = max(mx, float(s[1]))
             except Exception:
                 continue
+            try:
+                pw.append(float(s[6])); mem.append(float(s[7]))
+            except Exception:
+                pass
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": float(np.median(pw)) if pw else None, "mem_mhz": float(np.median(mem)) if mem else None}
 
 
 def cpu_baseline(workload, sample_instances: int, n_threads: int, first: int = 0):
