@@ -734,7 +734,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_full[st]);
 #ifdef H2SHA_DEBUG_TIMING
-      if (lane == 0 && k < 3 && (blockIdx.x % 37) == 0) {
+      if (H2SHA_DEBUG_TIMING == 1 && lane == 0 && k < 3 && (blockIdx.x % 37) == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         printf("P cta %3d prod %d job# %u cls %u: wait_trace %llu | empty-wait done +%llu, job fetched +%llu, trace loaded +%llu, full +%llu ns\n", blockIdx.x, st, k, cls,
                dbg_t2 - dbg_t1, dbg_p0 - dbg_t2, dbg_p1 - dbg_t2, dbg_p2 - dbg_t2, t - dbg_t2);
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       dbg_wait += t - dbg_w0; dbg_nwait++;
-      if (lane == 0 && (blockIdx.x % 37) == 0 && (warp % 7) == 0 && (k < 6 || t - dbg_w0 > 3000))
+      if (H2SHA_DEBUG_TIMING == 1 && lane == 0 && (blockIdx.x % 37) == 0 && (warp % 7) == 0 && (k < 6 || t - dbg_w0 > 3000))
         printf("C cta %3d warp %2d k %3u: waited %llu ns at +%llu ns\n", blockIdx.x, warp, k, t - dbg_w0, t - dbg_t2);
     }
 #endif
@@ -910,7 +910,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     if (A.cks && jc.batch == 1) flush_checksums(A.cks, inst0, ck_g, ck_l, ck_s, lane);
   }
 #ifdef H2SHA_DEBUG_TIMING
-  if (lane == 0 && (blockIdx.x % 37) == 0 && (warp % 7) == 0) {
+  if (lane == 0 && (H2SHA_DEBUG_TIMING == 2 ? (warp == 0 || warp == NCONS - 1) : ((blockIdx.x % 37) == 0 && (warp % 7) == 0))) {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     printf("E cta %3d warp %2d: done at +%llu ns, waited %llu ns in %u waits\n", blockIdx.x, warp, t - dbg_t2, dbg_wait, dbg_nwait);
   }

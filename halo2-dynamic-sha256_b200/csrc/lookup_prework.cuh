@@ -401,6 +401,7 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
       CUDA_TRY(cudaMalloc(&e->d_range_tab, (size_t)n_vals * 32));
       k_range_table<<<(n_vals + 255) / 256, 256, 0, st>>>(e->d_range_tab, n_vals);
       CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(st));   // one-time: later calls may come on another stream
     }
     A.vals = e->d_range_tab;
   } else {
