@@ -356,6 +356,19 @@ def main():
                   expected_digests=[hashlib.sha256(msg0).digest()])
         assert (np.concatenate([lk[c] for c in range(lay.n_lookup_cols)])[: lay.n_lookup_cells] == stream_cells[sh.lookup_src]).all()
         mock_prover_instances = 1
+    # MockProver-style check of EVERY instance of the step's output on the device (gates, copy constraints, both lookups,
+    # digest bytes): h2sha_check_batch; all ranks, violations summed over the job
+    res_all = pkg.BatchResult(None, None, gate, lookup, spread)
+    t_chk = time.perf_counter()
+    viol = cfg.check_batch(res_all, d_digests.data_ptr())
+    t_chk = time.perf_counter() - t_chk
+    vt = torch.tensor([viol[k] for k in ("gates", "copies", "range_lookups", "spread_lookups", "digest_bytes")], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(vt)
+    device_check = {"instances": world * per_gpu, "violations": dict(zip(("gates", "copies", "range_lookups", "spread_lookups", "digest_bytes"), vt.tolist())),
+                    "seconds_rank0": t_chk, "note": "h2sha_check_batch: every gate, copy constraint, range / spread lookup and digest byte of every "
+                                                    "instance, on the device (first call includes building the shape plan)"}
+    assert int(vt.sum().item()) == 0, f"constraint violations in the generated witness: {device_check}"
     # the only collective: gather digests + checksums (64 B / instance) after the hot path
     sh = ge.load_package_module("sharding")
     _, _, job_ck = sh.gather_results(d_digests, d_cks, world)
@@ -488,6 +501,7 @@ def main():
                          "k_expand_burst_ms": burst_ms,
                          "achieved_burst": (alg_bytes / (burst_ms * 1e-3) / 1e9) if burst_ms else None},
             "lookup_prework": prework,
+            "device_mock_prover": device_check,
             "verified_instances_vs_oracle": verified, "mock_prover_instances": mock_prover_instances, "job_checksum": job_ck,
         }
         if not args.no_cpu:

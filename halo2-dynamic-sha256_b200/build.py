@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libh2sha_b200.so")
 SOURCES = ["engine.cu", "planner.cc"]
-HEADERS = ["h2sha_defs.h", "planner.h", "fr_host.h", "lookup_prework.cuh", os.path.join("..", "..", "include", "h2sha_b200.h")]
+HEADERS = ["h2sha_defs.h", "planner.h", "fr_host.h", "lookup_prework.cuh", "batch_check.cuh", os.path.join("..", "..", "include", "h2sha_b200.h")]
 
 
 def needs_build() -> bool:

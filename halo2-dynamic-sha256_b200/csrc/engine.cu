@@ -1042,6 +1042,11 @@ struct h2sha_engine {
   uint64_t lk_ws_bytes = 0;
   uint32_t* d_lk_tab = nullptr;   // compressed spread table in sorted order
   uint32_t* d_range_tab = nullptr;   // Montgomery form of the range table's values
+  // device-side batch check (batch_check.cuh)
+  uint32_t *d_chk_gate_on = nullptr, *d_chk_pairs = nullptr, *d_chk_out_bytes = nullptr;
+  uint64_t *d_chk_fixed = nullptr, *d_chk_bytes = nullptr;
+  unsigned long long* d_chk_viol = nullptr;
+  uint32_t n_chk_gate_on = 0, n_chk_pairs = 0;
 };
 
 namespace {
@@ -1253,6 +1258,7 @@ void h2sha_destroy(h2sha_engine_t* e) {
   cudaFree(e->d_msgs); cudaFree(e->d_offsets); cudaFree(e->d_lens); cudaFree(e->d_pre); cudaFree(e->d_btrace); cudaFree(e->d_dtrace);
   cudaFree(e->d_digests_out); cudaFree(e->d_cks);
   cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab); cudaFree(e->d_range_tab);
+  cudaFree(e->d_chk_gate_on); cudaFree(e->d_chk_pairs); cudaFree(e->d_chk_out_bytes); cudaFree(e->d_chk_fixed); cudaFree(e->d_chk_bytes); cudaFree(e->d_chk_viol);
   delete e;
 }
 
@@ -1528,3 +1534,4 @@ int h2sha_last_kernel_ms(h2sha_engine_t* e, float* trace_ms, float* expand_ms) {
 }  // extern "C"
 
 #include "lookup_prework.cuh"
+#include "batch_check.cuh"

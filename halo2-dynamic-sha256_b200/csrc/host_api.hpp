@@ -87,6 +87,12 @@ class Sha256DynamicConfig {
     check(h2sha_permute_lookup(engine_, n_instances, lookup_idx, mult_dev, usable_rows, theta_mont, permuted_input_dev, permuted_table_dev,
                                errors_dev, stream));
   }
+  // MockProver-style check of every instance of a batch on the device (lib.rs:525-526): violations[5] = gates, copies,
+  // range lookups, spread lookups, digest bytes
+  void check_batch(uint64_t n_instances, const void* gate, const void* lookup, const void* spread, const uint8_t* digests_dev,
+                   uint64_t violations[5], void* stream) {
+    check(h2sha_check_batch(engine_, n_instances, gate, lookup, spread, digests_dev, violations, stream));
+  }
   h2sha_engine_t* raw() const { return engine_; }
 
  private:

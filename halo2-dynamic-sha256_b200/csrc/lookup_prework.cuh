@@ -60,7 +60,8 @@ struct LookupGeom {
   uint64_t mult_words;   // u32 words per instance in the multiplicity buffer
 };
 
-// range lookup: one thread per assigned cell of the lookup advice column(s).  grid = (tiles, instances).
+// range lookup: one thread per assigned cell of the lookup advice column(s).  grid = (tiles, instances).  mult == null: only count
+// the cells that are not in the table (batch_check.cuh).
 __global__ void __launch_bounds__(256) k_range_mult(const LookupGeom G, const uint64_t* __restrict__ lookup, uint32_t* __restrict__ mult,
                                                    uint32_t* __restrict__ bad) {
   const uint64_t inst = blockIdx.y;
@@ -72,11 +73,11 @@ __global__ void __launch_bounds__(256) k_range_mult(const LookupGeom G, const ui
     uint64_t x[4], v[4];
     load_cell(base + ((uint64_t)col * G.lookup_col_rows + row) * 4, x);
     mont_reduce(x, v);
-    if ((v[1] | v[2] | v[3]) == 0 && v[0] < n_vals) atomicAdd(&m_inst[(uint64_t)col * n_vals + (uint32_t)v[0]], 1u);
+    if ((v[1] | v[2] | v[3]) == 0 && v[0] < n_vals) { if (mult) atomicAdd(&m_inst[(uint64_t)col * n_vals + (uint32_t)v[0]], 1u); }
     else if (bad) atomicAdd(bad, 1u);
   }
   // never-assigned rows of a column hold 0
-  if (blockIdx.x == 0 && threadIdx.x < G.n_lookup_cols) {
+  if (mult && blockIdx.x == 0 && threadIdx.x < G.n_lookup_cols) {
     const uint32_t col = threadIdx.x;
     const uint32_t first = col * G.max_rows;
     const uint32_t used = (G.n_lookup > first) ? min(G.max_rows, G.n_lookup - first) : 0u;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) k_spread_mult(const LookupGeom G, const u
   }
   if (n_bad && bad) atomicAdd(bad, n_bad);
   __syncthreads();
+  if (!mult) return;   // check-only mode (batch_check.cuh): cells outside the table have been counted
   for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x)
     if (s_hist[i]) atomicAdd(&m_inst[i], s_hist[i]);
   if (blockIdx.x == 0 && threadIdx.x < G.spread_cols) {

@@ -170,6 +170,19 @@ int h2sha_lookup_multiplicities(h2sha_engine_t* e, uint64_t n_instances, const v
 int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint32_t usable_rows,
                          const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream);
 
+/* MockProver-style check of a whole batch where it lies, in HBM -- what the reference's tests accept a witness by
+ * (`MockProver::run(..).verify() == Ok(())`, lib.rs:525-526), for every instance instead of one:
+ *   violations[0] gates           q * (a + b*c - d) = 0 on every enabled gate row (halo2-base FlexGate, Vertical)
+ *   violations[1] copies          the chip's copy constraints (cell <-> cell, cell <-> fixed constant), the lookup-column cells
+ *                                 against the cells range.finalize copies (lib.rs:469), the spread-column cells against their gate
+ *                                 cells (spread.rs:209-227)
+ *   violations[2] range lookups   lookup-column cells that are not < 2^lookup_bits
+ *   violations[3] spread lookups  (dense, spread) pairs that are no row of the spread table (spread.rs:53-62,165-194)
+ *   violations[4] digest bytes    output-byte cells (lib.rs:311-341) that differ from digests_dev [n_msgs][32] (skipped when NULL)
+ * `violations_host` gets the five counters; the call synchronises `stream`.  The static shape is built on first use. */
+int h2sha_check_batch(h2sha_engine_t* e, uint64_t n_instances, const void* gate, const void* lookup, const void* spread, const uint8_t* digests_dev,
+                      uint64_t* violations_host, void* stream);
+
 /* Zero-fill output buffers (or just the never-assigned ranges when only_unassigned != 0). */
 int h2sha_zero_outputs(h2sha_engine_t* e, uint64_t n_instances, void* gate, void* lookup, void* spread, int only_unassigned, void* stream);
 

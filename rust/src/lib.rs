@@ -166,6 +166,14 @@ impl Sha256DynamicConfig {
         })
     }
 
+    /// `MockProver::run(..).verify()` (lib.rs:525-526) for every instance of a batch, on the device: violation counts
+    /// [gates, copies, range lookups, spread lookups, digest bytes]; all zero = the witness the reference's tests accept.
+    pub fn check_batch(&mut self, n: usize, gate: u64, lookup: u64, spread: u64, digests_dev: u64, stream: *mut std::ffi::c_void) -> Result<[u64; 5], Error> {
+        let mut v = [0u64; 5];
+        check(unsafe { h2sha_check_batch(self.engine, n as u64, gate as *const _, lookup as *const _, spread as *const _, digests_dev as *const u8, v.as_mut_ptr(), stream) })?;
+        Ok(v)
+    }
+
     pub fn lookup_info(&self) -> Result<h2sha_lookup_info_t, Error> {
         let mut li: h2sha_lookup_info_t = unsafe { std::mem::zeroed() };
         check(unsafe { h2sha_get_lookup_info(self.engine, &mut li) })?;
