@@ -196,6 +196,10 @@ def run_full_workload(args):
         step()
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 0.4:     # short configurations: let the clock sampler see the load it is timed under
+        step(); stream.synchronize()
+    barrier()
     steps = max(1, min(args.steps, 3))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
