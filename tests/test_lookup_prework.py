@@ -232,3 +232,37 @@ def test_permuted_pairs_at_batch_size_hold_the_lookup_rules(pkg):
             for i in range(0, n, 16):
                 assert int(got[i].astype(object).sum()) & ((1 << 64) - 1) == want
     cfg.close()
+
+
+@pytest.mark.gpu
+def test_prework_writes_stay_inside_their_buffers(pkg):
+    """guard bands around the multiplicity and the permuted buffers stay untouched (compute-sanitizer is closed on this pool)"""
+    import torch
+    rng = np.random.default_rng(9)
+    usable = (1 << 16) + 777                                 # not a multiple of the 256-row tiles
+    n = 5
+    msgs = [[bytes(rng.integers(0, 256, size=int(rng.integers(0, 56)), dtype=np.uint8))] for _ in range(n)]
+    cfg = pkg.Sha256DynamicConfig.configure([64], device=0)
+    res = cfg.digest_batch(msgs)
+    info = cfg.lookup_info()
+    L = pkg.load_library()
+    dev = res.gate.device
+    G = 4096
+    words = n * info["mult_words_per_instance"]
+    mbuf = torch.full((words + 2 * G,), 0x5A5A5A5A, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(0).cuda_stream
+    assert L.h2sha_lookup_multiplicities(cfg._h, n, res.lookup.data_ptr(), res.spread.data_ptr(), usable, mbuf[G:].data_ptr(), None, st) == 0
+    cells = n * usable * 4
+    theta = O.int_to_mont(12345678901234567890 % P)
+    for l in range(info["n_range_lookups"] + info["n_spread_lookups"]):
+        a = torch.full((cells + 2 * G,), 0x6B6B6B6B6B6B6B6B, dtype=torch.int64, device=dev)
+        s = torch.full((cells + 2 * G,), 0x6B6B6B6B6B6B6B6B, dtype=torch.int64, device=dev)
+        th = theta.ctypes.data if l >= info["n_range_lookups"] else None
+        assert L.h2sha_permute_lookup(cfg._h, n, l, mbuf[G:].data_ptr(), usable, th, a[G:].data_ptr(), s[G:].data_ptr(), None, st) == 0
+        torch.cuda.synchronize()
+        for t in (a, s):
+            assert bool((t[:G] == 0x6B6B6B6B6B6B6B6B).all()) and bool((t[G + cells:] == 0x6B6B6B6B6B6B6B6B).all()), "guard band overwritten"
+            assert not bool((t[G:G + cells].view(-1, 4) == 0x6B6B6B6B6B6B6B6B).all(-1).any()), "a row was not written"
+    assert bool((mbuf[:G] == 0x5A5A5A5A).all()) and bool((mbuf[G + words:] == 0x5A5A5A5A).all()), "multiplicity guard band overwritten"
+    assert bool((mbuf[G:G + words].view(n, -1).to(torch.int64).sum(-1) == usable * (info["n_range_lookups"] + info["n_spread_lookups"])).all())
+    cfg.close()

@@ -260,7 +260,7 @@ int main(int argc, char** argv) {
   for (int g = 1; g < gpus; g++) same_ck = same_ck && S.job_checksum[g] == S.job_checksum[0];
   printf("{\"runner\": \"native C++ (no Python, no PyTorch)\", \"metric\": \"SHA-256 blocks/sec witness-gen (bit-exact cells)\", \"workload\": \"%s\", "
          "\"n_gpus\": %d, \"instances_per_gpu\": %llu, \"blocks_per_instance\": %u, \"steps\": %d, \"value\": %.1f, \"unit\": \"blocks/s\", \"ms_per_step\": %.4f, "
-         "\"e2e\": {\"value\": %.1f, \"ms_per_step\": %.4f}, \"cells_per_s\": %.4g, \"digest_mismatches\": %d, \"gathered_checksum\": %llu, "
+         "\"e2e\": {\"value\": %.1f, \"ms_per_step\": %.4f}, \"cells_per_s\": %.4g, \"digest_mismatches\": %d, \"constraint_violations_all_instances\": %llu, \"gathered_checksum\": %llu, "
          "\"all_ranks_hold_the_same_gather\": %s}\n",
          w->name, gpus, (unsigned long long)S.per_gpu, S.layout.n_blocks, steps, blocks / (res_ms * 1e-3), res_ms, blocks / (e2e_ms * 1e-3), e2e_ms,
          blocks / (res_ms * 1e-3) * (double)S.layout.cells_per_instance / S.layout.n_blocks, bad, (unsigned long long)viol, (unsigned long long)S.job_checksum[0],
