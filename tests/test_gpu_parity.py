@@ -339,3 +339,14 @@ def test_export_instance_matches_halo2_witness_layout(pkg):
     with pytest.raises(pkg.EngineError):
         cfg.export_instance(res, 0, 1024)   # fewer rows than a column has assigned
     cfg.close()
+
+
+def test_largest_supported_digest_64_blocks(pkg):
+    """maximum size: a 4096-byte digest (64 blocks, 35 gate columns, 2 lookup columns) is bit-exact; beyond the engine's
+    shared-memory budget (the per-digest job keeps 78 slots per block) the configuration is refused, never mis-generated"""
+    rng = np.random.default_rng(77)
+    kw = dict(max_variable_byte_sizes=(4096,))
+    _compare(pkg, kw, [[bytes(rng.integers(0, 256, int(n), dtype=np.uint8))] for n in (0, 4096 - 9, 2051)], threads=3)
+    with pytest.raises(pkg.EngineError) as ei:
+        pkg.Sha256DynamicConfig.configure([6144], device=0)
+    assert ei.value.code == pkg.H2SHA_EINVAL
