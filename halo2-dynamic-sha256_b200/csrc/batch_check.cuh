@@ -259,4 +259,40 @@ int h2sha_check_batch(h2sha_engine_t* e, uint64_t n_instances, const void* gate,
   return H2SHA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The only collective of the path: all-gather of digests and per-instance checksums (64 B per instance) over
+// the caller's NCCL communicator.  NCCL is resolved at run time (dlopen of libnccl.so.2), so libh2sha_b200.so itself links
+// nothing but the CUDA runtime; without NCCL the call fails with H2SHA_EINVAL and a message.
+// ---------------------------------------------------------------------------------------------------
+int h2sha_gather(void* nccl_comm, uint64_t n_instances_per_rank, uint32_t n_digests, const uint8_t* digests_dev, const uint64_t* checksums_dev,
+                 uint8_t* all_digests_dev, uint64_t* all_checksums_dev, void* stream) {
+  if (!nccl_comm) return set_err(H2SHA_EINVAL, "null NCCL communicator");
+  if ((!digests_dev) != (!all_digests_dev) || (!checksums_dev) != (!all_checksums_dev)) return set_err(H2SHA_EINVAL, "send and receive buffers must be given in pairs");
+  typedef int (*all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+  typedef int (*group_fn)(void);
+  typedef const char* (*err_fn)(int);
+  static void* lib = nullptr;
+  static all_gather_fn p_all_gather = nullptr;
+  static group_fn p_start = nullptr, p_end = nullptr;
+  static err_fn p_err = nullptr;
+  if (!lib) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return set_err(H2SHA_EINVAL, std::string("NCCL is not loadable: ") + dlerror());
+    p_all_gather = (all_gather_fn)dlsym(lib, "ncclAllGather");
+    p_start = (group_fn)dlsym(lib, "ncclGroupStart");
+    p_end = (group_fn)dlsym(lib, "ncclGroupEnd");
+    p_err = (err_fn)dlsym(lib, "ncclGetErrorString");
+    if (!p_all_gather || !p_start || !p_end) { lib = nullptr; return set_err(H2SHA_EINVAL, "libnccl lacks ncclAllGather / ncclGroupStart / ncclGroupEnd"); }
+  }
+  const int kUint8 = 1, kUint64 = 5;   // ncclDataType_t values (nccl.h), stable across NCCL 2.x
+  int rc = p_start();
+  if (!rc && digests_dev) rc = p_all_gather(digests_dev, all_digests_dev, (size_t)n_instances_per_rank * n_digests * 32, kUint8, nccl_comm, (cudaStream_t)stream);
+  if (!rc && checksums_dev) rc = p_all_gather(checksums_dev, all_checksums_dev, (size_t)n_instances_per_rank * 4, kUint64, nccl_comm, (cudaStream_t)stream);
+  const int rc_end = p_end();
+  if (!rc) rc = rc_end;
+  if (rc) return set_err(H2SHA_ECUDA, std::string("NCCL: ") + (p_err ? p_err(rc) : "error"));
+  return H2SHA_OK;
+}
+
 }  // extern "C"

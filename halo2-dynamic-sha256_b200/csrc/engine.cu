@@ -11,6 +11,7 @@
 //             from registers.
 // There is no CPU path: every entry point fails with H2SHA_ECUDA when no device is usable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>

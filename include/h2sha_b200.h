@@ -184,6 +184,13 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
 int h2sha_check_batch(h2sha_engine_t* e, uint64_t n_instances, const void* gate, const void* lookup, const void* spread, const uint8_t* digests_dev,
                       uint64_t* violations_host, void* stream);
 
+/* The only collective of the path: all-gather of digests [n_instances_per_rank * n_digests][32] and per-instance checksums
+ * [n_instances_per_rank][4] over the caller's communicator (`ncclComm_t`, one per GPU/rank; inside an ncclGroup when one
+ * thread drives several GPUs).  Receive buffers hold n_ranks x the send size, rank-major.  Either pair may be NULL.
+ * NCCL is loaded at run time (libnccl.so.2); the library itself links only the CUDA runtime. */
+int h2sha_gather(void* nccl_comm, uint64_t n_instances_per_rank, uint32_t n_digests, const uint8_t* digests_dev, const uint64_t* checksums_dev,
+                 uint8_t* all_digests_dev, uint64_t* all_checksums_dev, void* stream);
+
 /* Zero-fill output buffers (or just the never-assigned ranges when only_unassigned != 0). */
 int h2sha_zero_outputs(h2sha_engine_t* e, uint64_t n_instances, void* gate, void* lookup, void* spread, int only_unassigned, void* stream);
 

@@ -181,6 +181,13 @@ impl Sha256DynamicConfig {
     }
 }
 
+/// The path's only collective: all-gather of digests and per-instance checksums over the caller's `ncclComm_t`
+/// (one per GPU).  Receive buffers are rank-major and hold `n_ranks` times the send size.
+pub fn gather(comm: *mut std::ffi::c_void, n_per_rank: usize, n_digests: u32, digests: u64, checksums: u64, all_digests: u64, all_checksums: u64,
+              stream: *mut std::ffi::c_void) -> Result<(), Error> {
+    check(unsafe { h2sha_gather(comm, n_per_rank as u64, n_digests, digests as *const u8, checksums as *const u64, all_digests as *mut u8, all_checksums as *mut u64, stream) })
+}
+
 impl Drop for Sha256DynamicConfig {
     fn drop(&mut self) {
         unsafe { h2sha_destroy(self.engine) }

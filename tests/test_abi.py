@@ -49,3 +49,10 @@ def test_no_device_means_error_not_fallback(pkg):
         assert e.code == pkg.H2SHA_ECUDA
     else:
         raise AssertionError("engine creation must fail without a CUDA device")
+
+
+def test_gather_rejects_a_null_communicator(pkg):
+    """h2sha_gather resolves NCCL at run time; argument errors come back as codes, never as crashes"""
+    L = pkg.load_library()
+    assert L.h2sha_gather(None, 1, 1, None, None, None, None, None) == pkg.H2SHA_EINVAL
+    assert b"communicator" in L.h2sha_last_error()

@@ -168,10 +168,11 @@ static void worker(Shared* S, int g) {
   // the only collective: all-gather of digests and checksums (64 B per instance) over NCCL
   sha.digest_batch(r);
   if (S->n_gpus > 1) {
-    NK(ncclGroupStart());
-    NK(ncclAllGather(d_dig + (size_t)g * n * 32, d_dig, n * 32, ncclUint8, S->comms[g], st));
-    NK(ncclAllGather(d_ck + (size_t)g * n * 4, d_ck, n * 4, ncclUint64, S->comms[g], st));
-    NK(ncclGroupEnd());
+    // h2sha_gather: ncclAllGather of this rank's slice into the rank-major buffers, over the communicator created in main()
+    if (h2sha_gather(S->comms[g], n, 1, d_dig + (size_t)g * n * 32, d_ck + (size_t)g * n * 4, d_dig, d_ck, st) != H2SHA_OK) {
+      fprintf(stderr, "h2sha_gather: %s\n", h2sha_last_error());
+      exit(2);
+    }
   }
   CK(cudaStreamSynchronize(st));
   // MockProver-style pass over every instance of this GPU's shard (gates, copies, lookups, digest bytes), on the device
