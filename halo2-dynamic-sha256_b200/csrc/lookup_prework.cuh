@@ -384,7 +384,10 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   const LookupGeom G = lookup_geom(e, n_instances, usable_rows);
   const uint32_t n_vals = is_range ? (1u << G.lookup_bits) : (1u << G.limb_bits);
   // workspace: scans + totals of one chunk of instances (the chunks run one after the other on `stream` and share it)
-  const uint64_t chunk = std::min<uint64_t>(n_instances, (uint64_t)std::max(1, tune_value("lkchunk", 256)));
+  if (n_vals > (1u << 22)) return set_err(H2SHA_EINVAL, "lookup table too large for the permutation workspace (lookup_bits > 22)");
+  // instances per pass: at most `lkchunk` (default 256) and at most ~1 GB of scans
+  const uint64_t by_mem = std::max<uint64_t>(1, (1ull << 30) / (3ull * n_vals * 4));
+  const uint64_t chunk = std::min<uint64_t>(std::min<uint64_t>(n_instances, by_mem), (uint64_t)std::max(1, tune_value("lkchunk", 256)));
   const uint64_t need = chunk * (3ull * n_vals + 2) * 4;
   if (need > e->lk_ws_bytes) {
     cudaFree(e->d_lk_ws); e->d_lk_ws = nullptr; e->lk_ws_bytes = 0;
