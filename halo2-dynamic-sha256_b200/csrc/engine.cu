@@ -56,7 +56,7 @@ struct DevPlan {
   // byte offsets inside the blob (all 16-byte aligned)
   uint32_t off_fill, off_cells, off_chunks, off_items, off_table_lo, off_table_hi, off_resident, off_prog, off_groups, off_tasks, off_types, off_classes,
       off_raw, off_breaks, off_digests;
-  uint32_t n_breaks, n_digests, n_block_parts;
+  uint32_t n_breaks, n_digests, n_block_parts, n_classes;
   // dynamic shared memory layout after the blob
   uint32_t off_trace, off_scratch, off_misc, smem_bytes;
   uint32_t stage_bytes, stage_off_slots, stage_off_desc;   // per producer warp: trace | slots | StageDesc
@@ -642,8 +642,8 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
   // jobs: all block-job parts first, then per digest the batched prologue/epilogue jobs
   const uint64_t n_block_jobs = A.n_inst * P.blocks_per_inst * P.n_block_parts;
   uint64_t n_jobs = n_block_jobs;
-  for (uint32_t d = 0; d < P.n_digests; d++) {
-    const uint32_t batch = s_classes[s_digests[d].dp.job_class].batch;
+  for (uint32_t c = P.n_block_parts; c < P.n_classes; c++) {
+    const uint32_t batch = s_classes[c].batch;
     n_jobs += (A.n_inst + batch - 1) / batch;
   }
 
@@ -691,16 +691,17 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         tr_words = TR_BLOCK_WORDS;
         for (uint32_t i = lane; i < tr_words; i += 32) s_trace[i] = tr_src[(uint64_t)i * tr_stride];
       } else {
+        // digest-job classes follow the block-job parts, digest by digest (a long digest owns several consecutive classes)
         uint64_t kk = job - n_block_jobs;
-        uint32_t d = 0, batch = s_classes[s_digests[0].dp.job_class].batch;
+        cls = P.n_block_parts;
+        uint32_t batch = s_classes[cls].batch;
         for (;;) {
           const uint64_t nb = (A.n_inst + batch - 1) / batch;
           if (kk < nb) break;
-          kk -= nb; d++;
-          batch = s_classes[s_digests[d].dp.job_class].batch;
+          kk -= nb; cls++;
+          batch = s_classes[cls].batch;
         }
-        const DevDigest& dd = s_digests[d];
-        cls = dd.dp.job_class;
+        const DevDigest& dd = s_digests[s_classes[cls].digest];
         inst = kk * batch;
         n_valid = (uint32_t)min((uint64_t)batch, A.n_inst - inst);
         gate0 = 0; lk0 = 0; limb0 = 0;
@@ -1187,6 +1188,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.n_breaks = (uint32_t)P.breaks.size();
   D.n_digests = (uint32_t)P.digests.size();
   D.n_block_parts = P.n_block_parts;
+  D.n_classes = (uint32_t)P.classes.size();
   D.cons_sleep = (uint32_t)tune_value("csleep", 0);
   D.prod_sleep = (uint32_t)tune_value("psleep", 256);
   D.wait_hint = (uint32_t)tune_value("hint", 0);
@@ -1398,10 +1400,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
     ja.cks = cks_dev; ja.job_counter = e->d_counter;
     uint64_t n_jobs = b->n_instances * (uint64_t)e->blocks_per_inst * P.n_block_parts;
-    for (uint32_t d = 0; d < D; d++) {
-      const uint32_t batch = P.classes[P.digests[d].job_class].batch;
-      n_jobs += (b->n_instances + batch - 1) / batch;
-    }
+    for (size_t c = P.n_block_parts; c < P.classes.size(); c++) n_jobs += (b->n_instances + P.classes[c].batch - 1) / P.classes[c].batch;
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
     if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     {

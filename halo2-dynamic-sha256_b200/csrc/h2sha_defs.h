@@ -158,7 +158,7 @@ struct JobClass {
   uint32_t n_trace_words;        // u32 words of trace the job loads, per circuit instance
   uint32_t batch;                // circuit instances one job covers (1 for block jobs; digest jobs are batched so that the
                                  // lanes of the slot VM are filled and its latency is amortised)
-  uint32_t pad;
+  uint32_t digest;               // digest-job classes: the digest() call the class belongs to (0 for block-job parts)
 };
 
 // Trace layout of a block job (u32 words), written by the trace kernel:
@@ -174,7 +174,8 @@ struct DigestPlace {
   uint32_t gate_base, lk_base, limb_base;   // start of this digest's prologue
   uint32_t blk_gate_base, blk_lk_base, blk_limb_base;   // block 0 of this digest (after the one-time zero cell, if any)
   uint32_t blk_gate_stride, blk_lk_stride, blk_limb_stride;
-  uint32_t job_class;            // digest-job class index (block-job parts are classes 0 .. n_block_parts-1)
+  uint32_t job_class;            // first digest-job class of this digest (block-job parts are classes 0 .. n_block_parts-1; a digest
+                                 // whose slots exceed one stage is cut into several consecutive classes, JobClass::digest names the owner)
   uint32_t trace_words;          // digest-job trace words
 };
 

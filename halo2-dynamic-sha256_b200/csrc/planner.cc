@@ -1443,7 +1443,34 @@ class Builder {
       batch = std::min<uint32_t>(batch, H2SHA_MAX_JOB_BATCH);
       while (batch > 1 && (slots_one * batch > std::max(block_slots, slots_one) || slots_one * batch > 0xffff)) batch--;
       P.digests[ci - 1].job_class = (uint32_t)P.classes.size();
-      add_class(gs, P.digests[ci - 1].trace_words, batch);
+      // very long digests (> 64 blocks): the prologue/epilogue units need more slots than a shared-memory stage should hold;
+      // cut the job into parts of whole warp tasks (<= 32 unit instances of one group), like the block job
+      const uint32_t kSplitAbove = 5300, kPartSlots = 2800;
+      if (slots_one <= kSplitAbove) {
+        add_class(gs, P.digests[ci - 1].trace_words, batch);
+        P.classes.back().digest = (uint32_t)(ci - 1);
+      } else {
+        const uint32_t n_parts = (slots_one + kPartSlots - 1) / kPartSlots;
+        const uint32_t target = (slots_one + n_parts - 1) / n_parts;
+        std::vector<UnitGroup> part;
+        uint32_t part_slots = 0;
+        auto flush = [&]() {
+          if (part.empty()) return;
+          add_class(part, P.digests[ci - 1].trace_words, 1);
+          P.classes.back().digest = (uint32_t)(ci - 1);
+          part.clear(); part_slots = 0;
+        };
+        for (const GroupRec& g : class_recs_[ci].groups) {
+          const uint32_t per_unit = P.types[type_idx_.at(g.type)].n_slots | 1u;
+          for (uint32_t first = 0; first < g.count; first += 32) {
+            const uint32_t cnt = std::min(32u, g.count - first);
+            if (part_slots && part_slots + cnt * per_unit > target) flush();
+            part.push_back(make_group(g, first, cnt));
+            part_slots += cnt * per_unit;
+          }
+        }
+        flush();
+      }
     }
     // ---- layout ----
     auto up8 = [](uint32_t x) { return (x + 7u) & ~7u; };   // column strides are multiples of 8 cells (256 B)

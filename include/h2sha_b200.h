@@ -46,8 +46,8 @@ typedef struct h2sha_engine h2sha_engine_t;
  * (lib.rs:409-418: lookup_bits, k) and ContextParams.max_rows (lib.rs:354-358). */
 typedef struct {
   uint32_t n_digests;                       /* max_variable_byte_sizes.len()                                   */
-  const uint32_t* max_variable_byte_sizes;  /* each a positive multiple of 64 (lib.rs:57-59); this engine: <= 4096 (64 blocks) per digest on a device
-                                               (the per-digest job's slots must fit in shared memory), <= 7808 plan-only; larger -> H2SHA_EINVAL */
+  const uint32_t* max_variable_byte_sizes;  /* each a positive multiple of 64 (lib.rs:57-59); this engine: <= 7808 (122 blocks) per digest
+                                               (inverse table of is_zero); larger -> H2SHA_EINVAL */
   uint32_t max_rows;                        /* range.gate.max_rows = 2^k - minimum_rows; 0 -> 2^17 - 9          */
   uint32_t lookup_bits;                     /* RangeConfig lookup_bits; 0 -> 16                                 */
   uint32_t num_bits_lookup;                 /* SpreadConfig limb bits, divides 16, <= 8; 0 -> 8                 */

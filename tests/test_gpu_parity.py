@@ -341,12 +341,13 @@ def test_export_instance_matches_halo2_witness_layout(pkg):
     cfg.close()
 
 
-def test_largest_supported_digest_64_blocks(pkg):
-    """maximum size: a 4096-byte digest (64 blocks, 35 gate columns, 2 lookup columns) is bit-exact; beyond the engine's
-    shared-memory budget (the per-digest job keeps 78 slots per block) the configuration is refused, never mis-generated"""
+def test_long_digests_up_to_122_blocks(pkg):
+    """maximum sizes: a 4096-byte digest (64 blocks, 35 gate columns) runs as one digest job; a 7808-byte digest (122 blocks,
+    the largest the inverse table of is_zero covers) has its prologue/epilogue job cut into several job classes.  Beyond that
+    the configuration is refused, never mis-generated."""
     rng = np.random.default_rng(77)
-    kw = dict(max_variable_byte_sizes=(4096,))
-    _compare(pkg, kw, [[bytes(rng.integers(0, 256, int(n), dtype=np.uint8))] for n in (0, 4096 - 9, 2051)], threads=3)
+    _compare(pkg, dict(max_variable_byte_sizes=(4096,)), [[bytes(rng.integers(0, 256, int(n), dtype=np.uint8))] for n in (0, 4096 - 9, 2051)], threads=3)
+    _compare(pkg, dict(max_variable_byte_sizes=(7808, 128)), [[bytes(rng.integers(0, 256, int(n), dtype=np.uint8)), b"abc"] for n in (7808 - 9, 6000)], threads=2)
     with pytest.raises(pkg.EngineError) as ei:
-        pkg.Sha256DynamicConfig.configure([6144], device=0)
+        pkg.Sha256DynamicConfig.configure([7872], device=0)
     assert ei.value.code == pkg.H2SHA_EINVAL

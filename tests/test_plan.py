@@ -18,6 +18,7 @@ CONFIGS = [
     dict(max_variable_byte_sizes=(64,), limb_bits=2, spread_cols=3),
     dict(max_variable_byte_sizes=(128,), spread_cols=1),
     dict(max_variable_byte_sizes=(128,), is_input_range_check=False),
+    dict(max_variable_byte_sizes=(6144, 64)),      # a 96-block digest: its prologue/epilogue job is cut into several job classes
 ]
 
 
