@@ -174,6 +174,31 @@ __device__ __forceinline__ void fr_negate(uint64_t r[4]) {
 __device__ __forceinline__ void mont_from_u32(uint32_t v, uint32_t x[8]) {
   const uint32_t* R = reinterpret_cast<const uint32_t*>(c_fr.r1);
   const uint32_t* PM = reinterpret_cast<const uint32_t*>(c_fr.p);
+#ifndef H2SHA_MONT32_SPLIT_MUL
+  // P = v * R (9 limbs) and M = low 256 bits of q * p, each as one chain of 32x32+64 multiply-adds (IMAD.WIDE: both halves
+  // of a product from one instruction, the carry rides in the 64-bit accumulator)
+  uint32_t pl[9];
+  {
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      acc = (uint64_t)v * R[k] + (acc >> 32);
+      pl[k] = (uint32_t)acc;
+    }
+    pl[8] = (uint32_t)(acc >> 32);
+  }
+  const uint32_t ph = __funnelshift_r(pl[7], pl[8], 30);   // (P >> 254), < 2^32
+  const uint32_t q = (uint32_t)(((uint64_t)ph * c_fr.mu32) >> 31);
+  uint32_t m[8], r[8];
+  {
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      acc = (uint64_t)q * PM[k] + (acc >> 32);
+      m[k] = (uint32_t)acc;
+    }
+  }
+#else
   // P = v * R  (9 limbs): limb k = lo(v*R[k]) + hi(v*R[k-1]) + carry
   uint32_t lo[8], hi[8], pl[9];
 #pragma unroll
@@ -207,6 +232,7 @@ __device__ __forceinline__ void mont_from_u32(uint32_t v, uint32_t x[8]) {
       : "=r"(m[1]), "=r"(m[2]), "=r"(m[3]), "=r"(m[4]), "=r"(m[5]), "=r"(m[6]), "=r"(m[7])
       : "r"(ml[1]), "r"(ml[2]), "r"(ml[3]), "r"(ml[4]), "r"(ml[5]), "r"(ml[6]), "r"(ml[7]),
         "r"(mh[0]), "r"(mh[1]), "r"(mh[2]), "r"(mh[3]), "r"(mh[4]), "r"(mh[5]), "r"(mh[6]));
+#endif
   asm("sub.cc.u32 %0, %8, %16;\n\t"
       "subc.cc.u32 %1, %9, %17;\n\t"
       "subc.cc.u32 %2, %10, %18;\n\t"
