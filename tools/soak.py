@@ -22,10 +22,11 @@ rng = np.random.default_rng(seed)
 t0 = time.perf_counter()
 n_cfg = n_cells = 0
 while time.perf_counter() - t0 < budget:
-    sizes = tuple(int(64 * rng.integers(1, 7)) for _ in range(int(rng.integers(1, 4))))
+    max_blocks = int(os.environ.get("SOAK_MAX_BLOCKS", "6"))     # e.g. 122: long digests (split digest jobs), fewer configurations per minute
+    sizes = tuple(int(64 * rng.integers(1, max_blocks + 1)) for _ in range(int(rng.integers(1, 4))))
     kw = dict(max_variable_byte_sizes=sizes, lookup_bits=int(rng.choice([8, 10, 12, 14, 16, 17, 18])), limb_bits=int(rng.choice([1, 2, 4, 8])),
               spread_cols=int(rng.integers(1, 5)), is_input_range_check=bool(rng.integers(0, 2)), max_rows=int(rng.integers(2500, 150000)))
-    n_inst = int(rng.integers(1, 40))
+    n_inst = int(rng.integers(1, 40 if max_blocks <= 8 else 4))
     use_pre = bool(rng.integers(0, 3) == 0)
     instances, pre = [], []
     for _ in range(n_inst):
