@@ -410,6 +410,37 @@ def main():
     h2d = int(blob.size) + offs.nbytes + lens.nbytes
     d2h = n_msgs * 32 + per_gpu * 32
 
+    # ---- extra datapoint: the same end-to-end steps alternating TWO engine handles on two streams (own outputs, own pinned
+    # result buffers): the next step's H2D copy, trace kernel and launch overlap the tail of the previous expansion ----
+    e2e_two = None
+    if world == 1 and per_gpu * lay.bytes_per_instance <= (8 << 30):
+        try:
+            cfg2_ = pkg.Sha256DynamicConfig.configure(list(w.max_variable_byte_sizes), device=local_rank)
+            out2 = cfg2_.alloc_outputs(per_gpu, zero=True)
+            s2 = torch.cuda.Stream(dev)
+            hd2 = torch.zeros((n_msgs, 32), dtype=torch.uint8).pin_memory(); hc2 = torch.zeros((per_gpu, 4), dtype=torch.int64).pin_memory()
+            lanes = [(cfg, (gate, lookup, spread), stream, h_digests, h_cks), (cfg2_, out2, s2, hd2, hc2)]
+
+            def step_lane(k):
+                c_, o_, st_, hd_, hc_ = lanes[k & 1]
+                st_.synchronize()      # the step that used this lane before has delivered its digests + checksums
+                c_.digest_batch_raw(per_gpu, h_blob.data_ptr(), False, int(blob.size), offs, lens, None, gate_ptr=o_[0].data_ptr(), lookup_ptr=o_[1].data_ptr(),
+                                    spread_ptr=o_[2].data_ptr(), digests_host_ptr=hd_.data_ptr(), checksums_host_ptr=hc_.data_ptr(), stream=st_.cuda_stream)
+
+            for k in range(4):
+                step_lane(k)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                step_lane(k)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            assert (hd2.numpy() == h_digests.numpy()).all() and (hc2.numpy() == h_cks.numpy()).all()
+            e2e_two = {"value": args.steps * blocks_per_step / dt, "unit": UNIT, "note": "as e2e, two engine handles on two streams alternating (wall clock)"}
+            cfg2_.close(); del out2
+        except Exception as ex:
+            e2e_two = {"error": str(ex)}
+
     # ---- extra datapoint: the same end-to-end step when the consumer is a CPU prover, i.e. the whole witness is also copied
     # to pinned host memory every step (PCIe-bound; single GPU and small batches only) ----
     e2e_witness = None
@@ -608,6 +639,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "host message buffers -> h2sha_digest_batch -> digests+checksums on host; the witness stays in HBM for the prover"},
+            "e2e_two_handles": e2e_two,
             "e2e_witness_to_host": e2e_witness,
             "gpu_launches": 2 * args.steps,
             "kernels_ms": {"k_trace": trace_ms, "k_expand": expand_ms},
