@@ -311,7 +311,8 @@ static void range_check(ctx_t* c, av_t a, uint32_t range_bits) {
     /* decompose into k limbs of lookup_bits; inner product with limb_bases (first base == 1):
      * | l0 | l1 | 2^lb | l0 + l1 2^lb | l2 | 2^2lb | acc | ... */
     uint64_t canon[4]; fr_canon(a.v, canon);
-    qc_t cells[3 * 8 + 1]; int gate_offs[8]; int n = 0, ng = 0;
+    qc_t cells[3 * 8 + 1]; int gate_offs[8] = {0}; int n = 0, ng = 0;
+    memset(cells, 0, sizeof cells);
     fr_t acc = FR_ZERO; av_t o[3 * 8 + 1]; int limb_pos[9];
     if (k > 8) { fprintf(stderr, "oracle: range_check too wide\n"); abort(); }
     for (uint32_t i = 0; i < k; i++) {
