@@ -581,7 +581,12 @@ __device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint6
     }
   }
   uint32_t x[8];
+#ifdef H2SHA_EXP_SKIP_BARRETT   // experiment build only (wrong cells): what do the conversions cost in time and power?
+  x[0] = (uint32_t)v; x[1] = (uint32_t)(v >> 32); x[2] = x[0] ^ 0x9E3779B1u; x[3] = x[1] + 0x85EBCA77u; x[4] = x[0] + 1u; x[5] = x[1] ^ 5u; x[6] = x[0] * 3u; x[7] = neg;
+  if (false) {
+#else
   if (__any_sync(0xffffffffu, (v >> 32) != 0)) {
+#endif
     uint64_t r[4];
     mont_from_u64(v, r);
     if (neg) fr_negate(r);
@@ -596,6 +601,13 @@ __device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint6
   return hash8(lo, hi);
 }
 
+// the copy loops' read of a cell's value from the warp scratch; H2SHA_EXP_SKIP_SCRATCH_READ (experiment build, wrong cells) replaces it by
+// register values to measure what the shared-memory reads cost
+#ifdef H2SHA_EXP_SKIP_SCRATCH_READ
+#define H2SHA_SCRATCH_READ(src) const uint4 lo = make_uint4(src, src + 1u, src ^ 7u, src * 3u), hi = make_uint4(src + 9u, src, src ^ 1u, src + 5u);
+#else
+#define H2SHA_SCRATCH_READ(src) const uint4 lo = ws.lo[src], hi = ws.hi[src];
+#endif
 // one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
 __device__ __forceinline__ void store_cell2(uint32_t* p, const uint4& lo, const uint4& hi) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
@@ -867,7 +879,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
             if (i >= 0) {
               const CellEntry ce = cells[i];
               const uint32_t src = H2SHA_CE_SRC(ce);
-              const uint4 lo = ws.lo[src], hi = ws.hi[src];
+              H2SHA_SCRATCH_READ(src)
               if (gate_out) store_cell2(out0 + (uint64_t)H2SHA_CE_DST(ce) * 8, lo, hi);
             }
           }
@@ -875,7 +887,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           for (uint32_t i = lane; i < ch.gate_len; i += 32) {
             const CellEntry ce = cells[i];
             const uint32_t src = H2SHA_CE_SRC(ce);
-            const uint4 lo = ws.lo[src], hi = ws.hi[src];
+            H2SHA_SCRATCH_READ(src)
             const uint32_t gidx = g_lo + H2SHA_CE_DST(ce);
             const uint32_t pos = gidx + ((gidx >= next_brk) ? off1 : off0);
             if (gate_out) store_cell2(gate_out + (uint64_t)pos * 8, lo, hi);
@@ -903,7 +915,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           if (i < 0) continue;
           const CellEntry ce = s_cells[ch.lk_off + i];
           const uint32_t src = H2SHA_CE_SRC(ce);
-          const uint4 lo = ws.lo[src], hi = ws.hi[src];
+          H2SHA_SCRATCH_READ(src)
           const uint32_t li = l_lo + H2SHA_CE_DST(ce);
           const uint32_t pos = li + ((li >= wrap) ? loff1 : loff0);
           if (lk_out) store_cell2(lk_out + (uint64_t)pos * 8, lo, hi);
@@ -916,7 +928,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         for (uint32_t i = lane; i < ch.limb_len; i += 32) {
           const CellEntry ce = s_cells[ch.limb_off + i];
           const uint32_t src = H2SHA_CE_SRC(ce);
-          const uint4 lo = ws.lo[src], hi = ws.hi[src];
+          H2SHA_SCRATCH_READ(src)
           const uint32_t n = m_lo + (H2SHA_CE_DST(ce) >> 1), which = H2SHA_CE_DST(ce) & 1u;
           uint32_t row, col;
           if (P.spread_cols_shift >= 0) { row = n >> P.spread_cols_shift; col = n & (P.spread_cols - 1u); }

@@ -13,6 +13,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 pkg = ge.load_package()
+if os.environ.get("TUNE_LIB"):   # another build of the engine (experiment variants under tools/ab/)
+    pkg.LIB_PATH = os.path.abspath(os.environ["TUNE_LIB"])
 S = ge.load_package_module("synthetic")
 w = S.WORKLOADS["cfg2"]
 n = int(os.environ.get("TUNE_N", "1024"))
