@@ -56,3 +56,15 @@ def test_gather_rejects_a_null_communicator(pkg):
     L = pkg.load_library()
     assert L.h2sha_gather(None, 1, 1, None, None, None, None, None) == pkg.H2SHA_EINVAL
     assert b"communicator" in L.h2sha_last_error()
+
+
+def test_header_is_plain_c_and_usable_from_c(pkg):
+    """include/h2sha_b200.h compiles as C99 (what bindgen / cgo / JNI parse) and a C program can drive the plan queries"""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "abi_c_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "cpp", "abi_c_check.c"),
+                           "-L" + libdir, "-lh2sha_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("ok blocks=4 gate_cols=3"), out.stdout + out.stderr
