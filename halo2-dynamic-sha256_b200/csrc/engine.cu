@@ -9,6 +9,13 @@
 //             programs (lanes = unit instances), phase 2 expands the templates: raw value -> BN254 Fr
 //             Montgomery form -> one 256-bit store per cell (st.global.v8.b32, sm_100+), checksums folded
 //             from registers.
+// Included at the end of this translation unit (they use the engine struct and the field helpers above):
+//   lookup_prework.cuh  k_range_mult / k_spread_mult / k_permute_scan / k_permute_fill: lookup-argument pre-work
+//   batch_check.cuh     k_check_gates / k_check_pairs / k_check_digest_bytes: MockProver-style pass over a whole batch; h2sha_gather
+// Build-time switches (never set for the product): H2SHA_DEBUG_TIMING (1 | 2: %globaltimer prints of the producer / consumer
+// hand-over), H2SHA_EXP_SKIP_BARRETT / H2SHA_EXP_SKIP_SCRATCH_READ (experiment builds that produce WRONG cells, used once to measure
+// what the conversions and the scratch reads cost: profiles/r1_power_probe.txt), H2SHA_MONT32_SPLIT_MUL (the earlier mul.lo / mul.hi
+// form of mont_from_u32).
 // There is no CPU path: every entry point fails with H2SHA_ECUDA when no device is usable.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
