@@ -99,3 +99,19 @@ def test_every_instance_of_config2_and_a_dynamic_batch_passes(pkg):
         v = cfg.check_batch(res, dig.data_ptr())
         assert sum(v.values()) == 0, (name, v)
         cfg.close()
+
+
+@pytest.mark.gpu
+def test_check_follows_widened_column_strides(pkg):
+    """the checker's cell positions come from the engine's own strides (2^k-row columns instead of tight ones)"""
+    import torch
+    rng = np.random.default_rng(12)
+    cfg = pkg.Sha256DynamicConfig.configure([128], device=0, gate_col_rows=1 << 17, lookup_col_rows=1 << 17, spread_rows=1 << 17)
+    msgs = [[bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8))] for n in (3, 119, 64)]
+    res = cfg.digest_batch(msgs)
+    assert res.gate.shape[2] == 1 << 17
+    dig = torch.from_numpy(res.digests).cuda()
+    assert sum(cfg.check_batch(res, dig.data_ptr()).values()) == 0
+    res.gate[1, 0, 1000] = _mont(99).cuda()
+    assert sum(cfg.check_batch(res, dig.data_ptr()).values()) >= 1
+    cfg.close()
