@@ -266,3 +266,21 @@ def test_prework_writes_stay_inside_their_buffers(pkg):
     assert bool((mbuf[:G] == 0x5A5A5A5A).all()) and bool((mbuf[G + words:] == 0x5A5A5A5A).all()), "multiplicity guard band overwritten"
     assert bool((mbuf[G:G + words].view(n, -1).to(torch.int64).sum(-1) == usable * (info["n_range_lookups"] + info["n_spread_lookups"])).all())
     cfg.close()
+
+
+@pytest.mark.gpu
+def test_multiplicities_follow_widened_column_strides(pkg):
+    """2^k-row column strides (the layout a prover holds): the histogram reads the assigned prefix of each column, wherever the stride puts it"""
+    rng = np.random.default_rng(10)
+    usable = (1 << 17) - 6
+    msgs = [[bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8))] for n in (0, 55, 119)]
+    tight = pkg.Sha256DynamicConfig.configure([128], device=0)
+    wide = pkg.Sha256DynamicConfig.configure([128], device=0, gate_col_rows=1 << 17, lookup_col_rows=1 << 17, spread_rows=1 << 17)
+    m_t, bad_t = tight.lookup_multiplicities(tight.digest_batch(msgs), usable)
+    res_w = wide.digest_batch(msgs)
+    m_w, bad_w = wide.lookup_multiplicities(res_w, usable)
+    assert bad_t == 0 and bad_w == 0 and bool((m_t == m_w).all())
+    a_t, s_t = tight.permute_lookup(m_t, 0, usable)
+    a_w, s_w = wide.permute_lookup(m_w, 0, usable)
+    assert bool((a_t == a_w).all()) and bool((s_t == s_w).all())
+    tight.close(); wide.close()
