@@ -612,6 +612,10 @@ __device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint6
 // register values to measure what the shared-memory reads cost
 #ifdef H2SHA_EXP_SKIP_SCRATCH_READ
 #define H2SHA_SCRATCH_READ(src) const uint4 lo = make_uint4(src, src + 1u, src ^ 7u, src * 3u), hi = make_uint4(src + 9u, src, src ^ 1u, src + 5u);
+#elif defined(H2SHA_EXP_SKIP_RESIDENT_READ)   // only the reads of the resident constants (scratch slots [0, n_resident)) are skipped
+#define H2SHA_SCRATCH_READ(src)                                                                  \
+  uint4 lo = make_uint4(src, src + 1u, src ^ 7u, src * 3u), hi = make_uint4(src + 9u, src, src ^ 1u, src + 5u); \
+  if (src >= P.n_resident) { lo = ws.lo[src]; hi = ws.hi[src]; }
 #else
 #define H2SHA_SCRATCH_READ(src) const uint4 lo = ws.lo[src], hi = ws.hi[src];
 #endif
