@@ -268,23 +268,34 @@ int h2sha_gather(void* nccl_comm, uint64_t n_instances_per_rank, uint32_t n_dige
                  uint8_t* all_digests_dev, uint64_t* all_checksums_dev, void* stream) {
   if (!nccl_comm) return set_err(H2SHA_EINVAL, "null NCCL communicator");
   if ((!digests_dev) != (!all_digests_dev) || (!checksums_dev) != (!all_checksums_dev)) return set_err(H2SHA_EINVAL, "send and receive buffers must be given in pairs");
-  typedef int (*all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
-  typedef int (*group_fn)(void);
-  typedef const char* (*err_fn)(int);
-  static void* lib = nullptr;
-  static all_gather_fn p_all_gather = nullptr;
-  static group_fn p_start = nullptr, p_end = nullptr;
-  static err_fn p_err = nullptr;
-  if (!lib) {
+  // resolved once per process; the static-local initialiser is thread-safe (C++11) and publishes the pointers only after all
+  // of them are known, so one host thread per GPU may make its first call at the same moment (tools/native_runner.cc)
+  struct Nccl {
+    typedef int (*all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+    typedef int (*group_fn)(void);
+    typedef const char* (*err_fn)(int);
+    void* lib = nullptr;
+    all_gather_fn all_gather = nullptr;
+    group_fn start = nullptr, end = nullptr;
+    err_fn err = nullptr;
+    std::string why;
+  };
+  static const Nccl nccl = [] {
+    Nccl n;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
-    if (!lib) return set_err(H2SHA_EINVAL, std::string("NCCL is not loadable: ") + dlerror());
-    p_all_gather = (all_gather_fn)dlsym(lib, "ncclAllGather");
-    p_start = (group_fn)dlsym(lib, "ncclGroupStart");
-    p_end = (group_fn)dlsym(lib, "ncclGroupEnd");
-    p_err = (err_fn)dlsym(lib, "ncclGetErrorString");
-    if (!p_all_gather || !p_start || !p_end) { lib = nullptr; return set_err(H2SHA_EINVAL, "libnccl lacks ncclAllGather / ncclGroupStart / ncclGroupEnd"); }
-  }
+    for (const char* nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
+    if (!n.lib) { const char* de = dlerror(); n.why = std::string("NCCL is not loadable: ") + (de ? de : "dlopen failed"); return n; }
+    n.all_gather = (Nccl::all_gather_fn)dlsym(n.lib, "ncclAllGather");
+    n.start = (Nccl::group_fn)dlsym(n.lib, "ncclGroupStart");
+    n.end = (Nccl::group_fn)dlsym(n.lib, "ncclGroupEnd");
+    n.err = (Nccl::err_fn)dlsym(n.lib, "ncclGetErrorString");
+    if (!n.all_gather || !n.start || !n.end) { n.why = "libnccl lacks ncclAllGather / ncclGroupStart / ncclGroupEnd"; n.all_gather = nullptr; }
+    return n;
+  }();
+  if (!nccl.all_gather) return set_err(H2SHA_EINVAL, nccl.why);
+  const auto p_all_gather = nccl.all_gather;
+  const auto p_start = nccl.start, p_end = nccl.end;
+  const auto p_err = nccl.err;
   const int kUint8 = 1, kUint64 = 5;   // ncclDataType_t values (nccl.h), stable across NCCL 2.x
   int rc = p_start();
   if (!rc && digests_dev) rc = p_all_gather(digests_dev, all_digests_dev, (size_t)n_instances_per_rank * n_digests * 32, kUint8, nccl_comm, (cudaStream_t)stream);

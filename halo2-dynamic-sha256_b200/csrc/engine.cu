@@ -12,10 +12,8 @@
 // Included at the end of this translation unit (they use the engine struct and the field helpers above):
 //   lookup_prework.cuh  k_range_mult / k_spread_mult / k_permute_scan / k_permute_fill: lookup-argument pre-work
 //   batch_check.cuh     k_check_gates / k_check_pairs / k_check_digest_bytes: MockProver-style pass over a whole batch; h2sha_gather
-// Build-time switches (never set for the product): H2SHA_DEBUG_TIMING (1 | 2: %globaltimer prints of the producer / consumer
-// hand-over), H2SHA_EXP_SKIP_BARRETT / H2SHA_EXP_SKIP_SCRATCH_READ (experiment builds that produce WRONG cells, used once to measure
-// what the conversions and the scratch reads cost: profiles/r1_power_probe.txt), H2SHA_MONT32_SPLIT_MUL (the earlier mul.lo / mul.hi
-// form of mont_from_u32).
+// Build-time switch (never set for the product): H2SHA_DEBUG_TIMING (1 | 2: %globaltimer prints of the producer / consumer
+// hand-over).  The wrong-cell experiment builds of round 1 (profiles/r1_power_probe.txt) are gone from this file.
 // There is no CPU path: every entry point fails with H2SHA_ECUDA when no device is usable.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -181,7 +179,6 @@ __device__ __forceinline__ void fr_negate(uint64_t r[4]) {
 __device__ __forceinline__ void mont_from_u32(uint32_t v, uint32_t x[8]) {
   const uint32_t* R = reinterpret_cast<const uint32_t*>(c_fr.r1);
   const uint32_t* PM = reinterpret_cast<const uint32_t*>(c_fr.p);
-#ifndef H2SHA_MONT32_SPLIT_MUL
   // P = v * R (9 limbs) and M = low 256 bits of q * p, each as one chain of 32x32+64 multiply-adds (IMAD.WIDE: both halves
   // of a product from one instruction, the carry rides in the 64-bit accumulator)
   uint32_t pl[9];
@@ -205,41 +202,6 @@ __device__ __forceinline__ void mont_from_u32(uint32_t v, uint32_t x[8]) {
       m[k] = (uint32_t)acc;
     }
   }
-#else
-  // P = v * R  (9 limbs): limb k = lo(v*R[k]) + hi(v*R[k-1]) + carry
-  uint32_t lo[8], hi[8], pl[9];
-#pragma unroll
-  for (int k = 0; k < 8; k++) { lo[k] = v * R[k]; hi[k] = __umulhi(v, R[k]); }
-  pl[0] = lo[0];
-  asm("add.cc.u32 %0, %8, %15;\n\t"
-      "addc.cc.u32 %1, %9, %16;\n\t"
-      "addc.cc.u32 %2, %10, %17;\n\t"
-      "addc.cc.u32 %3, %11, %18;\n\t"
-      "addc.cc.u32 %4, %12, %19;\n\t"
-      "addc.cc.u32 %5, %13, %20;\n\t"
-      "addc.cc.u32 %6, %14, %21;\n\t"
-      "addc.u32 %7, %22, 0;"
-      : "=r"(pl[1]), "=r"(pl[2]), "=r"(pl[3]), "=r"(pl[4]), "=r"(pl[5]), "=r"(pl[6]), "=r"(pl[7]), "=r"(pl[8])
-      : "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]),
-        "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]));
-  const uint32_t ph = __funnelshift_r(pl[7], pl[8], 30);   // (P >> 254), < 2^32
-  const uint32_t q = (uint32_t)(((uint64_t)ph * c_fr.mu32) >> 31);
-  // M = low 256 bits of q * p, then r = P - M
-  uint32_t ml[8], mh[8], m[8], r[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) { ml[k] = q * PM[k]; mh[k] = __umulhi(q, PM[k]); }
-  m[0] = ml[0];
-  asm("add.cc.u32 %0, %7, %14;\n\t"
-      "addc.cc.u32 %1, %8, %15;\n\t"
-      "addc.cc.u32 %2, %9, %16;\n\t"
-      "addc.cc.u32 %3, %10, %17;\n\t"
-      "addc.cc.u32 %4, %11, %18;\n\t"
-      "addc.cc.u32 %5, %12, %19;\n\t"
-      "addc.u32 %6, %13, %20;"
-      : "=r"(m[1]), "=r"(m[2]), "=r"(m[3]), "=r"(m[4]), "=r"(m[5]), "=r"(m[6]), "=r"(m[7])
-      : "r"(ml[1]), "r"(ml[2]), "r"(ml[3]), "r"(ml[4]), "r"(ml[5]), "r"(ml[6]), "r"(ml[7]),
-        "r"(mh[0]), "r"(mh[1]), "r"(mh[2]), "r"(mh[3]), "r"(mh[4]), "r"(mh[5]), "r"(mh[6]));
-#endif
   asm("sub.cc.u32 %0, %8, %16;\n\t"
       "subc.cc.u32 %1, %9, %17;\n\t"
       "subc.cc.u32 %2, %10, %18;\n\t"
@@ -588,12 +550,7 @@ __device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint6
     }
   }
   uint32_t x[8];
-#ifdef H2SHA_EXP_SKIP_BARRETT   // experiment build only (wrong cells): what do the conversions cost in time and power?
-  x[0] = (uint32_t)v; x[1] = (uint32_t)(v >> 32); x[2] = x[0] ^ 0x9E3779B1u; x[3] = x[1] + 0x85EBCA77u; x[4] = x[0] + 1u; x[5] = x[1] ^ 5u; x[6] = x[0] * 3u; x[7] = neg;
-  if (false) {
-#else
   if (__any_sync(0xffffffffu, (v >> 32) != 0)) {
-#endif
     uint64_t r[4];
     mont_from_u64(v, r);
     if (neg) fr_negate(r);
@@ -608,17 +565,8 @@ __device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint6
   return hash8(lo, hi);
 }
 
-// the copy loops' read of a cell's value from the warp scratch; H2SHA_EXP_SKIP_SCRATCH_READ (experiment build, wrong cells) replaces it by
-// register values to measure what the shared-memory reads cost
-#ifdef H2SHA_EXP_SKIP_SCRATCH_READ
-#define H2SHA_SCRATCH_READ(src) const uint4 lo = make_uint4(src, src + 1u, src ^ 7u, src * 3u), hi = make_uint4(src + 9u, src, src ^ 1u, src + 5u);
-#elif defined(H2SHA_EXP_SKIP_RESIDENT_READ)   // only the reads of the resident constants (scratch slots [0, n_resident)) are skipped
-#define H2SHA_SCRATCH_READ(src)                                                                  \
-  uint4 lo = make_uint4(src, src + 1u, src ^ 7u, src * 3u), hi = make_uint4(src + 9u, src, src ^ 1u, src + 5u); \
-  if (src >= P.n_resident) { lo = ws.lo[src]; hi = ws.hi[src]; }
-#else
+// the copy loops' read of a cell's value from the warp scratch
 #define H2SHA_SCRATCH_READ(src) const uint4 lo = ws.lo[src], hi = ws.hi[src];
-#endif
 // one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
 __device__ __forceinline__ void store_cell2(uint32_t* p, const uint4& lo, const uint4& hi) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
@@ -1036,10 +984,8 @@ struct ExpandVariant {
 template <int NC, int NP>
 ExpandVariant make_variant() { return ExpandVariant{NC, NP, (const void*)k_expand<NC, NP>}; }
 const ExpandVariant* expand_variants(int* n) {
-  static const ExpandVariant v[] = {make_variant<16, 4>(), make_variant<12, 4>(), make_variant<20, 4>(), make_variant<24, 4>(), make_variant<16, 2>(),
-                                    make_variant<20, 2>(), make_variant<24, 6>(), make_variant<8, 2>(), make_variant<8, 4>(), make_variant<18, 6>(),
-                                    make_variant<16, 6>(), make_variant<20, 5>(), make_variant<20, 6>(), make_variant<16, 8>(), make_variant<21, 4>(),
-                                    make_variant<22, 4>(), make_variant<18, 4>(), make_variant<22, 3>(), make_variant<21, 3>(), make_variant<16, 3>()};
+  // the tuned default and the fallback chain for plans that need more shared memory (fewer consumer warps = less scratch)
+  static const ExpandVariant v[] = {make_variant<20, 4>(), make_variant<16, 4>(), make_variant<12, 4>(), make_variant<8, 4>(), make_variant<8, 2>()};
   *n = (int)(sizeof v / sizeof v[0]);
   return v;
 }
@@ -1058,6 +1004,35 @@ uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 // ---------------------------------------------------------------------------------------------------
 // host engine
 // ---------------------------------------------------------------------------------------------------
+// One of the two device-side input / trace workspaces.  Calls alternate between them, so the H2D copy and the trace kernel
+// of batch i+1 (on the engine's copy stream) can run while the expansion kernel of batch i still reads its traces.
+struct InputSet {
+  uint64_t cap_msgs = 0, cap_inst = 0, cap_in = 0;
+  uint8_t* d_in = nullptr;            // offsets [n] u64 | lens [n] u32 | precomputed_lens [n] u32 | message bytes: one H2D copy
+  uint32_t* d_btrace = nullptr;
+  uint32_t* d_dtrace = nullptr;
+  uint8_t* d_digests_out = nullptr;
+  unsigned long long* d_cks = nullptr;
+  unsigned long long* d_counter = nullptr;
+  cudaEvent_t trace_done = nullptr;   // recorded on the copy stream after k_trace
+  cudaEvent_t expand_done = nullptr;  // recorded on the caller's stream after the last reader of this set (k_expand, D2H copies)
+  bool used = false;
+  cudaStream_t last_stream = nullptr;
+  // inputs resident in this set (reuse_inputs)
+  uint64_t n_instances = 0;
+  bool has_pre = false;
+  const uint8_t* msgs = nullptr;
+};
+// One slot of the pinned staging ring: the caller's host arrays are copied here before the call returns, so the call itself
+// never waits for the device.
+struct HostSlot {
+  uint8_t* p = nullptr;
+  uint64_t cap = 0;
+  cudaEvent_t copied = nullptr;       // recorded after the H2D copy out of this slot
+  bool used = false;
+};
+enum { H2SHA_N_SETS = 2, H2SHA_N_SLOTS = 4 };
+
 struct h2sha_engine {
   Plan plan;
   int device = 0;
@@ -1067,26 +1042,19 @@ struct h2sha_engine {
   DevDigest* d_digests = nullptr;
   uint32_t* d_zero_ranges[3] = {nullptr, nullptr, nullptr};
   uint32_t n_zero_ranges[3] = {0, 0, 0};
-  // workspace (grown on demand)
-  uint64_t ws_msgs = 0, ws_bytes = 0;
-  uint8_t* d_msgs = nullptr;
-  uint64_t* d_offsets = nullptr;
-  uint32_t* d_lens = nullptr;
-  uint32_t* d_pre = nullptr;
-  uint32_t* d_btrace = nullptr;
-  uint32_t* d_dtrace = nullptr;
-  unsigned long long* d_counter = nullptr;
-  uint8_t* d_digests_out = nullptr;
-  unsigned long long* d_cks = nullptr;
+  // input / trace workspaces (grown on demand), pinned staging ring, copy stream
+  InputSet sets[H2SHA_N_SETS];
+  HostSlot slots[H2SHA_N_SLOTS];
+  cudaStream_t copy_stream = nullptr;
+  uint64_t seq = 0;                  // calls that uploaded inputs
+  int resident_set = -1;             // set holding the inputs of the last such call
+  bool overlap_enabled = true;       // H2SHA_TUNE overlap=0: everything on the caller's stream
   uint32_t blocks_per_inst = 0, dtrace_words_per_inst = 0;
   int last_launches = 0;
   int expand_ctas = 0;
   ExpandVariant variant{};
-  uint64_t resident_instances = 0;   // instances whose inputs are in the workspace (reuse_inputs)
-  bool resident_has_pre = false;
-  const uint8_t* resident_msgs = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // trace start/stop, expand start/stop
-  bool timed = false;
+  bool timed = false, timed_expand = false;
   // lookup-argument pre-work (lookup_prework.cuh)
   bool lookup_consts_ready = false;
   uint32_t* d_lk_ws = nullptr;    // scans of the permutation kernels
@@ -1102,35 +1070,63 @@ struct h2sha_engine {
 
 namespace {
 
-int ensure_workspace(h2sha_engine* e, uint64_t n_inst, uint64_t msg_bytes) {
-  uint64_t n_msgs = n_inst * e->plan.digests.size();
-  if (n_msgs > e->ws_msgs) {
-    cudaFree(e->d_offsets); cudaFree(e->d_lens); cudaFree(e->d_pre); cudaFree(e->d_btrace); cudaFree(e->d_dtrace);
-    cudaFree(e->d_digests_out); cudaFree(e->d_cks);
-    e->ws_msgs = 0;
-    CUDA_TRY(cudaMalloc(&e->d_offsets, n_msgs * 8));
-    CUDA_TRY(cudaMalloc(&e->d_lens, n_msgs * 4));
-    CUDA_TRY(cudaMalloc(&e->d_pre, n_msgs * 4));
-    CUDA_TRY(cudaMalloc(&e->d_btrace, n_inst * e->blocks_per_inst * (uint64_t)TR_BLOCK_WORDS * 4));
-    CUDA_TRY(cudaMalloc(&e->d_dtrace, n_inst * (uint64_t)e->dtrace_words_per_inst * 4));
-    CUDA_TRY(cudaMalloc(&e->d_digests_out, n_msgs * 32));
-    CUDA_TRY(cudaMalloc(&e->d_cks, n_inst * 32));
-    e->ws_msgs = n_msgs;
+// frees *p (nulling it, so that a later failure leaves no dangling pointer behind) and allocates `bytes`
+template <class T>
+int dev_realloc(T*& p, size_t bytes) {
+  if (p) { cudaFree(p); p = nullptr; }
+  CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16));
+  return H2SHA_OK;
+}
+
+int ensure_set(h2sha_engine* e, InputSet* S, uint64_t n_inst, uint64_t in_bytes) {
+  const uint64_t n_msgs = n_inst * e->plan.digests.size();
+  int rc;
+  if (n_msgs > S->cap_msgs || n_inst > S->cap_inst) {
+    S->cap_msgs = 0; S->cap_inst = 0;
+    if ((rc = dev_realloc(S->d_btrace, n_inst * e->blocks_per_inst * (uint64_t)TR_BLOCK_WORDS * 4))) return rc;
+    if ((rc = dev_realloc(S->d_dtrace, n_inst * (uint64_t)e->dtrace_words_per_inst * 4))) return rc;
+    if ((rc = dev_realloc(S->d_digests_out, n_msgs * 32))) return rc;
+    if ((rc = dev_realloc(S->d_cks, n_inst * 32))) return rc;
+    S->cap_msgs = n_msgs; S->cap_inst = n_inst;
   }
-  if (msg_bytes + 16 > e->ws_bytes) {
-    cudaFree(e->d_msgs);
-    e->ws_bytes = 0;
-    CUDA_TRY(cudaMalloc(&e->d_msgs, msg_bytes + 16));
-    e->ws_bytes = msg_bytes + 16;
+  if (in_bytes + 16 > S->cap_in) {
+    S->cap_in = 0;
+    if ((rc = dev_realloc(S->d_in, in_bytes + 16))) return rc;
+    S->cap_in = in_bytes + 16;
   }
   return H2SHA_OK;
 }
+
+int ensure_slot(HostSlot* H, uint64_t bytes) {
+  if (H->used) { CUDA_TRY(cudaEventSynchronize(H->copied)); H->used = false; }   // the copy that last read this slot (3 calls ago) is long done
+  if (bytes > H->cap) {
+    if (H->p) { cudaFreeHost(H->p); H->p = nullptr; }
+    H->cap = 0;
+    const uint64_t cap = std::max<uint64_t>(bytes + bytes / 4, 1 << 16);
+    CUDA_TRY(cudaHostAlloc((void**)&H->p, cap, cudaHostAllocDefault));
+    H->cap = cap;
+  }
+  return H2SHA_OK;
+}
+
+struct EngineGuard {   // error paths of h2sha_create: releases whatever has been allocated so far
+  h2sha_engine* e;
+  ~EngineGuard() { if (e) h2sha_destroy(e); }
+};
 
 }  // namespace
 
 extern "C" {
 
 const char* h2sha_last_error(void) { return g_err.c_str(); }
+
+#ifndef H2SHA_BUILD_ID_STR
+#define H2SHA_BUILD_ID_STR "unstamped"
+#endif
+const char* h2sha_build_id(void) {
+  static const char id[] = "H2SHA_BUILD_ID=" H2SHA_BUILD_ID_STR;   // build.py finds this marker in the file
+  return id + 15;
+}
 
 int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   if (!cfg || !out) return set_err(H2SHA_EINVAL, "null argument");
@@ -1164,14 +1160,15 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   pc.resident_consts = (uint32_t)tune_value("res", (int)pc.resident_consts);
   pc.digest_batch = (uint32_t)tune_value("dbatch", (int)pc.digest_batch);
   h2sha_engine* e = new h2sha_engine();
-  std::string err;
-  if (!build_plan(pc, &e->plan, &err)) { delete e; return set_err(H2SHA_EINVAL, err); }
-  Plan& P = e->plan;
-  if (cfg->gate_col_rows) { if (cfg->gate_col_rows < P.gate_col_rows) { delete e; return set_err(H2SHA_EINVAL, "gate_col_rows too small"); } P.gate_col_rows = cfg->gate_col_rows; }
-  if (cfg->lookup_col_rows) { if (cfg->lookup_col_rows < P.lookup_col_rows) { delete e; return set_err(H2SHA_EINVAL, "lookup_col_rows too small"); } P.lookup_col_rows = cfg->lookup_col_rows; }
-  if (cfg->spread_rows) { if (cfg->spread_rows < P.spread_rows) { delete e; return set_err(H2SHA_EINVAL, "spread_rows too small"); } P.spread_rows = cfg->spread_rows; }
-  if ((P.gate_col_rows | P.lookup_col_rows | P.spread_rows) & 1u) { delete e; return set_err(H2SHA_EINVAL, "column row strides must be even"); }
   e->device = cfg->device;
+  EngineGuard guard{e};   // every early return below destroys the half-built engine (h2sha_destroy frees what exists)
+  std::string err;
+  if (!build_plan(pc, &e->plan, &err)) return set_err(H2SHA_EINVAL, err);
+  Plan& P = e->plan;
+  if (cfg->gate_col_rows) { if (cfg->gate_col_rows < P.gate_col_rows) return set_err(H2SHA_EINVAL, "gate_col_rows too small"); P.gate_col_rows = cfg->gate_col_rows; }
+  if (cfg->lookup_col_rows) { if (cfg->lookup_col_rows < P.lookup_col_rows) return set_err(H2SHA_EINVAL, "lookup_col_rows too small"); P.lookup_col_rows = cfg->lookup_col_rows; }
+  if (cfg->spread_rows) { if (cfg->spread_rows < P.spread_rows) return set_err(H2SHA_EINVAL, "spread_rows too small"); P.spread_rows = cfg->spread_rows; }
+  if ((P.gate_col_rows | P.lookup_col_rows | P.spread_rows) & 1u) return set_err(H2SHA_EINVAL, "column row strides must be even");
   e->n_sms = prop.multiProcessorCount;
   {
     uint32_t bp0 = 0, dw0 = 0;
@@ -1179,7 +1176,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
     e->blocks_per_inst = bp0; e->dtrace_words_per_inst = dw0;
   }
   compute_zero_ranges(&P);  // against the final (possibly widened) strides
-  if (plan_only) { *out = e; return H2SHA_OK; }
+  if (plan_only) { guard.e = nullptr; *out = e; return H2SHA_OK; }
 
   // ---- field constants ----
   FrConsts fc;
@@ -1265,7 +1262,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
         ok = D.smem_bytes <= 227 * 1024;
       }
     }
-    if (!ok) { delete e; return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory (or H2SHA_TUNE names no launch variant)"); }
+    if (!ok) return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory (or H2SHA_TUNE names no launch variant)");
   }
   D.max_rows = pc.max_rows; D.spread_cols = pc.spread_cols;
   D.spread_cols_shift = -1;
@@ -1281,7 +1278,6 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.blob = e->d_blob;
   CUDA_TRY(cudaMalloc(&e->d_digests, dds.size() * sizeof(DevDigest)));
   CUDA_TRY(cudaMemcpy(e->d_digests, dds.data(), dds.size() * sizeof(DevDigest), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&e->d_counter, 8));
   for (int b = 0; b < 3; b++) {
     std::vector<uint32_t> rr;
     for (auto& z : P.zero_ranges) if ((int)z.buf == b) { rr.push_back(z.pos); rr.push_back(z.count); }
@@ -1292,11 +1288,23 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
     }
   }
   const int expand_threads = (e->variant.ncons + e->variant.nprod) * 32;
-  CUDA_TRY(cudaFuncSetAttribute(e->variant.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
+  // the attribute belongs to the kernel function, not to this engine: always raise it to the 227 KB cap, so that engines of
+  // different configurations that share a launch variant never lower each other's limit
+  CUDA_TRY(cudaFuncSetAttribute(e->variant.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e->variant.fn, expand_threads, D.smem_bytes));
-  if (occ < 1) { delete e; return set_err(H2SHA_ECUDA, "expand kernel does not fit on an SM"); }
+  if (occ < 1) return set_err(H2SHA_ECUDA, "expand kernel does not fit on an SM");
   e->expand_ctas = occ * e->n_sms;
+  // ---- copy stream, events, job counters ----
+  e->overlap_enabled = tune_value("overlap", 1) != 0;
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (InputSet& S : e->sets) {
+    CUDA_TRY(cudaEventCreateWithFlags(&S.trace_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&S.expand_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&S.d_counter, 8));
+  }
+  for (HostSlot& H : e->slots) CUDA_TRY(cudaEventCreateWithFlags(&H.copied, cudaEventDisableTiming));
+  guard.e = nullptr;
   *out = e;
   return H2SHA_OK;
 }
@@ -1305,10 +1313,20 @@ void h2sha_destroy(h2sha_engine_t* e) {
   if (!e) return;
   if (e->device < 0) { delete e; return; }
   cudaSetDevice(e->device);
-  cudaFree(e->d_blob); cudaFree(e->d_digests); cudaFree(e->d_counter);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  cudaFree(e->d_blob); cudaFree(e->d_digests);
   for (int b = 0; b < 3; b++) cudaFree(e->d_zero_ranges[b]);
-  cudaFree(e->d_msgs); cudaFree(e->d_offsets); cudaFree(e->d_lens); cudaFree(e->d_pre); cudaFree(e->d_btrace); cudaFree(e->d_dtrace);
-  cudaFree(e->d_digests_out); cudaFree(e->d_cks);
+  for (InputSet& S : e->sets) {
+    if (S.expand_done && S.used) cudaEventSynchronize(S.expand_done);   // no kernel of ours may still read the workspace
+    cudaFree(S.d_in); cudaFree(S.d_btrace); cudaFree(S.d_dtrace); cudaFree(S.d_digests_out); cudaFree(S.d_cks); cudaFree(S.d_counter);
+    if (S.trace_done) cudaEventDestroy(S.trace_done);
+    if (S.expand_done) cudaEventDestroy(S.expand_done);
+  }
+  for (HostSlot& H : e->slots) {
+    if (H.copied) cudaEventDestroy(H.copied);
+    if (H.p) cudaFreeHost(H.p);
+  }
+  for (int i = 0; i < 4; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab); cudaFree(e->d_range_tab);
   cudaFree(e->d_chk_gate_on); cudaFree(e->d_chk_pairs); cudaFree(e->d_chk_out_bytes); cudaFree(e->d_chk_fixed); cudaFree(e->d_chk_bytes); cudaFree(e->d_chk_viol);
   delete e;
@@ -1384,97 +1402,117 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   const Plan& P = e->plan;
   const uint32_t D = (uint32_t)P.digests.size();
   const uint64_t n_msgs = b->n_instances * D;
-  if (n_msgs * (uint64_t)1 > 0xffffffffull) return set_err(H2SHA_EINVAL, "batch too large");
+  if (n_msgs > 0xffffffffull) return set_err(H2SHA_EINVAL, "batch too large");
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)b->stream;
-  const uint8_t* d_msgs = nullptr;
-  bool has_pre = false;
-  cudaEvent_t copied = nullptr;
+  const bool timed = b->time_kernels != 0;
+  InputSet* S = nullptr;
+  cudaStream_t ts = st;        // stream of the H2D copy and the trace kernel
+  bool overlap = false;
   if (b->reuse_inputs) {
-    if (b->n_instances > e->resident_instances) return set_err(H2SHA_EINVAL, "reuse_inputs: no resident inputs for that many instances");
-    d_msgs = e->resident_msgs; has_pre = e->resident_has_pre;
+    if (e->resident_set < 0 || b->n_instances > e->sets[e->resident_set].n_instances)
+      return set_err(H2SHA_EINVAL, "reuse_inputs: no resident inputs for that many instances");
+    S = &e->sets[e->resident_set];
+    if (S->used && S->last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, S->expand_done, 0));   // ordered after the call that left them there
   } else {
     if (!b->msgs && b->msgs_bytes) return set_err(H2SHA_EINVAL, "msgs is null");
     if (!b->offsets || !b->lens) return set_err(H2SHA_EINVAL, "offsets / lens are null");
-    // the reference's panics (lib.rs:89-90) become error returns
+    // every host array is staged in the engine's pinned ring before the call returns: the call only enqueues
+    const uint64_t hdr = n_msgs * 16;
+    const uint64_t in_bytes = hdr + (b->msgs_on_device ? 0 : b->msgs_bytes);
+    HostSlot* H = &e->slots[e->seq % H2SHA_N_SLOTS];
+    int rc = ensure_slot(H, in_bytes);
+    if (rc) return rc;
+    uint64_t* h_off = reinterpret_cast<uint64_t*>(H->p);
+    uint32_t* h_len = reinterpret_cast<uint32_t*>(H->p + n_msgs * 8);
+    uint32_t* h_pre = reinterpret_cast<uint32_t*>(H->p + n_msgs * 12);
+    // the reference's panics (lib.rs:89-90) become error returns; lengths are checked in 64 bits (no wrap on the device)
     for (uint64_t m = 0; m < n_msgs; m++) {
       const uint32_t maxb = P.digests[m % D].max_bytes;
-      const uint64_t len = b->lens[m], pre = b->precomputed_lens ? b->precomputed_lens[m] : 0;
+      const uint64_t len = b->lens[m], pre = b->precomputed_lens ? b->precomputed_lens[m] : 0, off = b->offsets[m];
       if (pre % 64 != 0) return set_err(H2SHA_EPANIC, "precomputed_input_len is not a multiple of 64 (lib.rs:89), message " + std::to_string(m));
       const uint64_t padded = (len + 9 + 63) / 64 * 64;
       if (padded < pre || padded - pre > maxb)
         return set_err(H2SHA_EPANIC, "padded input does not fit max_variable_byte_size (lib.rs:90), message " + std::to_string(m));
-      if (b->offsets[m] + len > b->msgs_bytes) return set_err(H2SHA_EINVAL, "message " + std::to_string(m) + " exceeds msgs_bytes");
+      if (off > b->msgs_bytes || len > b->msgs_bytes - off) return set_err(H2SHA_EINVAL, "message " + std::to_string(m) + " exceeds msgs_bytes");
+      h_off[m] = off; h_len[m] = (uint32_t)len; h_pre[m] = (uint32_t)pre;
     }
-    e->resident_instances = 0;
-    int rc = ensure_workspace(e, b->n_instances, b->msgs_on_device ? 0 : b->msgs_bytes);
-    if (rc) return rc;
-    d_msgs = b->msgs;
-    if (!b->msgs_on_device) {
-      if (b->msgs_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_msgs, b->msgs, b->msgs_bytes, cudaMemcpyHostToDevice, st));
-      d_msgs = e->d_msgs;
-    }
-    CUDA_TRY(cudaMemcpyAsync(e->d_offsets, b->offsets, n_msgs * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->d_lens, b->lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
-    if (b->precomputed_lens) CUDA_TRY(cudaMemcpyAsync(e->d_pre, b->precomputed_lens, n_msgs * 4, cudaMemcpyHostToDevice, st));
-    has_pre = b->precomputed_lens != nullptr;
-    // host arrays must be consumed before we return: wait for the copies (not for the kernels) below
-    CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventRecord(copied, st));
-    e->resident_instances = b->n_instances; e->resident_has_pre = has_pre; e->resident_msgs = d_msgs;
+    if (!b->msgs_on_device && b->msgs_bytes) memcpy(H->p + hdr, b->msgs, b->msgs_bytes);
+    S = &e->sets[e->seq % H2SHA_N_SETS];
+    e->resident_set = -1;
+    if ((rc = ensure_set(e, S, b->n_instances, in_bytes))) return rc;
+    // host in, host out (no caller-owned device result buffer the trace kernel would have to touch early): the copy and
+    // the trace kernel go to the engine's copy stream and overlap the previous batch's expansion on the caller's stream
+    overlap = e->overlap_enabled && !b->msgs_on_device && !b->digests_dev && !b->checksums_dev && !timed;
+    ts = overlap ? e->copy_stream : st;
+    if (S->used && !(ts == st && S->last_stream == st)) CUDA_TRY(cudaStreamWaitEvent(ts, S->expand_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(S->d_in, H->p, in_bytes, cudaMemcpyHostToDevice, ts));
+    CUDA_TRY(cudaEventRecord(H->copied, ts));
+    H->used = true;
+    S->n_instances = b->n_instances; S->has_pre = b->precomputed_lens != nullptr;
+    S->msgs = b->msgs_on_device ? b->msgs : S->d_in + hdr;
+    e->resident_set = (int)(e->seq % H2SHA_N_SETS);
+    e->seq++;
   }
-  e->timed = b->time_kernels != 0;
-  if (e->timed && !e->ev[0])
+  e->timed = timed; e->timed_expand = false;
+  if (timed && !e->ev[0])
     for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&e->ev[i]));
 
-  uint8_t* dig_dev = b->digests_dev ? b->digests_dev : (b->digests_host ? e->d_digests_out : nullptr);
-  unsigned long long* cks_dev = b->checksums_dev ? (unsigned long long*)b->checksums_dev : (b->checksums_host ? e->d_cks : nullptr);
+  // caller-owned device result buffers are written on the caller's stream only; the overlap path (never taken when they
+  // are given) uses the set's own buffers
+  uint8_t* dig_dev = b->digests_dev ? b->digests_dev : (b->digests_host ? S->d_digests_out : nullptr);
+  unsigned long long* cks_dev = b->checksums_dev ? (unsigned long long*)b->checksums_dev : (b->checksums_host ? S->d_cks : nullptr);
   int launches = 0;
+  const uint64_t cap_n = S->n_instances * D;   // the header layout follows the uploaded batch, not this (possibly smaller) one
   TraceArgs ta{};
-  ta.n_msgs = n_msgs; ta.n_digests = D; ta.msgs = d_msgs; ta.offsets = e->d_offsets; ta.lens = e->d_lens;
-  ta.pre_lens = has_pre ? e->d_pre : nullptr;
-  ta.btrace = e->d_btrace; ta.dtrace = e->d_dtrace; ta.digests = dig_dev; ta.digests_plan = e->d_digests;
+  ta.n_msgs = n_msgs; ta.n_digests = D; ta.msgs = S->msgs;
+  ta.offsets = reinterpret_cast<const uint64_t*>(S->d_in);
+  ta.lens = reinterpret_cast<const uint32_t*>(S->d_in + cap_n * 8);
+  ta.pre_lens = S->has_pre ? reinterpret_cast<const uint32_t*>(S->d_in + cap_n * 12) : nullptr;
+  ta.btrace = S->d_btrace; ta.dtrace = S->d_dtrace; ta.digests = dig_dev; ta.digests_plan = e->d_digests;
   ta.blocks_per_inst = e->blocks_per_inst; ta.dtrace_words_per_inst = e->dtrace_words_per_inst;
   const bool expand = b->gate || b->lookup || b->spread || cks_dev;
-  ta.job_counter = expand ? e->d_counter : nullptr;
+  ta.job_counter = expand ? S->d_counter : nullptr;
   ta.cks = cks_dev;
-  if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[0], st));
-  k_trace<<<(unsigned)((n_msgs + 63) / 64), 64, 0, st>>>(ta);
+  if (timed) CUDA_TRY(cudaEventRecord(e->ev[0], ts));
+  k_trace<<<(unsigned)((n_msgs + 63) / 64), 64, 0, ts>>>(ta);
   launches++;
   CUDA_TRY(cudaGetLastError());
-  if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[1], st));
+  if (timed) CUDA_TRY(cudaEventRecord(e->ev[1], ts));
+  if (overlap) {
+    CUDA_TRY(cudaEventRecord(S->trace_done, ts));
+    CUDA_TRY(cudaStreamWaitEvent(st, S->trace_done, 0));
+  }
   if (expand) {
     JobArgs ja{};
-    ja.n_inst = b->n_instances; ja.btrace = e->d_btrace; ja.dtrace = e->d_dtrace;
+    ja.n_inst = b->n_instances; ja.btrace = S->d_btrace; ja.dtrace = S->d_dtrace;
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
-    ja.cks = cks_dev; ja.job_counter = e->d_counter;
+    ja.cks = cks_dev; ja.job_counter = S->d_counter;
     uint64_t n_jobs = b->n_instances * (uint64_t)e->blocks_per_inst * P.n_block_parts;
     for (size_t c = P.n_block_parts; c < P.classes.size(); c++) n_jobs += (b->n_instances + P.classes[c].batch - 1) / P.classes[c].batch;
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
-    if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
+    if (timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     {
-      // programmatic dependent launch: prologue (plan -> shared memory) overlaps the trace kernel
+      // programmatic dependent launch: prologue (plan -> shared memory) overlaps the trace kernel when both are on one stream
       void* args[2] = {(void*)&e->dplan, (void*)&ja};
       cudaLaunchConfig_t lc{};
       lc.gridDim = dim3(grid); lc.blockDim = dim3((e->variant.ncons + e->variant.nprod) * 32);
       lc.dynamicSmemBytes = e->dplan.smem_bytes; lc.stream = st;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = e->timed ? 0 : 1;   // plain serialisation when kernels are timed individually
+      at[0].val.programmaticStreamSerializationAllowed = (timed || overlap) ? 0 : 1;   // plain serialisation when kernels are timed individually
       lc.attrs = at; lc.numAttrs = 1;
       CUDA_TRY(cudaLaunchKernelExC(&lc, e->variant.fn, args));
     }
     launches++;
     CUDA_TRY(cudaGetLastError());
-    if (e->timed) CUDA_TRY(cudaEventRecord(e->ev[3], st));
+    if (timed) { CUDA_TRY(cudaEventRecord(e->ev[3], st)); e->timed_expand = true; }
   }
   if (b->digests_host) CUDA_TRY(cudaMemcpyAsync(b->digests_host, dig_dev, n_msgs * 32, cudaMemcpyDeviceToHost, st));
   if (b->checksums_host) CUDA_TRY(cudaMemcpyAsync(b->checksums_host, cks_dev, b->n_instances * 32, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(S->expand_done, st));
+  S->used = true; S->last_stream = st;
   e->last_launches = launches;
-  if (copied) {
-    CUDA_TRY(cudaEventSynchronize(copied));
-    cudaEventDestroy(copied);
-  }
   return H2SHA_OK;
 }
 
@@ -1522,9 +1560,11 @@ int h2sha_zero_outputs(h2sha_engine_t* e, uint64_t n_inst, void* gate, void* loo
     if (!bufs[b]) continue;
     if (!only_unassigned) { CUDA_TRY(cudaMemsetAsync(bufs[b], 0, n_inst * cells[b] * 32, st)); continue; }
     if (e->n_zero_ranges[b] == 0) continue;
-    dim3 grid(64, (unsigned)n_inst);
-    k_zero_ranges<<<grid, 256, 0, st>>>((uint4*)bufs[b], cells[b], n_inst, e->d_zero_ranges[b], e->n_zero_ranges[b]);
-    CUDA_TRY(cudaGetLastError());
+    for (uint64_t i0 = 0; i0 < n_inst; i0 += 65535) {   // grid.y = instance: at most 65535 per launch
+      const uint64_t ni = std::min<uint64_t>(65535, n_inst - i0);
+      k_zero_ranges<<<dim3(64, (unsigned)ni), 256, 0, st>>>((uint4*)bufs[b] + i0 * cells[b] * 2, cells[b], ni, e->d_zero_ranges[b], e->n_zero_ranges[b]);
+      CUDA_TRY(cudaGetLastError());
+    }
   }
   return H2SHA_OK;
 }
@@ -1574,9 +1614,12 @@ int h2sha_last_launch_count(const h2sha_engine_t* e) { return e ? e->last_launch
 
 int h2sha_last_kernel_ms(h2sha_engine_t* e, float* trace_ms, float* expand_ms) {
   if (!e || !e->timed || !e->ev[0]) return set_err(H2SHA_EINVAL, "last batch was not run with time_kernels");
-  CUDA_TRY(cudaEventSynchronize(e->ev[3]));
+  CUDA_TRY(cudaEventSynchronize(e->timed_expand ? e->ev[3] : e->ev[1]));
   if (trace_ms) CUDA_TRY(cudaEventElapsedTime(trace_ms, e->ev[0], e->ev[1]));
-  if (expand_ms) CUDA_TRY(cudaEventElapsedTime(expand_ms, e->ev[2], e->ev[3]));
+  if (expand_ms) {
+    *expand_ms = 0.f;   // a digests-only batch has no expansion step
+    if (e->timed_expand) CUDA_TRY(cudaEventElapsedTime(expand_ms, e->ev[2], e->ev[3]));
+  }
   return H2SHA_OK;
 }
 

@@ -77,6 +77,8 @@ typedef struct {
 int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out);
 void h2sha_destroy(h2sha_engine_t* e);
 const char* h2sha_last_error(void);
+/* Stamp of the sources and flags this library was built from (halo2-dynamic-sha256_b200/build.py compares it with the tree). */
+const char* h2sha_build_id(void);
 int h2sha_get_layout(const h2sha_engine_t* e, h2sha_layout_t* out);
 
 /* Gate-stream index -> (column,row): column c holds stream indices [breaks[c], breaks[c+1]).  `breaks` gets n_gate_cols entries. */
