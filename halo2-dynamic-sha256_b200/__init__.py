@@ -28,7 +28,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
-    "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_build_id", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_shape", "h2sha_get_lookup_tables",
+    "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_build_id", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_digest_ranges", "h2sha_get_shape", "h2sha_get_lookup_tables",
     "h2sha_digest_batch", "h2sha_export_instance", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_check_batch", "h2sha_gather", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_debug_int_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
@@ -47,7 +47,8 @@ class _Config(C.Structure):
     _fields_ = [("n_digests", C.c_uint32), ("max_variable_byte_sizes", C.POINTER(C.c_uint32)), ("max_rows", C.c_uint32),
                 ("lookup_bits", C.c_uint32), ("num_bits_lookup", C.c_uint32), ("num_advice_columns", C.c_uint32),
                 ("is_input_range_check", C.c_uint32), ("gate_col_rows", C.c_uint32), ("lookup_col_rows", C.c_uint32),
-                ("spread_rows", C.c_uint32), ("device", C.c_int32), ("build_shape", C.c_uint32), ("block_parts", C.c_uint32)]
+                ("spread_rows", C.c_uint32), ("device", C.c_int32), ("build_shape", C.c_uint32), ("block_parts", C.c_uint32),
+                ("num_lookup_advice", C.c_uint32)]
 
 
 class _Layout(C.Structure):
@@ -62,7 +63,8 @@ class _Batch(C.Structure):
     _fields_ = [("n_instances", C.c_uint64), ("msgs", C.c_void_p), ("msgs_on_device", C.c_int32), ("msgs_bytes", C.c_uint64),
                 ("offsets", C.c_void_p), ("lens", C.c_void_p), ("precomputed_lens", C.c_void_p), ("gate", C.c_void_p), ("lookup", C.c_void_p),
                 ("spread", C.c_void_p), ("digests_dev", C.c_void_p), ("checksums_dev", C.c_void_p), ("digests_host", C.c_void_p),
-                ("checksums_host", C.c_void_p), ("stream", C.c_void_p), ("reuse_inputs", C.c_int32), ("time_kernels", C.c_int32)]
+                ("checksums_host", C.c_void_p), ("stream", C.c_void_p), ("reuse_inputs", C.c_int32), ("time_kernels", C.c_int32),
+                ("only_digest", C.c_uint32)]
 
 
 class _LookupInfo(C.Structure):
@@ -88,6 +90,7 @@ def load_library():
     L.h2sha_get_layout.argtypes = [C.c_void_p, C.POINTER(_Layout)]
     L.h2sha_get_breaks.argtypes = [C.c_void_p, C.c_void_p]
     L.h2sha_get_handles.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.h2sha_get_digest_ranges.argtypes = [C.c_void_p, C.c_void_p]
     L.h2sha_get_shape.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.h2sha_get_lookup_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
@@ -194,11 +197,12 @@ class Sha256DynamicConfig:
     def configure(cls, max_variable_byte_sizes: Sequence[int], *, max_rows: int = (1 << 17) - 9, lookup_bits: int = 16,
                   num_bits_lookup: int = 8, num_advice_columns: int = 2, is_input_range_check: bool = True, device: int = 0,
                   build_shape: bool = False, gate_col_rows: int = 0, lookup_col_rows: int = 0, spread_rows: int = 0,
-                  block_parts: int = 0) -> "Sha256DynamicConfig":
+                  block_parts: int = 0, num_lookup_advice: int = 0) -> "Sha256DynamicConfig":
         L = load_library()
         sizes = (C.c_uint32 * len(max_variable_byte_sizes))(*max_variable_byte_sizes)
         cfg = _Config(len(max_variable_byte_sizes), sizes, max_rows, lookup_bits, num_bits_lookup, num_advice_columns,
-                      1 if is_input_range_check else 0, gate_col_rows, lookup_col_rows, spread_rows, device, 1 if build_shape else 0, block_parts)
+                      1 if is_input_range_check else 0, gate_col_rows, lookup_col_rows, spread_rows, device, 1 if build_shape else 0, block_parts,
+                      num_lookup_advice)
         h = C.c_void_p()
         _check(L.h2sha_create(C.byref(cfg), C.byref(h)))
         return cls(h, max_variable_byte_sizes, device)
@@ -239,6 +243,12 @@ class Sha256DynamicConfig:
         ob = np.zeros(32, dtype=np.uint32)
         _check(load_library().h2sha_get_handles(self._h, d, C.byref(il), ib.ctypes.data_as(C.c_void_p), ob.ctypes.data_as(C.c_void_p)))
         return AssignedHashResult(int(il.value), ib, ob)
+
+    def digest_ranges(self) -> np.ndarray:
+        """[n_digests, 6]: gate_lo, gate_hi, lookup_lo, lookup_hi, limb_lo, limb_hi of the stream ranges each digest() call owns."""
+        r = np.zeros((len(self.max_variable_byte_sizes), 6), dtype=np.uint32)
+        _check(load_library().h2sha_get_digest_ranges(self._h, r.ctypes.data_as(C.c_void_p)))
+        return r
 
     def shape(self) -> Shape:
         lay = self.layout
@@ -286,7 +296,7 @@ class Sha256DynamicConfig:
     def digest_batch_raw(self, n_instances: int, msgs_ptr: int, msgs_on_device: bool, msgs_bytes: int, offsets: np.ndarray, lens: np.ndarray,
                          precomputed_lens: Optional[np.ndarray], *, gate_ptr: int = 0, lookup_ptr: int = 0, spread_ptr: int = 0,
                          digests_dev_ptr: int = 0, checksums_dev_ptr: int = 0, digests_host_ptr: int = 0, checksums_host_ptr: int = 0,
-                         stream: int = 0, reuse_inputs: bool = False, time_kernels: bool = False):
+                         stream: int = 0, reuse_inputs: bool = False, time_kernels: bool = False, only_digest: int = 0):
         """Thin wrapper over h2sha_digest_batch (all pointers are integers)."""
         if reuse_inputs:
             off_p = len_p = pre_p = None
@@ -296,7 +306,7 @@ class Sha256DynamicConfig:
             pre_p = precomputed_lens.ctypes.data if precomputed_lens is not None else None
         b = _Batch(n_instances, msgs_ptr or None, 1 if msgs_on_device else 0, msgs_bytes, off_p, len_p, pre_p, gate_ptr or None,
                    lookup_ptr or None, spread_ptr or None, digests_dev_ptr or None, checksums_dev_ptr or None, digests_host_ptr or None,
-                   checksums_host_ptr or None, stream or None, 1 if reuse_inputs else 0, 1 if time_kernels else 0)
+                   checksums_host_ptr or None, stream or None, 1 if reuse_inputs else 0, 1 if time_kernels else 0, only_digest)
         _check(load_library().h2sha_digest_batch(self._h, C.byref(b)))
 
     def last_kernel_ms(self) -> Tuple[float, float]:

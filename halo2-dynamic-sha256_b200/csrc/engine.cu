@@ -83,6 +83,7 @@ struct JobArgs {
   uint32_t* spread;
   unsigned long long* cks;  // [n_inst][4] or null
   unsigned long long* job_counter;
+  uint32_t only_digest;     // 0: all; d + 1: only the jobs of digest() call d
 };
 
 __constant__ uint32_t c_K[64] = {
@@ -658,6 +659,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       unsigned long long dbg_p0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p0));
 #endif
       unsigned long long job = 0;
+    next_job:
       if (lane == 0) job = atomicAdd(A.job_counter, 1ULL);
       job = __shfl_sync(0xffffffffu, job, 0);
 #ifdef H2SHA_DEBUG_TIMING
@@ -678,6 +680,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         uint32_t r = (uint32_t)(blk - inst * P.blocks_per_inst);
         uint32_t d = 0;
         while (d + 1 < P.n_digests && r >= s_digests[d + 1].blk_prefix) d++;
+        if (A.only_digest && d + 1 != A.only_digest) goto next_job;
         const DevDigest& dd = s_digests[d];
         uint32_t jb = r - dd.blk_prefix;
         gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
@@ -698,6 +701,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           kk -= nb; cls++;
           batch = s_classes[cls].batch;
         }
+        if (A.only_digest && s_classes[cls].digest + 1 != A.only_digest) goto next_job;
         const DevDigest& dd = s_digests[s_classes[cls].digest];
         inst = kk * batch;
         n_valid = (uint32_t)min((uint64_t)batch, A.n_inst - inst);
@@ -1031,7 +1035,7 @@ struct HostSlot {
   cudaEvent_t copied = nullptr;       // recorded after the H2D copy out of this slot
   bool used = false;
 };
-enum { H2SHA_N_SETS = 2, H2SHA_N_SLOTS = 4 };
+enum { H2SHA_N_SETS = 2, H2SHA_N_SLOTS = 8 };
 
 struct h2sha_engine {
   Plan plan;
@@ -1098,7 +1102,7 @@ int ensure_set(h2sha_engine* e, InputSet* S, uint64_t n_inst, uint64_t in_bytes)
 }
 
 int ensure_slot(HostSlot* H, uint64_t bytes) {
-  if (H->used) { CUDA_TRY(cudaEventSynchronize(H->copied)); H->used = false; }   // the copy that last read this slot (3 calls ago) is long done
+  if (H->used) { CUDA_TRY(cudaEventSynchronize(H->copied)); H->used = false; }   // the copy that last read this slot (8 calls ago) is normally long done
   if (bytes > H->cap) {
     if (H->p) { cudaFreeHost(H->p); H->p = nullptr; }
     H->cap = 0;
@@ -1169,6 +1173,11 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   if (cfg->lookup_col_rows) { if (cfg->lookup_col_rows < P.lookup_col_rows) return set_err(H2SHA_EINVAL, "lookup_col_rows too small"); P.lookup_col_rows = cfg->lookup_col_rows; }
   if (cfg->spread_rows) { if (cfg->spread_rows < P.spread_rows) return set_err(H2SHA_EINVAL, "spread_rows too small"); P.spread_rows = cfg->spread_rows; }
   if ((P.gate_col_rows | P.lookup_col_rows | P.spread_rows) & 1u) return set_err(H2SHA_EINVAL, "column row strides must be even");
+  if (cfg->num_lookup_advice) {   // RangeConfig's NUM_LOOKUP_ADVICE: a configure-time input of halo2-base, not something the cells decide
+    if (cfg->num_lookup_advice < P.n_lookup_cols)
+      return set_err(H2SHA_EINVAL, "num_lookup_advice: the looked-up cells need " + std::to_string(P.n_lookup_cols) + " lookup advice column(s)");
+    P.n_lookup_cols = cfg->num_lookup_advice;
+  }
   e->n_sms = prop.multiProcessorCount;
   {
     uint32_t bp0 = 0, dw0 = 0;
@@ -1367,6 +1376,19 @@ int h2sha_get_handles(const h2sha_engine_t* e, uint32_t d, uint32_t* input_len_i
   return H2SHA_OK;
 }
 
+int h2sha_get_digest_ranges(const h2sha_engine_t* e, uint32_t* ranges) {
+  if (!e || !ranges) return set_err(H2SHA_EINVAL, "null argument");
+  const Plan& P = e->plan;
+  for (size_t d = 0; d < P.digests.size(); d++) {
+    const bool last = d + 1 == P.digests.size();
+    uint32_t* r = ranges + 6 * d;
+    r[0] = P.digests[d].gate_base; r[1] = last ? P.n_gate : P.digests[d + 1].gate_base;
+    r[2] = P.digests[d].lk_base; r[3] = last ? P.n_lookup : P.digests[d + 1].lk_base;
+    r[4] = P.digests[d].limb_base; r[5] = last ? P.n_limb : P.digests[d + 1].limb_base;
+  }
+  return H2SHA_OK;
+}
+
 int h2sha_get_shape(const h2sha_engine_t* e, uint8_t* selectors, uint32_t* copies, uint64_t* fixed, uint32_t* lookup_src,
                     uint32_t* limb_dense_src, uint32_t* limb_spread_src) {
   if (!e) return set_err(H2SHA_EINVAL, "null argument");
@@ -1403,6 +1425,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   const uint32_t D = (uint32_t)P.digests.size();
   const uint64_t n_msgs = b->n_instances * D;
   if (n_msgs > 0xffffffffull) return set_err(H2SHA_EINVAL, "batch too large");
+  if (b->only_digest > D) return set_err(H2SHA_EINVAL, "only_digest names a digest() call the configuration does not have");
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)b->stream;
   const bool timed = b->time_kernels != 0;
@@ -1487,7 +1510,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     JobArgs ja{};
     ja.n_inst = b->n_instances; ja.btrace = S->d_btrace; ja.dtrace = S->d_dtrace;
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
-    ja.cks = cks_dev; ja.job_counter = S->d_counter;
+    ja.cks = cks_dev; ja.job_counter = S->d_counter; ja.only_digest = b->only_digest;
     uint64_t n_jobs = b->n_instances * (uint64_t)e->blocks_per_inst * P.n_block_parts;
     for (size_t c = P.n_block_parts; c < P.classes.size(); c++) n_jobs += (b->n_instances + P.classes[c].batch - 1) / P.classes[c].batch;
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);

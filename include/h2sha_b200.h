@@ -59,6 +59,10 @@ typedef struct {
   int32_t device;                           /* CUDA device ordinal; -1 = plan-only (host queries, no witness)   */
   uint32_t build_shape;                     /* also build selectors / copy constraints / fixed column (host)    */
   uint32_t block_parts;                     /* tuning: GPU jobs per sha256_compression; 0 -> default            */
+  uint32_t num_lookup_advice;               /* RangeConfig's NUM_LOOKUP_ADVICE (lib.rs:413,492): lookup advice columns the circuit has;
+                                               0 -> as many as the looked-up cells need.  Fewer than needed -> H2SHA_EINVAL (halo2-base
+                                               would panic); more -> the extra columns stay empty.  Cells fill column 0 up to max_rows,
+                                               then column 1: for more than ONE column this order is an unpinned recollection of halo2-base */
 } h2sha_config_t;
 
 typedef struct {
@@ -86,6 +90,10 @@ int h2sha_get_breaks(const h2sha_engine_t* e, uint32_t* breaks);
 /* AssignedHashResult (lib.rs:31-36, 342-346) of digest d as gate-stream indices:
  * input_len (1), input_bytes (max_variable_byte_sizes[d]), output_bytes (32). */
 int h2sha_get_handles(const h2sha_engine_t* e, uint32_t d, uint32_t* input_len_idx, uint32_t* input_bytes_idx, uint32_t* output_bytes_idx);
+/* The stream ranges each digest() call owns (what that call appends in the reference, lib.rs:122-341):
+ * ranges [n_digests][6] = gate_lo, gate_hi, lookup_lo, lookup_hi, limb_lo, limb_hi (half-open; gate-stream indices,
+ * cells_to_lookup indices, spread-limb indices).  A facade that assigns cells digest() call by digest() call uses them. */
+int h2sha_get_digest_ranges(const h2sha_engine_t* e, uint32_t* ranges);
 
 /* Shape (needs build_shape): what keygen needs and what MockProver checks.
  *   selectors  [n_gate_cells] u8        gate selector per gate-stream index (q * (a + b*c - d) = 0 over 4 rows)
@@ -124,11 +132,19 @@ typedef struct {
                                         still resident in HBM and are reused (no validation, no H2D); n_instances
                                         must not exceed that call's                                                */
   int32_t time_kernels;              /* 1: bracket each kernel with CUDA events on `stream` (h2sha_last_kernel_ms) */
+  uint32_t only_digest;              /* 0: every digest() call of every instance; d + 1: only the cells digest() call d owns
+                                        (h2sha_get_digest_ranges) are generated -- for a facade that assigns call by call */
 } h2sha_batch_t;
 
 /* Replaces `digest` (lib.rs:71-349) for a whole batch: padding and length selection, the precomputed
- * prefix state (sha2::compress256, lib.rs:153-160), every compression and every cell.  Asynchronous on
- * batch->stream; host arrays `offsets/lens/precomputed_lens` are consumed before the call returns. */
+ * prefix state (sha2::compress256, lib.rs:153-160), every compression and every cell.
+ * The call only enqueues: every host INPUT array (msgs when it is host memory, offsets, lens, precomputed_lens) is copied
+ * into the engine's pinned staging ring before the call returns and may be reused at once; the call never waits for
+ * the device (exception: more than 8 calls in flight, when the oldest staging slot is still being copied from).
+ * Results reach digests_host / checksums_host in stream order: synchronise `stream` (or an event recorded after the
+ * call) before reading them; they must stay valid until then and should be pinned (a pageable destination makes the
+ * CUDA runtime block inside the call).  With host messages and host result buffers the H2D copy and the trace kernel
+ * run on an engine-owned stream and overlap the previous batch's expansion kernel. */
 int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* batch);
 
 /* Prover hand-off: copy ONE instance's advice columns from the batch buffers to host memory, one vector per advice
