@@ -1030,8 +1030,7 @@ struct InputSet {
 // One slot of the pinned staging ring: the caller's host arrays are copied here before the call returns, so the call itself
 // never waits for the device.
 struct HostSlot {
-  uint8_t* p = nullptr;
-  uint64_t cap = 0;
+  uint8_t* p = nullptr;               // inside the engine's pinned arena (one allocation for the whole ring: cudaHostAlloc costs ~1 ms a call)
   cudaEvent_t copied = nullptr;       // recorded after the H2D copy out of this slot
   bool used = false;
 };
@@ -1049,6 +1048,8 @@ struct h2sha_engine {
   // input / trace workspaces (grown on demand), pinned staging ring, copy stream
   InputSet sets[H2SHA_N_SETS];
   HostSlot slots[H2SHA_N_SLOTS];
+  uint8_t* pinned_arena = nullptr;
+  uint64_t slot_cap = 0;             // bytes per ring slot
   cudaStream_t copy_stream = nullptr;
   uint64_t seq = 0;                  // calls that uploaded inputs
   int resident_set = -1;             // set holding the inputs of the last such call
@@ -1101,15 +1102,19 @@ int ensure_set(h2sha_engine* e, InputSet* S, uint64_t n_inst, uint64_t in_bytes)
   return H2SHA_OK;
 }
 
-int ensure_slot(HostSlot* H, uint64_t bytes) {
-  if (H->used) { CUDA_TRY(cudaEventSynchronize(H->copied)); H->used = false; }   // the copy that last read this slot (8 calls ago) is normally long done
-  if (bytes > H->cap) {
-    if (H->p) { cudaFreeHost(H->p); H->p = nullptr; }
-    H->cap = 0;
-    const uint64_t cap = std::max<uint64_t>(bytes + bytes / 4, 1 << 16);
-    CUDA_TRY(cudaHostAlloc((void**)&H->p, cap, cudaHostAllocDefault));
-    H->cap = cap;
+int ensure_slot(h2sha_engine* e, HostSlot* H, uint64_t bytes) {
+  if (bytes > e->slot_cap) {
+    // grow the whole ring: every slot has to be idle first
+    for (HostSlot& X : e->slots)
+      if (X.used) { CUDA_TRY(cudaEventSynchronize(X.copied)); X.used = false; }
+    if (e->pinned_arena) { cudaFreeHost(e->pinned_arena); e->pinned_arena = nullptr; }
+    e->slot_cap = 0;
+    const uint64_t cap = (std::max<uint64_t>(bytes + bytes / 4, 1 << 16) + 4095) / 4096 * 4096;
+    CUDA_TRY(cudaHostAlloc((void**)&e->pinned_arena, cap * H2SHA_N_SLOTS, cudaHostAllocDefault));
+    e->slot_cap = cap;
+    for (int i = 0; i < H2SHA_N_SLOTS; i++) e->slots[i].p = e->pinned_arena + (uint64_t)i * cap;
   }
+  if (H->used) { CUDA_TRY(cudaEventSynchronize(H->copied)); H->used = false; }   // the copy that last read this slot (8 calls ago): back-pressure on a host that runs far ahead
   return H2SHA_OK;
 }
 
@@ -1331,10 +1336,9 @@ void h2sha_destroy(h2sha_engine_t* e) {
     if (S.trace_done) cudaEventDestroy(S.trace_done);
     if (S.expand_done) cudaEventDestroy(S.expand_done);
   }
-  for (HostSlot& H : e->slots) {
+  for (HostSlot& H : e->slots)
     if (H.copied) cudaEventDestroy(H.copied);
-    if (H.p) cudaFreeHost(H.p);
-  }
+  if (e->pinned_arena) cudaFreeHost(e->pinned_arena);
   for (int i = 0; i < 4; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab); cudaFree(e->d_range_tab);
   cudaFree(e->d_chk_gate_on); cudaFree(e->d_chk_pairs); cudaFree(e->d_chk_out_bytes); cudaFree(e->d_chk_fixed); cudaFree(e->d_chk_bytes); cudaFree(e->d_chk_viol);
@@ -1444,7 +1448,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     const uint64_t hdr = n_msgs * 16;
     const uint64_t in_bytes = hdr + (b->msgs_on_device ? 0 : b->msgs_bytes);
     HostSlot* H = &e->slots[e->seq % H2SHA_N_SLOTS];
-    int rc = ensure_slot(H, in_bytes);
+    int rc = ensure_slot(e, H, in_bytes);
     if (rc) return rc;
     uint64_t* h_off = reinterpret_cast<uint64_t*>(H->p);
     uint32_t* h_len = reinterpret_cast<uint32_t*>(H->p + n_msgs * 8);
