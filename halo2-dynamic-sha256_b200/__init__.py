@@ -29,7 +29,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_build_id", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_digest_ranges", "h2sha_get_shape", "h2sha_get_lookup_tables",
-    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_check_batch", "h2sha_gather", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_debug_int_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
+    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_export_batch", "h2sha_get_compact_info", "h2sha_get_compact_map", "h2sha_expand_compact", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_check_batch", "h2sha_gather", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_debug_int_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
 
@@ -64,7 +64,12 @@ class _Batch(C.Structure):
                 ("offsets", C.c_void_p), ("lens", C.c_void_p), ("precomputed_lens", C.c_void_p), ("gate", C.c_void_p), ("lookup", C.c_void_p),
                 ("spread", C.c_void_p), ("digests_dev", C.c_void_p), ("checksums_dev", C.c_void_p), ("digests_host", C.c_void_p),
                 ("checksums_host", C.c_void_p), ("stream", C.c_void_p), ("reuse_inputs", C.c_int32), ("time_kernels", C.c_int32),
-                ("only_digest", C.c_uint32)]
+                ("only_digest", C.c_uint32), ("lookup_mult_dev", C.c_void_p), ("mult_usable_rows", C.c_uint32), ("mult_not_in_table_dev", C.c_void_p),
+                ("compact_dict", C.c_void_p)]
+
+
+class _CompactInfo(C.Structure):
+    _fields_ = [("dict_cells_per_instance", C.c_uint64), ("dict_bytes_per_instance", C.c_uint64), ("cells_per_instance", C.c_uint64), ("n_consts", C.c_uint32)]
 
 
 class _LookupInfo(C.Structure):
@@ -95,6 +100,10 @@ def load_library():
     L.h2sha_get_lookup_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
     L.h2sha_export_instance.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]
+    L.h2sha_export_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+    L.h2sha_get_compact_info.argtypes = [C.c_void_p, C.POINTER(_CompactInfo)]
+    L.h2sha_get_compact_map.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.h2sha_expand_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32]
     L.h2sha_get_lookup_info.argtypes = [C.c_void_p, C.POINTER(_LookupInfo)]
     L.h2sha_lookup_multiplicities.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.h2sha_permute_lookup.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -296,7 +305,8 @@ class Sha256DynamicConfig:
     def digest_batch_raw(self, n_instances: int, msgs_ptr: int, msgs_on_device: bool, msgs_bytes: int, offsets: np.ndarray, lens: np.ndarray,
                          precomputed_lens: Optional[np.ndarray], *, gate_ptr: int = 0, lookup_ptr: int = 0, spread_ptr: int = 0,
                          digests_dev_ptr: int = 0, checksums_dev_ptr: int = 0, digests_host_ptr: int = 0, checksums_host_ptr: int = 0,
-                         stream: int = 0, reuse_inputs: bool = False, time_kernels: bool = False, only_digest: int = 0):
+                         stream: int = 0, reuse_inputs: bool = False, time_kernels: bool = False, only_digest: int = 0,
+                         lookup_mult_ptr: int = 0, mult_usable_rows: int = 0, mult_bad_ptr: int = 0, compact_dict_ptr: int = 0):
         """Thin wrapper over h2sha_digest_batch (all pointers are integers)."""
         if reuse_inputs:
             off_p = len_p = pre_p = None
@@ -306,7 +316,8 @@ class Sha256DynamicConfig:
             pre_p = precomputed_lens.ctypes.data if precomputed_lens is not None else None
         b = _Batch(n_instances, msgs_ptr or None, 1 if msgs_on_device else 0, msgs_bytes, off_p, len_p, pre_p, gate_ptr or None,
                    lookup_ptr or None, spread_ptr or None, digests_dev_ptr or None, checksums_dev_ptr or None, digests_host_ptr or None,
-                   checksums_host_ptr or None, stream or None, 1 if reuse_inputs else 0, 1 if time_kernels else 0, only_digest)
+                   checksums_host_ptr or None, stream or None, 1 if reuse_inputs else 0, 1 if time_kernels else 0, only_digest,
+                   lookup_mult_ptr or None, mult_usable_rows, mult_bad_ptr or None, compact_dict_ptr or None)
         _check(load_library().h2sha_digest_batch(self._h, C.byref(b)))
 
     def last_kernel_ms(self) -> Tuple[float, float]:
@@ -362,6 +373,46 @@ class Sha256DynamicConfig:
         _check(load_library().h2sha_export_instance(self._h, instance, res.gate.data_ptr(), res.lookup.data_ptr(), res.spread.data_ptr(), ptrs,
                                                     rows_per_column, torch.cuda.current_stream(self.device).cuda_stream))
         torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    # ---- prover hand-off of whole batches ----
+    def n_columns(self) -> int:
+        lay = self.layout
+        return lay.n_gate_cols + lay.n_lookup_cols + lay.n_spread_cols
+
+    def export_batch(self, res: "BatchResult", first: int, n: int, rows_per_column: int, out=None):
+        """Instances [first, first+n) of a batch as a pinned host tensor [n, n_columns, rows_per_column, 4] int64 (zero-padded columns in
+        the reference's allocation order): three strided D2H copies for the whole range."""
+        import torch
+        if out is None:
+            out = torch.zeros((n, self.n_columns(), rows_per_column, 4), dtype=torch.int64).pin_memory()
+        _check(load_library().h2sha_export_batch(self._h, first, n, res.gate.data_ptr(), res.lookup.data_ptr(), res.spread.data_ptr(), out.data_ptr(),
+                                                 rows_per_column, 0, torch.cuda.current_stream(self.device).cuda_stream))
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    def compact_info(self) -> dict:
+        ci = _CompactInfo()
+        _check(load_library().h2sha_get_compact_info(self._h, C.byref(ci)))
+        return {f[0]: int(getattr(ci, f[0])) for f in _CompactInfo._fields_}
+
+    def compact_map(self):
+        """(gate_map, lookup_map, dense_map, spread_map, consts): which dictionary entry (or 0x80000000 | constant index) each cell copies."""
+        lay, ci = self.layout, self.compact_info()
+        g = np.zeros(lay.n_gate_cells, np.uint32); l = np.zeros(lay.n_lookup_cells, np.uint32)
+        d = np.zeros(lay.n_spread_limbs, np.uint32); s = np.zeros(lay.n_spread_limbs, np.uint32)
+        c = np.zeros((ci["n_consts"], 4), np.uint64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _check(load_library().h2sha_get_compact_map(self._h, p(g), p(l), p(d), p(s), p(c)))
+        return g, l, d, s, c
+
+    def expand_compact(self, dict_host, n: int, rows_per_column: int, out=None, n_threads: int = 0, zero_fill: bool = True):
+        """Host-side expander of the compact hand-off: dictionary [n, dict_cells, 4] (numpy or CPU tensor) -> [n, n_columns, rows_per_column, 4]."""
+        dptr = dict_host.ctypes.data if isinstance(dict_host, np.ndarray) else dict_host.data_ptr()
+        if out is None:
+            out = np.empty((n, self.n_columns(), rows_per_column, 4), dtype=np.uint64)
+        optr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        _check(load_library().h2sha_expand_compact(self._h, C.c_void_p(dptr), n, C.c_void_p(optr), rows_per_column, 1 if zero_fill else 0, n_threads))
         return out
 
     def check_batch(self, res: "BatchResult", digests_dev_ptr: int = 0) -> dict:

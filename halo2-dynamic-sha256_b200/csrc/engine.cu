@@ -60,7 +60,7 @@ struct DevPlan {
   uint32_t blob_bytes;
   // byte offsets inside the blob (all 16-byte aligned)
   uint32_t off_fill, off_cells, off_chunks, off_items, off_table_lo, off_table_hi, off_resident, off_prog, off_groups, off_tasks, off_types, off_classes,
-      off_raw, off_breaks, off_digests;
+      off_raw, off_breaks, off_digests, off_item_dict;
   uint32_t n_breaks, n_digests, n_block_parts, n_classes;
   // dynamic shared memory layout after the blob
   uint32_t off_trace, off_scratch, off_misc, smem_bytes;
@@ -84,6 +84,15 @@ struct JobArgs {
   unsigned long long* cks;  // [n_inst][4] or null
   unsigned long long* job_counter;
   uint32_t only_digest;     // 0: all; d + 1: only the jobs of digest() call d
+  // table-row multiplicities of the two kinds of lookups, counted while the cells are written (null: not wanted)
+  uint32_t* mult;           // [n_inst][mult_words]: range lookups [n_lookup_cols][2^lookup_bits], then spread lookups [spread_cols][2^limb_bits]
+  uint32_t* mult_bad;       // cells that are no table row (null: not counted)
+  uint64_t mult_words;
+  uint32_t usable_rows;     // rows every lookup is evaluated on: never-assigned rows count as table row 0
+  uint32_t lookup_bits, limb_bits, n_lookup_total, n_limb_total;
+  // compact hand-off: every DISTINCT value of an instance, once (null: not wanted)
+  uint32_t* dict;           // [n_inst][dict_inst_cells] Fr as 8 x u32
+  uint64_t dict_inst_cells;
 };
 
 __constant__ uint32_t c_K[64] = {
@@ -424,6 +433,7 @@ struct StageDesc {
   uint32_t cls, gate0, lk0, limb0;
   uint32_t valid;               // 0: the producer has run out of jobs
   uint32_t n_inst;              // circuit instances the job covers (digest jobs are batched)
+  uint32_t dict0;               // dictionary index of the job's first distinct value inside its instance (compact hand-off)
 };
 
 // ---- mbarrier helpers (shared::cta) ----
@@ -520,22 +530,31 @@ __device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitT
   }
 }
 
+// one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
+__device__ __forceinline__ void store_cell2(uint32_t* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
+               "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
 // fill phase: the chunk's distinct values -> warp scratch.  Each function returns the checksum hash of the value.
 __device__ __forceinline__ uint32_t hash8(const uint4& lo, const uint4& hi) {
   return lo.x * c_CKM[0] + lo.y * c_CKM[1] + lo.z * c_CKM[2] + lo.w * c_CKM[3] + hi.x * c_CKM[4] + hi.y * c_CKM[5] + hi.z * c_CKM[6] +
          hi.w * c_CKM[7];
 }
 __device__ __forceinline__ uint32_t fill_table(const FillEntry& e, const uint64_t* slots, const uint4* table_lo, const uint4* table_hi,
-                                               const WarpScratch& ws) {
+                                               const WarpScratch& ws, uint32_t* raw, uint32_t* dict_out) {
   const uint32_t i = H2SHA_TE_DST(e);
   const uint64_t s = slots[H2SHA_TE_SLOT(e)];
-  const uint32_t idx = H2SHA_TE_TBL(e) + (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
+  *raw = (uint32_t)extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e));
+  const uint32_t idx = H2SHA_TE_TBL(e) + *raw;
   const uint4 lo = table_lo[idx], hi = table_hi[idx];
   ws.lo[i] = lo; ws.hi[i] = hi;
+  if (dict_out) store_cell2(dict_out, lo, hi);
   return hash8(lo, hi);
 }
 // Barrett entries: the 32-bit path when every lane of the warp iteration holds a value < 2^32, else the 64-bit path
-__device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint64_t* slots, const WarpScratch& ws, bool active) {
+__device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint64_t* slots, const WarpScratch& ws, bool active, uint64_t* raw, uint32_t* dict_out) {
   const uint32_t i = H2SHA_TE_DST(e);
   bool neg = false;
   uint64_t v = 0;
@@ -550,6 +569,7 @@ __device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint6
       v = extract(s, H2SHA_TE_SH(e), H2SHA_TE_W(e)) << H2SHA_TE_SHL(e);
     }
   }
+  *raw = v;
   uint32_t x[8];
   if (__any_sync(0xffffffffu, (v >> 32) != 0)) {
     uint64_t r[4];
@@ -562,19 +582,15 @@ __device__ __forceinline__ uint32_t fill_generic(const FillEntry& e, const uint6
     if (neg) fr_negate32(x);
   }
   const uint4 lo = make_uint4(x[0], x[1], x[2], x[3]), hi = make_uint4(x[4], x[5], x[6], x[7]);
-  if (active) { ws.lo[i] = lo; ws.hi[i] = hi; }
+  if (active) {
+    ws.lo[i] = lo; ws.hi[i] = hi;
+    if (dict_out) store_cell2(dict_out, lo, hi);
+  }
   return hash8(lo, hi);
 }
 
 // the copy loops' read of a cell's value from the warp scratch
 #define H2SHA_SCRATCH_READ(src) const uint4 lo = ws.lo[src], hi = ws.hi[src];
-// one 256-bit store per Fr cell (STG.E.256, sm_100+); p must be 32-byte aligned
-__device__ __forceinline__ void store_cell2(uint32_t* p, const uint4& lo, const uint4& hi) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x),
-               "r"(hi.y), "r"(hi.z), "r"(hi.w)
-               : "memory");
-}
-
 // warp-reduce the three checksum accumulators and add them to the instance's totals (gate, lookup, spread, all)
 __device__ __forceinline__ void flush_checksums(unsigned long long* cks, uint64_t inst, unsigned long long ck_g, unsigned long long ck_l,
                                                 unsigned long long ck_s, int lane) {
@@ -592,11 +608,20 @@ __device__ __forceinline__ void flush_checksums(unsigned long long* cks, uint64_
   }
 }
 
+// one looked-up value with multiplicity `cnt` -> its bin of the range lookup (a value outside the table is counted as bad, not binned)
+__device__ __forceinline__ void count_range(uint32_t* bins, uint32_t* bad, uint64_t raw, uint32_t cnt, uint32_t lookup_bits) {
+  if ((raw >> lookup_bits) == 0) atomicAdd(&bins[(uint32_t)raw], cnt);
+  else if (bad) atomicAdd(bad, cnt);
+}
+
 // Warp-specialised persistent kernel: NPROD producer warps run phase 1 (job fetch, trace load, slot programs) into
 // their own stage buffer; NCONS consumer warps run phase 2 (fill + copy) stage after stage.  Stages are handed over
 // with mbarriers, so no warp ever waits at a CTA-wide barrier inside the job loop.
-template <int NCONS, int NPROD>
+// MODE 0: cells (+ checksums); 1: also count the lookup multiplicities (A.mult); 2: also write the dictionary of distinct values
+// (A.dict).  Separate instantiations: the extra code costs registers the plain path (80 per thread at 768 threads) does not have.
+template <int NCONS, int NPROD, int MODE>
 __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPlan P, const JobArgs A) {
+  constexpr bool MULT = MODE == 1, DICT = MODE == 2;
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int NT = (NCONS + NPROD) * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -621,6 +646,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
   const uint64_t* s_raw = reinterpret_cast<const uint64_t*>(smem + P.off_raw);
   const uint32_t* s_breaks = reinterpret_cast<const uint32_t*>(smem + P.off_breaks);
   const DevDigest* s_digests = reinterpret_cast<const DevDigest*>(smem + P.off_digests);
+  [[maybe_unused]] const uint32_t* s_item_dict = reinterpret_cast<const uint32_t*>(smem + P.off_item_dict);
   uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + P.off_misc);   // [NPROD]
   uint64_t* s_empty = s_full + NPROD;                                  // [NPROD]
   if (tid == 0) {
@@ -672,7 +698,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         break;
       }
       // ---- decode job ----
-      uint64_t inst; uint32_t cls, gate0, lk0, limb0, n_valid = 1, tr_words;
+      uint64_t inst; uint32_t cls, gate0, lk0, limb0, n_valid = 1, tr_words, dict0;
       if (job < n_block_jobs) {
         const uint64_t blk = job / P.n_block_parts;          // global block index = inst * blocks_per_inst + r
         cls = (uint32_t)(job - blk * P.n_block_parts);        // part of the block job
@@ -686,6 +712,22 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         gate0 = dd.dp.blk_gate_base + jb * dd.dp.blk_gate_stride;
         lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
         limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
+        dict0 = dd.dp.dict_base + dd.dp.dict_dig_len + jb * dd.dp.dict_blk_len;
+        if (MULT && cls == 0 && r == 0) {
+          // once per instance: the never-assigned rows of every lookup input column hold 0 = table row 0 of either table
+          uint32_t* mi = A.mult + inst * A.mult_words;
+          for (uint32_t c = lane; c < P.n_lookup_cols + P.spread_cols; c += 32) {
+            if (c < P.n_lookup_cols) {
+              const uint32_t first = c * P.max_rows;
+              const uint32_t used = A.n_lookup_total > first ? min(P.max_rows, A.n_lookup_total - first) : 0u;
+              if (A.usable_rows > used) atomicAdd(&mi[(uint64_t)c << A.lookup_bits], A.usable_rows - used);
+            } else {
+              const uint32_t cc = c - P.n_lookup_cols;
+              const uint32_t used = A.n_limb_total > cc ? (A.n_limb_total - cc + P.spread_cols - 1) / P.spread_cols : 0u;
+              if (A.usable_rows > used) atomicAdd(&mi[((uint64_t)P.n_lookup_cols << A.lookup_bits) + ((uint64_t)cc << A.limb_bits)], A.usable_rows - used);
+            }
+          }
+        }
         const uint32_t* tr_src = A.btrace + (uint64_t)r * A.n_inst + inst;
         const uint64_t tr_stride = (uint64_t)P.blocks_per_inst * A.n_inst;
         tr_words = TR_BLOCK_WORDS;
@@ -706,6 +748,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         inst = kk * batch;
         n_valid = (uint32_t)min((uint64_t)batch, A.n_inst - inst);
         gate0 = 0; lk0 = 0; limb0 = 0;
+        dict0 = dd.dp.dict_base;
         tr_words = dd.dp.trace_words;
         // word-major global layout: consecutive instances are adjacent, so lanes run over the instances of the batch
         const uint32_t* tr_src = A.dtrace + (uint64_t)dd.dtrace_off * A.n_inst + inst;
@@ -715,7 +758,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         }
       }
       const JobClass jc = s_classes[cls];
-      if (lane == 0) { desc->inst = inst; desc->cls = cls; desc->gate0 = gate0; desc->lk0 = lk0; desc->limb0 = limb0; desc->valid = 1; desc->n_inst = n_valid; }
+      if (lane == 0) { desc->inst = inst; desc->cls = cls; desc->gate0 = gate0; desc->lk0 = lk0; desc->limb0 = limb0; desc->valid = 1; desc->n_inst = n_valid; desc->dict0 = dict0; }
       __syncwarp();
 #ifdef H2SHA_DEBUG_TIMING
       unsigned long long dbg_p2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p2));
@@ -807,27 +850,67 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       // checksum weight of a value carried by cnt cells whose offsets sum to sumdst: sum (2*pos+1) = cnt*w0 + 2*sumdst
       const unsigned long long w0 = straddle ? 0ull : (unsigned long long)(2u * (g_lo + off0) + 1u);
       const unsigned long long w1 = straddle ? 0ull : 2ull;
+      // ---- lookup multiplicities: the chunk's looked-up cells all lie in one lookup column unless the column wraps inside the
+      // chunk (then they are counted cell by cell after the fill) ----
+      [[maybe_unused]] uint32_t* mult_inst = nullptr;
+      [[maybe_unused]] uint32_t* mult_range = nullptr;
+      [[maybe_unused]] bool lk_wrap_inside = false;
+      if constexpr (MULT) mult_inst = A.mult + inst * A.mult_words;
+      if (MULT && ch.lk_len) {
+        const uint32_t l_first = lk0 + item.lk_rel + H2SHA_CE_DST(s_cells[ch.lk_off]);
+        const uint32_t l_last = lk0 + item.lk_rel + H2SHA_CE_DST(s_cells[ch.lk_off + ch.lk_len - 1]);
+        const uint32_t colf = l_first / P.max_rows;
+        lk_wrap_inside = l_last / P.max_rows != colf;
+        if (!lk_wrap_inside) mult_range = mult_inst + ((uint64_t)colf << A.lookup_bits);
+      }
+      // ---- compact hand-off: the chunk's distinct values also go to the instance's dictionary, fill entry i -> entry dict_chunk + i ----
+      [[maybe_unused]] uint32_t* dict_chunk = nullptr;
+      if constexpr (DICT) dict_chunk = A.dict + (inst * A.dict_inst_cells + desc->dict0 + s_item_dict[jc.item_off + it]) * 8;
       // ---- fill: table copies, then Barrett conversions ----
       {
         const FillEntry* fl = s_fill + ch.fill_off;
         const uint32_t n_tab = ch.n_fill_table, n_all = ch.n_fill;
         for (uint32_t i = lane; i < n_tab; i += 32) {
           const FillEntry e = fl[i];
-          const uint32_t h = fill_table(e, slots, s_table_lo, s_table_hi, ws);
-          ck_g += (unsigned long long)h * (e.cnt * w0 + e.sumdst * w1);
+          uint32_t raw;
+          const uint32_t h = fill_table(e, slots, s_table_lo, s_table_hi, ws, &raw, DICT ? dict_chunk + (uint64_t)i * 8 : nullptr);
+          ck_g += (unsigned long long)h * (H2SHA_FE_GATE_CNT(e) * w0 + e.sumdst * w1);
+          if constexpr (MULT) { if (mult_range && H2SHA_FE_LK_CNT(e)) count_range(mult_range, A.mult_bad, raw, H2SHA_FE_LK_CNT(e), A.lookup_bits); }
         }
         for (uint32_t i0 = n_tab; i0 < n_all; i0 += 32) {
           const uint32_t i = i0 + lane;
           const bool active = i < n_all;
           FillEntry e = fl[active ? i : n_tab];
-          const uint32_t h = fill_generic(e, slots, ws, active);
-          if (active) ck_g += (unsigned long long)h * (e.cnt * w0 + e.sumdst * w1);
+          uint64_t raw;
+          const uint32_t h = fill_generic(e, slots, ws, active, &raw, DICT ? dict_chunk + (uint64_t)i * 8 : nullptr);
+          if (active) {
+            ck_g += (unsigned long long)h * (H2SHA_FE_GATE_CNT(e) * w0 + e.sumdst * w1);
+            if constexpr (MULT) { if (mult_range && H2SHA_FE_LK_CNT(e)) count_range(mult_range, A.mult_bad, raw, H2SHA_FE_LK_CNT(e), A.lookup_bits); }
+          }
         }
         if (lane == 0 && !straddle) ck_g += ch.res_a + ch.res_b * w0;
       }
       __syncwarp();
+      if (MULT && lk_wrap_inside) {
+        // rare (once per lookup-column wrap): per fill entry, count the chunk's lookup cells that carry it on either side of the wrap
+        const FillEntry* fl = s_fill + ch.fill_off;
+        const uint32_t l_lo2 = lk0 + item.lk_rel;
+        for (uint32_t i = lane; i < ch.n_fill; i += 32) {
+          const FillEntry e = fl[i];
+          if (!H2SHA_FE_LK_CNT(e)) continue;
+          const uint64_t sv = slots[H2SHA_TE_SLOT(e)];
+          uint64_t raw = extract(sv, H2SHA_TE_SH(e), H2SHA_TE_W(e));
+          if (H2SHA_TE_KIND(e) != KIND_TABLE) raw <<= H2SHA_TE_SHL(e);
+          for (uint32_t k2 = 0; k2 < ch.lk_len; k2++) {
+            const CellEntry ce = s_cells[ch.lk_off + k2];
+            if (H2SHA_CE_SRC(ce) != H2SHA_TE_DST(e)) continue;
+            const uint32_t col = (l_lo2 + H2SHA_CE_DST(ce)) / P.max_rows;
+            count_range(mult_inst + ((uint64_t)col << A.lookup_bits), A.mult_bad, raw, 1u, A.lookup_bits);
+          }
+        }
+      }
       // ---- copy: gate cells ----
-      if (ch.gate_len) {
+      if (ch.gate_len && (gate_out || (straddle && A.cks))) {   // nothing to do when only the dictionary / checksums of a non-straddling chunk are wanted
         const CellEntry* cells = s_cells + ch.gate_off;
         if (!straddle) {
           // warp stores are aligned to 256-byte groups of the output: iteration k covers the 32 cells starting at
@@ -859,7 +942,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         }
       }
       // ---- lookup-column cells (range.finalize copies cells_to_lookup in push order, wrapping at max_rows) ----
-      if (ch.lk_len) {
+      if (ch.lk_len && (lk_out || A.cks)) {
         const uint32_t l_lo = lk0 + item.lk_rel;
         // pos = li + loff0 before the column wrap at `wrap`, li + loff1 after it (no division in the loop)
         uint32_t loff0 = 0, loff1 = 0, wrap = 0xffffffffu;
@@ -886,16 +969,21 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         }
       }
       // ---- spread-table columns: limb n -> column n % cols, row n / cols (spread.rs:202,228-231); dense then spread ----
-      if (ch.limb_len) {
+      if (ch.limb_len && (sp_out || A.cks || MULT)) {
         const uint32_t m_lo = limb0 + item.limb_rel;
+        [[maybe_unused]] uint32_t* mult_spread = nullptr;
+        if constexpr (MULT) mult_spread = mult_inst + ((uint64_t)P.n_lookup_cols << A.lookup_bits);
         for (uint32_t i = lane; i < ch.limb_len; i += 32) {
           const CellEntry ce = s_cells[ch.limb_off + i];
-          const uint32_t src = H2SHA_CE_SRC(ce);
+          const uint32_t src = H2SHA_LE_SRC(ce);
           H2SHA_SCRATCH_READ(src)
-          const uint32_t n = m_lo + (H2SHA_CE_DST(ce) >> 1), which = H2SHA_CE_DST(ce) & 1u;
+          const uint32_t n = m_lo + (H2SHA_LE_DST(ce) >> 1), which = H2SHA_LE_DST(ce) & 1u;
           uint32_t row, col;
           if (P.spread_cols_shift >= 0) { row = n >> P.spread_cols_shift; col = n & (P.spread_cols - 1u); }
           else { row = n / P.spread_cols; col = n - row * P.spread_cols; }
+          // the (dense, spread) pair of limb n is row `dense` of the spread table: count it once, with the dense cell
+          if (MULT && which == 0)
+            atomicAdd(&mult_spread[((uint64_t)col << A.limb_bits) + (uint32_t)extract(slots[H2SHA_LE_SLOT(ce)], H2SHA_LE_SH(ce), A.limb_bits)], 1u);
           const uint32_t pos = (which * P.spread_cols + col) * P.spread_rows + row;
           if (sp_out) store_cell2(sp_out + (uint64_t)pos * 8, lo, hi);
           ck_s += (unsigned long long)hash8(lo, hi) * (unsigned long long)(2u * pos + 1u);
@@ -983,10 +1071,10 @@ __global__ void k_zero_ranges(uint4* buf, uint64_t inst_cells, uint64_t n_inst, 
 // launch variants (consumer warps, producer warps); selected at engine creation (H2SHA_TUNE "cons=..,prod=..")
 struct ExpandVariant {
   int ncons, nprod;
-  const void* fn;
+  const void* fn[3];   // by MODE: plain | + lookup multiplicities | + dictionary of distinct values
 };
 template <int NC, int NP>
-ExpandVariant make_variant() { return ExpandVariant{NC, NP, (const void*)k_expand<NC, NP>}; }
+ExpandVariant make_variant() { return ExpandVariant{NC, NP, {(const void*)k_expand<NC, NP, 0>, (const void*)k_expand<NC, NP, 1>, (const void*)k_expand<NC, NP, 2>}}; }
 const ExpandVariant* expand_variants(int* n) {
   // the tuned default and the fallback chain for plans that need more shared memory (fewer consumer warps = less scratch)
   static const ExpandVariant v[] = {make_variant<20, 4>(), make_variant<16, 4>(), make_variant<12, 4>(), make_variant<8, 4>(), make_variant<8, 2>()};
@@ -1036,6 +1124,8 @@ struct HostSlot {
 };
 enum { H2SHA_N_SETS = 2, H2SHA_N_SLOTS = 8 };
 
+struct h2sha_compact_state;   // export.cuh
+
 struct h2sha_engine {
   Plan plan;
   int device = 0;
@@ -1071,6 +1161,8 @@ struct h2sha_engine {
   uint64_t *d_chk_fixed = nullptr, *d_chk_bytes = nullptr;
   unsigned long long* d_chk_viol = nullptr;
   uint32_t n_chk_gate_on = 0, n_chk_pairs = 0;
+  // compact hand-off (export.cuh): the cell -> dictionary-entry map, planned on first use
+  h2sha_compact_state* compact = nullptr;
 };
 
 namespace {
@@ -1117,6 +1209,8 @@ int ensure_slot(h2sha_engine* e, HostSlot* H, uint64_t bytes) {
   if (H->used) { CUDA_TRY(cudaEventSynchronize(H->copied)); H->used = false; }   // the copy that last read this slot (8 calls ago): back-pressure on a host that runs far ahead
   return H2SHA_OK;
 }
+
+uint32_t lookup_rows_needed(const Plan& P);   // lookup_prework.cuh
 
 struct EngineGuard {   // error paths of h2sha_create: releases whatever has been allocated so far
   h2sha_engine* e;
@@ -1244,6 +1338,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   D.off_raw = put(P.raw_consts.data(), P.raw_consts.size() * 8);
   D.off_breaks = put(P.breaks.data(), P.breaks.size() * 4);
   D.off_digests = put(dds.data(), dds.size() * sizeof(DevDigest));
+  D.off_item_dict = put(P.item_dict.data(), P.item_dict.size() * 4);
   D.blob_bytes = (uint32_t)blob.size();
   D.n_breaks = (uint32_t)P.breaks.size();
   D.n_digests = (uint32_t)P.digests.size();
@@ -1304,9 +1399,13 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   const int expand_threads = (e->variant.ncons + e->variant.nprod) * 32;
   // the attribute belongs to the kernel function, not to this engine: always raise it to the 227 KB cap, so that engines of
   // different configurations that share a launch variant never lower each other's limit
-  CUDA_TRY(cudaFuncSetAttribute(e->variant.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (const void* fn : e->variant.fn) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e->variant.fn, expand_threads, D.smem_bytes));
+  for (const void* fn : e->variant.fn) {
+    int o = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, expand_threads, D.smem_bytes));
+    occ = (fn == e->variant.fn[0]) ? o : std::min(occ, o);
+  }
   if (occ < 1) return set_err(H2SHA_ECUDA, "expand kernel does not fit on an SM");
   e->expand_ctas = occ * e->n_sms;
   // ---- copy stream, events, job counters ----
@@ -1323,8 +1422,11 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   return H2SHA_OK;
 }
 
+void h2sha_free_compact_state(h2sha_compact_state* s);   // defined after export.cuh (complete type)
+
 void h2sha_destroy(h2sha_engine_t* e) {
   if (!e) return;
+  h2sha_free_compact_state(e->compact); e->compact = nullptr;
   if (e->device < 0) { delete e; return; }
   cudaSetDevice(e->device);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
@@ -1430,6 +1532,13 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   const uint64_t n_msgs = b->n_instances * D;
   if (n_msgs > 0xffffffffull) return set_err(H2SHA_EINVAL, "batch too large");
   if (b->only_digest > D) return set_err(H2SHA_EINVAL, "only_digest names a digest() call the configuration does not have");
+  if (b->compact_dict && (b->lookup_mult_dev || b->only_digest))
+    return set_err(H2SHA_EINVAL, "compact_dict cannot be combined with lookup_mult_dev or only_digest (separate kernel instantiations): issue two calls");
+  if (b->lookup_mult_dev) {
+    if (b->only_digest) return set_err(H2SHA_EINVAL, "lookup multiplicities need every digest() call of the region (only_digest must be 0)");
+    if (!b->gate || !b->lookup || !b->spread) return set_err(H2SHA_EINVAL, "lookup multiplicities are counted while the cells are written: gate, lookup and spread must be given");
+    if (b->mult_usable_rows < lookup_rows_needed(P)) return set_err(H2SHA_EINVAL, "mult_usable_rows is smaller than an assigned column or a lookup table");
+  }
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)b->stream;
   const bool timed = b->time_kernels != 0;
@@ -1498,9 +1607,15 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   ta.pre_lens = S->has_pre ? reinterpret_cast<const uint32_t*>(S->d_in + cap_n * 12) : nullptr;
   ta.btrace = S->d_btrace; ta.dtrace = S->d_dtrace; ta.digests = dig_dev; ta.digests_plan = e->d_digests;
   ta.blocks_per_inst = e->blocks_per_inst; ta.dtrace_words_per_inst = e->dtrace_words_per_inst;
-  const bool expand = b->gate || b->lookup || b->spread || cks_dev;
+  const bool expand = b->gate || b->lookup || b->spread || cks_dev || b->compact_dict;
   ta.job_counter = expand ? S->d_counter : nullptr;
   ta.cks = cks_dev;
+  if (b->lookup_mult_dev) {
+    // bins are zeroed on the caller's stream before anything of this batch runs there (the expansion kernel adds to them)
+    const uint64_t mw = ((uint64_t)P.n_lookup_cols << P.cfg.lookup_bits) + ((uint64_t)P.cfg.spread_cols << P.cfg.limb_bits);
+    CUDA_TRY(cudaMemsetAsync(b->lookup_mult_dev, 0, b->n_instances * mw * 4, st));
+    if (b->mult_not_in_table_dev) CUDA_TRY(cudaMemsetAsync(b->mult_not_in_table_dev, 0, 4, st));
+  }
   if (timed) CUDA_TRY(cudaEventRecord(e->ev[0], ts));
   k_trace<<<(unsigned)((n_msgs + 63) / 64), 64, 0, ts>>>(ta);
   launches++;
@@ -1515,6 +1630,12 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     ja.n_inst = b->n_instances; ja.btrace = S->d_btrace; ja.dtrace = S->d_dtrace;
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
     ja.cks = cks_dev; ja.job_counter = S->d_counter; ja.only_digest = b->only_digest;
+    if (b->compact_dict) { ja.dict = (uint32_t*)b->compact_dict; ja.dict_inst_cells = P.dict_cells; }
+    if (b->lookup_mult_dev) {
+      ja.mult = b->lookup_mult_dev; ja.mult_bad = b->mult_not_in_table_dev; ja.usable_rows = b->mult_usable_rows;
+      ja.mult_words = ((uint64_t)P.n_lookup_cols << P.cfg.lookup_bits) + ((uint64_t)P.cfg.spread_cols << P.cfg.limb_bits);
+      ja.lookup_bits = P.cfg.lookup_bits; ja.limb_bits = P.cfg.limb_bits; ja.n_lookup_total = P.n_lookup; ja.n_limb_total = P.n_limb;
+    }
     uint64_t n_jobs = b->n_instances * (uint64_t)e->blocks_per_inst * P.n_block_parts;
     for (size_t c = P.n_block_parts; c < P.classes.size(); c++) n_jobs += (b->n_instances + P.classes[c].batch - 1) / P.classes[c].batch;
     unsigned grid = (unsigned)std::min<uint64_t>(n_jobs, (uint64_t)e->expand_ctas);
@@ -1529,7 +1650,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = (timed || overlap) ? 0 : 1;   // plain serialisation when kernels are timed individually
       lc.attrs = at; lc.numAttrs = 1;
-      CUDA_TRY(cudaLaunchKernelExC(&lc, e->variant.fn, args));
+      CUDA_TRY(cudaLaunchKernelExC(&lc, e->variant.fn[b->lookup_mult_dev ? 1 : (b->compact_dict ? 2 : 0)], args));
     }
     launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1654,3 +1775,6 @@ int h2sha_last_kernel_ms(h2sha_engine_t* e, float* trace_ms, float* expand_ms) {
 
 #include "lookup_prework.cuh"
 #include "batch_check.cuh"
+#include "export.cuh"
+
+void h2sha_free_compact_state(h2sha_compact_state* s) { delete s; }

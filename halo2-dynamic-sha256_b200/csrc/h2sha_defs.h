@@ -76,18 +76,27 @@ static inline uint32_t vm_operand_const(uint32_t idx) { return 1u | (idx << 1); 
 //   copy:  every cell is a 32-byte copy  scratch[src] -> its (column,row)  (CellEntry).
 // ---------------------------------------------------------------------------------------------
 struct CellEntry {
-  uint32_t v;  // src (16) | dst (16).  src = index into the warp's scratch table
+  uint32_t v;  // gate / lookup cells: src (16) | dst (16).  src = index into the warp's scratch table
+               // spread-column cells: src (8) | dst (10) | slot (8) | sh (6): slot / sh say where the limb's raw value sits in the
+               // unit's slots (width = limb bits), so that the table-row multiplicities can be counted while the cells are written
 };
 #define H2SHA_CE_SRC(e) ((e).v & 0xffffu)
 #define H2SHA_CE_DST(e) ((e).v >> 16)
+#define H2SHA_LE_SRC(e) ((e).v & 0xffu)
+#define H2SHA_LE_DST(e) (((e).v >> 8) & 0x3ffu)
+#define H2SHA_LE_SLOT(e) (((e).v >> 18) & 0xffu)
+#define H2SHA_LE_SH(e) ((e).v >> 26)
 enum { H2SHA_MAX_FILL_LIMIT = 256 };   // the actual limit is Config::max_fill (runtime, <= this)
 
 // Fill entry: how to materialise one distinct value (same packing as TmplEntry, dst = scratch slot) plus the weight of
-// the value in the gate checksum: it is carried by `cnt` gate cells of the chunk whose unit-relative offsets sum to `sumdst`.
+// the value in the gate checksum: it is carried by `cnt & 0xffff` gate cells of the chunk whose unit-relative offsets sum to
+// `sumdst`.  `cnt >> 16` = lookup-column cells of the chunk that carry the value (its multiplicity in the range lookup).
 struct alignas(16) FillEntry {
   uint32_t lo, hi;
   uint32_t cnt, sumdst;
 };
+#define H2SHA_FE_GATE_CNT(e) ((e).cnt & 0xffffu)
+#define H2SHA_FE_LK_CNT(e) ((e).cnt >> 16)
 
 // multipliers of the cell checksum hash (include/h2sha_b200.h: H2SHA_CK_M)
 static const uint32_t kCkM[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
@@ -110,6 +119,7 @@ struct UnitType {
   uint32_t prog_off, prog_len;   // VmIns
   uint32_t chunk_off, n_chunks;  // Chunk
   uint32_t gate_len, lk_len, limb_len;   // cells per instance (limb_len = 2 per limb)
+  uint32_t dict_len;                     // distinct values per instance = fill entries of all its chunks (compact hand-off)
 };
 
 // Input source of slot k of a unit instance u: trace[in_base + in_stride * u]; or the instance index u itself.
@@ -128,6 +138,7 @@ struct UnitGroup {
   uint32_t gate_base, gate_stride;   // gate-stream index of instance 0 relative to the job's gate base, and per-instance stride
   uint32_t lk_base, lk_stride;       // same for the lookup stream
   uint32_t limb_base, limb_stride;   // same for spread limbs
+  uint32_t dict_base;                // dictionary index of instance 0's first distinct value, relative to the job's dictionary base
   InputMap in[MAX_UNIT_INPUTS];
 };
 
@@ -174,6 +185,8 @@ struct DigestPlace {
   uint32_t gate_base, lk_base, limb_base;   // start of this digest's prologue
   uint32_t blk_gate_base, blk_lk_base, blk_limb_base;   // block 0 of this digest (after the one-time zero cell, if any)
   uint32_t blk_gate_stride, blk_lk_stride, blk_limb_stride;
+  uint32_t dict_base, dict_dig_len, dict_blk_len;   // compact hand-off: the digest's dictionary range starts at dict_base with the prologue /
+                                 // epilogue units (dict_dig_len values), followed by n_blocks x dict_blk_len values of its compressions
   uint32_t job_class;            // first digest-job class of this digest (block-job parts are classes 0 .. n_block_parts-1; a digest
                                  // whose slots exceed one stage is cut into several consecutive classes, JobClass::digest names the owner)
   uint32_t trace_words;          // digest-job trace words

@@ -68,6 +68,7 @@ struct GroupRec {
   std::string type;
   uint32_t count = 0, seen = 0;
   uint32_t gate_base = 0, gate_stride = 0, lk_base = 0, lk_stride = 0, limb_base = 0, limb_stride = 0;
+  uint32_t dict_base = 0;   // set in finalize: dictionary index of instance 0 relative to the job's dictionary base
   std::vector<InputMap> in;
   bool same_as(const GroupRec& o) const {
     if (type != o.type || count != o.count || gate_base != o.gate_base || gate_stride != o.gate_stride || lk_base != o.lk_base ||
@@ -1162,15 +1163,24 @@ class Builder {
         loc[vi] = free_slots[residue[vi]].back();
         free_slots[residue[vi]].pop_back();
       }
-      // gate-checksum weights of every distinct value
-      std::vector<uint32_t> cnt(nd, 0), sumdst(nd, 0);
+      // gate-checksum weights of every distinct value, and how many lookup-column cells carry it
+      std::vector<uint32_t> cnt(nd, 0), sumdst(nd, 0), lkcnt(nd, 0);
       uint32_t dmin = 0xffff, dmax = 0;
-      for (auto& pc : cur)
+      for (auto& pc : cur) {
+        const uint32_t vi = index.at(sym_key(pc.s));
         if (pc.kind == EV_GATE) {
-          uint32_t vi = index.at(sym_key(pc.s));
           cnt[vi]++; sumdst[vi] += pc.dst;
           dmin = std::min(dmin, pc.dst); dmax = std::max(dmax, pc.dst);
+        } else if (pc.kind == EV_LK) {
+          // the fused multiplicity count reads the raw value of a looked-up cell from its fill entry: a byte-table value or a
+          // plain (shifted) extract -- the only kinds the reference ever range-checks
+          const Sym& sy = order[vi];
+          const bool ok = (sy.kind == KIND_TABLE && sy.table == T_BYTE) || (sy.kind == KIND_GENERIC && !sy.neg);
+          if (!ok || resident[vi]) fail("a looked-up cell holds a constant, a negated or a signed value");
+          lkcnt[vi]++;
         }
+      }
+      for (uint32_t i2 = 0; i2 < nd; i2++) if (cnt[i2] > 0xffff || lkcnt[i2] > 0xffff) fail("chunk too large for the fill-entry counters");
       Chunk c{};
       c.fill_off = (uint32_t)P.fill.size();
       c.gate_dst_min = (uint16_t)dmin; c.gate_dst_max = (uint16_t)dmax;
@@ -1206,14 +1216,21 @@ class Builder {
           if (cls == 1) c.n_fill32++;
           c.n_fill++;
           TmplEntry te = tmpl_pack(loc[i2], sy.kind == KIND_TABLE ? table_index(sy) : 0, sy.slot, sy.sh, sy.w, sy.shl, sy.kind, sy.neg);
-          P.fill.push_back(FillEntry{te.lo, te.hi, cnt[i2], sumdst[i2]});
+          P.fill.push_back(FillEntry{te.lo, te.hi, cnt[i2] | (lkcnt[i2] << 16), sumdst[i2]});
         }
       }
       for (int kind = 0; kind < 3; kind++) {
         uint32_t off = (uint32_t)P.cells.size(), n = 0;
         for (auto& pc : cur) {
           if (pc.kind != kind) continue;
-          P.cells.push_back(CellEntry{loc[index.at(sym_key(pc.s))] | (pc.dst << 16)});
+          const uint32_t sl = loc[index.at(sym_key(pc.s))];
+          if (kind == EV_LIMB) {
+            // src (8) | dst (10) | slot (8) | sh (6): where the limb's raw value sits (dense: the extract itself; spread: its table index)
+            if (sl > 0xff || pc.dst > 0x3ff || pc.s.kind != KIND_TABLE || pc.s.w != cfg_.limb_bits) fail("spread-column cell does not fit its descriptor");
+            P.cells.push_back(CellEntry{sl | (pc.dst << 8) | ((uint32_t)pc.s.slot << 18) | ((uint32_t)pc.s.sh << 26)});
+          } else {
+            P.cells.push_back(CellEntry{sl | (pc.dst << 16)});
+          }
           n++;
         }
         if (kind == EV_GATE) { c.gate_off = off; c.gate_len = (uint16_t)n; }
@@ -1279,7 +1296,7 @@ class Builder {
       g.count = g.per_inst * batch;
       g.slot_base = slot_base;
       slot_base += g.count * (P.types[g.type].n_slots | 1u);
-      P.groups.push_back(g);
+      P.groups.push_back(g);   // g.dict_base was set by the caller (relative to the job's dictionary base)
     }
     jc.n_slots_total = slot_base;
     P.max_slots = std::max(P.max_slots, slot_base);
@@ -1293,7 +1310,7 @@ class Builder {
     jc.n_tasks = (uint32_t)ts.size();
     // phase-2 items, heaviest first
     jc.item_off = (uint32_t)P.items.size();
-    std::vector<std::pair<uint32_t, ItemDesc>> its;
+    std::vector<std::pair<uint32_t, std::pair<ItemDesc, uint32_t>>> its;
     for (uint32_t gi = 0; gi < groups.size(); gi++) {
       const UnitGroup& g = groups[gi];
       const UnitType& ut = P.types[g.type];
@@ -1307,11 +1324,13 @@ class Builder {
           d.lk_rel = g.lk_base + uu * g.lk_stride;
           d.limb_rel = g.limb_base + uu * g.limb_stride;
           d.slot_chunk = slot_off | ((ut.chunk_off + c) << 16) | (inst_off << 27);
-          its.push_back({chunk_cost(P.chunks[ut.chunk_off + c]), d});
+          uint32_t dict_rel = g.dict_base + uu * ut.dict_len;
+          for (uint32_t c2 = 0; c2 < c; c2++) dict_rel += P.chunks[ut.chunk_off + c2].n_fill;
+          its.push_back({chunk_cost(P.chunks[ut.chunk_off + c]), {d, dict_rel}});
         }
     }
     std::stable_sort(its.begin(), its.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
-    for (auto& it : its) P.items.push_back(it.second);
+    for (auto& it : its) { P.items.push_back(it.second.first); P.item_dict.push_back(it.second.second); }
     jc.n_items = (uint32_t)its.size();
     jc.n_trace_words = n_trace_words;
     P.max_trace_words = std::max(P.max_trace_words, n_trace_words * batch);
@@ -1324,12 +1343,55 @@ class Builder {
     ug.gate_base = g.gate_base + first * g.gate_stride; ug.gate_stride = g.gate_stride;
     ug.lk_base = g.lk_base + first * g.lk_stride; ug.lk_stride = g.lk_stride;
     ug.limb_base = g.limb_base + first * g.limb_stride; ug.limb_stride = g.limb_stride;
+    ug.dict_base = g.dict_base + first * P_->types[ug.type].dict_len;
     for (size_t i = 0; i < g.in.size(); i++) {
       ug.in[i] = g.in[i];
       if (ug.in[i].base >= 0) ug.in[i].base += g.in[i].stride * (int32_t)first;
       else ug.in[i].stride = (int32_t)first;  // instance-index input: value = stride + u
     }
     return ug;
+  }
+
+  // which dictionary entry (or resident constant) every cell of an instance copies: what the host-side expander of the compact
+  // hand-off needs, derived from the same fill / cell lists the kernel walks
+  void build_compact_map() {
+    Plan& P = *P_;
+    const uint32_t kUnset = 0xffffffffu;
+    P.map_gate.assign(n_gate_, kUnset); P.map_lookup.assign(n_lk_, kUnset); P.map_dense.assign(n_limb_, kUnset); P.map_spread.assign(n_limb_, kUnset);
+    auto map_unit = [&](const UnitType& ut, uint32_t gate0, uint32_t lk0, uint32_t limb0, uint32_t dict0) {
+      uint32_t doff = dict0;
+      std::vector<uint32_t> ent(cfg_.max_fill);
+      for (uint32_t c = 0; c < ut.n_chunks; c++) {
+        const Chunk& ch = P.chunks[ut.chunk_off + c];
+        std::fill(ent.begin(), ent.end(), kUnset);
+        for (uint32_t sl = 0; sl < P.resident.size(); sl++) ent[sl] = 0x80000000u | P.resident[sl];
+        for (uint32_t i = 0; i < ch.n_fill; i++) ent[H2SHA_TE_DST(P.fill[ch.fill_off + i])] = doff + i;
+        for (uint32_t i = 0; i < ch.gate_len; i++) { const CellEntry ce = P.cells[ch.gate_off + i]; P.map_gate[gate0 + H2SHA_CE_DST(ce)] = ent[H2SHA_CE_SRC(ce)]; }
+        for (uint32_t i = 0; i < ch.lk_len; i++) { const CellEntry ce = P.cells[ch.lk_off + i]; P.map_lookup[lk0 + H2SHA_CE_DST(ce)] = ent[H2SHA_CE_SRC(ce)]; }
+        for (uint32_t i = 0; i < ch.limb_len; i++) {
+          const CellEntry ce = P.cells[ch.limb_off + i];
+          const uint32_t n = limb0 + (H2SHA_LE_DST(ce) >> 1);
+          ((H2SHA_LE_DST(ce) & 1u) ? P.map_spread : P.map_dense)[n] = ent[H2SHA_LE_SRC(ce)];
+        }
+        doff += ch.n_fill;
+      }
+    };
+    auto map_class = [&](const ClassRec& c, uint32_t g0, uint32_t l0, uint32_t m0, uint32_t dict0) {
+      for (const GroupRec& g : c.groups) {
+        const UnitType& ut = P.types[type_idx_.at(g.type)];
+        for (uint32_t u = 0; u < g.count; u++)
+          map_unit(ut, g0 + g.gate_base + u * g.gate_stride, l0 + g.lk_base + u * g.lk_stride, m0 + g.limb_base + u * g.limb_stride, dict0 + g.dict_base + u * ut.dict_len);
+      }
+    };
+    for (size_t d = 0; d < P.digests.size(); d++) {
+      const DigestPlace& dp = P.digests[d];
+      map_class(class_recs_[1 + d], 0, 0, 0, dp.dict_base);
+      for (uint32_t j = 0; j < dp.n_blocks; j++)
+        map_class(class_recs_[0], dp.blk_gate_base + j * dp.blk_gate_stride, dp.blk_lk_base + j * dp.blk_lk_stride, dp.blk_limb_base + j * dp.blk_limb_stride,
+                  dp.dict_base + dp.dict_dig_len + j * dp.dict_blk_len);
+    }
+    for (auto* m : {&P.map_gate, &P.map_lookup, &P.map_dense, &P.map_spread})
+      for (uint32_t v : *m) if (v == kUnset) fail("compact map: a cell has no dictionary entry");
   }
 
   void finalize() {
@@ -1383,11 +1445,29 @@ class Builder {
       P.prog.insert(P.prog.end(), u.prog.begin(), u.prog.end());
       stat_cost_greedy_ = stat_cost_final_ = stat_cost_ideal_ = 0;
       build_chunks(u, &ut);
+      for (uint32_t c = 0; c < ut.n_chunks; c++) ut.dict_len += P.chunks[ut.chunk_off + c].n_fill;
       if (getenv("H2SHA_PLAN_STATS"))   // multi-chunk types run the chunking twice (see build_chunks): their numbers are doubled
         fprintf(stderr, "[plan] %-8s chunks %2u gate %4u lk %3u limb %3u | quarter-warp scratch accesses per unit: conflict-free %.1f greedy %.1f searched %.1f\n",
                 P.type_names[t].c_str(), ut.n_chunks, ut.gate_len, ut.lk_len, ut.limb_len, (double)stat_cost_ideal_ / stat_norm_,
                 (double)stat_cost_greedy_ / stat_norm_, (double)stat_cost_final_ / stat_norm_);
       P.types.push_back(ut);
+    }
+    // ---- compact hand-off: dictionary ranges.  Per digest: its prologue / epilogue units, then its compressions ----
+    {
+      std::vector<uint32_t> class_len(class_recs_.size(), 0);
+      for (size_t ci = 0; ci < class_recs_.size(); ci++)
+        for (GroupRec& g : class_recs_[ci].groups) {
+          g.dict_base = class_len[ci];
+          class_len[ci] += g.count * P.types[type_idx_.at(g.type)].dict_len;
+        }
+      uint32_t base = 0;
+      for (size_t d = 0; d < P.digests.size(); d++) {
+        P.digests[d].dict_base = base;
+        P.digests[d].dict_dig_len = class_len[1 + d];
+        P.digests[d].dict_blk_len = class_len[0];
+        base += class_len[1 + d] + P.digests[d].n_blocks * class_len[0];
+      }
+      P.dict_cells = base;
     }
     // ---- job classes: the block job is split into `block_parts` parts of roughly equal cell count ----
     P.max_slots = 0;
@@ -1472,6 +1552,7 @@ class Builder {
         flush();
       }
     }
+    if (cfg_.record_compact_map) build_compact_map();
     // ---- layout ----
     auto up8 = [](uint32_t x) { return (x + 7u) & ~7u; };   // column strides are multiples of 8 cells (256 B)
     P.n_gate_cols = (uint32_t)P.breaks.size();

@@ -23,6 +23,7 @@ struct Config {
   uint32_t spread_cols = 2;                       // SpreadConfig num_advice_columns
   uint32_t is_input_range_check = 1;
   uint32_t record_shape = 1;                      // also build selectors / copy constraints / fixed column
+  uint32_t record_compact_map = 0;                // also build the cell -> dictionary-entry map of the compact hand-off (host side)
   uint32_t block_parts = 3;                       // engine tuning: jobs per sha256_compression (load balance vs. overhead)
   uint32_t max_fill = 144;                        // engine tuning: distinct values per chunk (size of a warp's scratch table)
   uint32_t digest_batch = 0;                      // engine tuning: instances per digest job (0 = as many as fit, <= 32)
@@ -55,6 +56,7 @@ struct Plan {
   std::vector<CellEntry> cells;         // cell lists of all chunks
   std::vector<Chunk> chunks;
   std::vector<ItemDesc> items;          // phase-2 work items of all classes
+  std::vector<uint32_t> item_dict;      // per item: dictionary index of its chunk's first distinct value, relative to the job's dictionary base
   uint32_t n_block_parts = 1;
   std::vector<UnitGroup> groups;
   std::vector<WarpTask> tasks;
@@ -78,6 +80,12 @@ struct Plan {
   std::vector<uint32_t> lookup_cells;        // cells_to_lookup as gate-stream indices
   std::vector<uint32_t> limb_gate_dense, limb_gate_spread;
   std::vector<DigestHandles> handles;
+  // ---- compact hand-off (host only): which dictionary entry every cell copies.  Entry = index into the instance's dictionary of
+  // distinct values, or 0x80000000 | index into mont_table for the constants every warp keeps resident ----
+  uint32_t dict_cells = 0;                   // distinct values per instance
+  std::vector<uint32_t> map_gate;            // per gate-stream index
+  std::vector<uint32_t> map_lookup;          // per cells_to_lookup index
+  std::vector<uint32_t> map_dense, map_spread;   // per spread limb
   // ---- statistics ----
   uint64_t cells_per_instance() const { return (uint64_t)n_gate + n_lookup + 2ull * n_limb; }
 };

@@ -134,6 +134,15 @@ typedef struct {
   int32_t time_kernels;              /* 1: bracket each kernel with CUDA events on `stream` (h2sha_last_kernel_ms) */
   uint32_t only_digest;              /* 0: every digest() call of every instance; d + 1: only the cells digest() call d owns
                                         (h2sha_get_digest_ranges) are generated -- for a facade that assigns call by call */
+  uint32_t* lookup_mult_dev;         /* device [n_instances][mult_words_per_instance] u32 or NULL: the table-row multiplicities
+                                        h2sha_lookup_multiplicities would compute from the finished witness, counted here while the
+                                        cells are written (no second pass over HBM).  Needs gate, lookup and spread.            */
+  uint32_t mult_usable_rows;         /* rows every lookup is evaluated on (2^k - blinding factors - 1), for lookup_mult_dev     */
+  uint32_t* mult_not_in_table_dev;   /* device u32 or NULL: looked-up cells that are no table row (0 for an honest witness)     */
+  void* compact_dict;                /* device [n_instances][dict_cells_per_instance] Fr or NULL: the compact hand-off -- every DISTINCT
+                                        value of an instance once (3.7x fewer bytes than its cells); h2sha_get_compact_map says which
+                                        entry each cell copies, h2sha_expand_compact rebuilds the columns on the host.  gate / lookup /
+                                        spread may be NULL then (nothing but the dictionary is written)                         */
 } h2sha_batch_t;
 
 /* Replaces `digest` (lib.rs:71-349) for a whole batch: padding and length selection, the precomputed
@@ -155,6 +164,31 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* batch);
  * memory is pinned; any of the device buffers may be NULL (its columns are skipped). */
 int h2sha_export_instance(h2sha_engine_t* e, uint64_t instance, const void* gate, const void* lookup, const void* spread,
                           uint64_t* const* host_columns, uint32_t rows_per_column, void* stream);
+
+/* Prover hand-off of a whole batch: instances [first_instance, first_instance + n_instances) of the batch buffers to host memory
+ * laid out [instance][column][rows_per_column] Fr (column order as h2sha_export_instance; rows_per_column normally 2^k) with three
+ * strided copies in total (one per buffer kind) on `stream`; asynchronous when host_out is pinned.  Rows nobody assigns are not
+ * written: zero_fill != 0 clears host_out first (needed once per host buffer -- the shape is static).  NULL buffers are skipped. */
+int h2sha_export_batch(h2sha_engine_t* e, uint64_t first_instance, uint64_t n_instances, const void* gate, const void* lookup, const void* spread,
+                       void* host_out, uint32_t rows_per_column, int zero_fill, void* stream);
+
+/* ---- Compact hand-off: h2sha_batch_t.compact_dict holds every DISTINCT value of an instance once (~27 % of its cells, 3.7x fewer
+ * bytes over PCIe); which entry each cell copies is static (input-independent) and comes from h2sha_get_compact_map:
+ *   gate_map [n_gate_cells], lookup_map [n_lookup_cells], dense_map / spread_map [n_spread_limbs]: per gate-stream index /
+ *   cells_to_lookup index / spread limb, either an index into the instance's dictionary or 0x80000000 | index into `consts`
+ *   ([n_consts][4] u64 Montgomery: the few constants the kernel keeps resident instead of writing them per instance).
+ * h2sha_expand_compact rebuilds [instance][column][rows_per_column] host vectors (the layout of h2sha_export_batch) from a
+ * dictionary in host memory with n_threads host threads (0 = all cores): 32-byte copies only, no field arithmetic.  Both
+ * calls work on a plan-only engine (device = -1), i.e. on a prover box without a GPU. */
+typedef struct {
+  uint64_t dict_cells_per_instance, dict_bytes_per_instance;
+  uint64_t cells_per_instance;
+  uint32_t n_consts;
+} h2sha_compact_info_t;
+int h2sha_get_compact_info(const h2sha_engine_t* e, h2sha_compact_info_t* out);
+int h2sha_get_compact_map(h2sha_engine_t* e, uint32_t* gate_map, uint32_t* lookup_map, uint32_t* dense_map, uint32_t* spread_map, uint64_t* consts);
+int h2sha_expand_compact(h2sha_engine_t* e, const void* dict_host, uint64_t n_instances, void* host_out, uint32_t rows_per_column, int zero_fill,
+                         uint32_t n_threads);
 
 /* ---- Lookup-argument pre-work on the witness in HBM (the step after assignment in create_proof) --------------------
  * The chip has two kinds of lookups, neither with a selector (every usable row is looked up):

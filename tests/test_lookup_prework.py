@@ -284,3 +284,47 @@ def test_multiplicities_follow_widened_column_strides(pkg):
     a_w, s_w = wide.permute_lookup(m_w, 0, usable)
     assert bool((a_t == a_w).all()) and bool((s_t == s_w).all())
     tight.close(); wide.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [
+    dict(sizes=[64], n=48),                                                        # config 2 shape
+    dict(sizes=[128, 128], n=5),                                                   # the reference's TestCircuit: two digests per region
+    dict(sizes=[320], n=7, max_rows=9973),                                         # lookup column wraps: 2 lookup advice columns, wraps inside chunks
+    dict(sizes=[192], n=3, lookup_bits=9, num_bits_lookup=4, num_advice_columns=3),  # other table sizes, 3 spread column pairs (not a power of two)
+    dict(sizes=[64], n=4, lookup_bits=20, num_bits_lookup=2, num_advice_columns=1),
+], ids=lambda k: "x".join(map(str, k["sizes"])) + "_" + "_".join(f"{a}{b}" for a, b in k.items() if a not in ("sizes", "n")))
+def test_multiplicities_counted_while_the_cells_are_written(pkg, kw):
+    """h2sha_batch_t.lookup_mult_dev: the table-row multiplicities come out of the expansion kernel itself and are bit-identical to
+    the second pass over the finished witness (h2sha_lookup_multiplicities), which the tests above pin against the oracle."""
+    import torch
+    kw = dict(kw)
+    sizes, n = kw.pop("sizes"), kw.pop("n")
+    cfg = pkg.Sha256DynamicConfig.configure(sizes, device=0, **kw)
+    info = cfg.lookup_info()
+    usable = info["min_usable_rows"] + 11
+    rng = np.random.default_rng(9)
+    msgs = [[bytes(rng.integers(0, 256, int(rng.integers(0, s - 8)), dtype=np.uint8)) for s in sizes] for _ in range(n)]
+    blob, offs, lens = pkg.pack_messages(msgs)
+    gate, lookup, spread = cfg.alloc_outputs(n)
+    dev = gate.device
+    fused = torch.full((n, info["mult_words_per_instance"]), 123456, dtype=torch.int32, device=dev)   # must be overwritten, not accumulated into
+    bad = torch.full((1,), 77, dtype=torch.int32, device=dev)
+    for _ in range(2):   # twice: the bins are zeroed by every call
+        cfg.digest_batch_raw(n, blob.ctypes.data if blob.size else 0, False, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(),
+                             lookup_ptr=lookup.data_ptr(), spread_ptr=spread.data_ptr(), lookup_mult_ptr=fused.data_ptr(), mult_usable_rows=usable,
+                             mult_bad_ptr=bad.data_ptr(), stream=torch.cuda.current_stream(0).cuda_stream)
+    torch.cuda.synchronize()
+    second_pass, bad2 = cfg.lookup_multiplicities(pkg.BatchResult(None, None, gate, lookup, spread), usable)
+    assert int(bad.item()) == 0 and bad2 == 0
+    assert torch.equal(fused, second_pass), f"{int((fused != second_pass).sum())} bins differ"
+    assert int(fused.sum(dim=1)[0]) == usable * (info["n_range_lookups"] + info["n_spread_lookups"])
+    # argument checks
+    L = pkg.load_library()
+    with pytest.raises(pkg.EngineError):
+        cfg.digest_batch_raw(n, blob.ctypes.data if blob.size else 0, False, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(),
+                             lookup_mult_ptr=fused.data_ptr(), mult_usable_rows=usable)
+    with pytest.raises(pkg.EngineError):
+        cfg.digest_batch_raw(n, blob.ctypes.data if blob.size else 0, False, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(),
+                             lookup_ptr=lookup.data_ptr(), spread_ptr=spread.data_ptr(), lookup_mult_ptr=fused.data_ptr(), mult_usable_rows=10)
+    cfg.close()
