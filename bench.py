@@ -586,6 +586,53 @@ def main():
                                                  "prover would need); PCIe-bound, not the headline"}
         del h_gate, h_lookup, h_spread
 
+    # ---- the same hand-off in its compact form: the launch writes only the dictionary of distinct values (27 % of the cells), that
+    # is copied to pinned host memory, and the host rebuilds the columns with 32-byte copies (h2sha_expand_compact) ----
+    e2e_compact = None
+    if world == 1 and not args.no_witness_d2h:
+        try:
+            ci = cfg.compact_info()
+            d_dict = torch.empty((per_gpu, ci["dict_cells_per_instance"], 4), dtype=torch.int64, device=dev)
+            h_dict = torch.empty(d_dict.shape, dtype=torch.int64).pin_memory()
+
+            def step_compact():
+                cfg.digest_batch_raw(per_gpu, h_blob.data_ptr(), False, int(blob.size), offs, lens, None, digests_host_ptr=h_digests[0].data_ptr(),
+                                     checksums_host_ptr=h_cks[0].data_ptr(), compact_dict_ptr=d_dict.data_ptr(), stream=sp)
+                h_dict.copy_(d_dict, non_blocking=True)
+                stream.synchronize()
+
+            step_compact()
+            n_c = 6
+            t0 = time.perf_counter()
+            for _ in range(n_c):
+                step_compact()
+            dt_wire = (time.perf_counter() - t0) / n_c
+            assert (h_cks[0].numpy() == h_cks[1].numpy()).all(), "the compact launch changes the cell checksums"
+            # host-side expansion into [instance][column][2^k] vectors (what halo2's prover holds), on a slice that fits in host memory
+            k_rows = 1 << int(np.ceil(np.log2(max(lay.gate_col_rows, lay.lookup_col_rows, lay.spread_rows))))
+            n_x = int(max(1, min(per_gpu, (3 << 30) // (cfg.n_columns() * k_rows * 32))))
+            cores = os.cpu_count() or 1
+            h_cols = np.zeros((n_x, cfg.n_columns(), k_rows, 4), dtype=np.uint64)
+            cfg.expand_compact(h_dict[:n_x].numpy(), n_x, k_rows, out=h_cols, zero_fill=False)
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 2 or time.perf_counter() - t0 < 1.0:
+                cfg.expand_compact(h_dict[:n_x].numpy(), n_x, k_rows, out=h_cols, zero_fill=False); reps += 1
+            dt_x = (time.perf_counter() - t0) / reps / n_x
+            # bit-exactness of the whole chain on the slice: expander(dictionary) == the cells of the batch buffers
+            gate_h = gate[:n_x].cpu().numpy().view(np.uint64)
+            rg = min(k_rows, lay.gate_col_rows)
+            assert (h_cols[:, : lay.n_gate_cols, :rg] == gate_h[:, :, :rg]).all(), "expander(compact) differs from the gate cells"
+            e2e_compact = {"wire": {"value": blocks_per_launch / dt_wire, "unit": UNIT, "d2h_bytes_per_launch": n_msgs * 32 + per_gpu * 32 + h_dict.nbytes,
+                                    "launches": n_c, "note": "host messages -> h2sha_digest_batch(compact_dict only) -> dictionary in pinned host memory"},
+                           "expand_on_host": {"value": lay.n_blocks / dt_x, "unit": UNIT, "threads": cores, "instances": n_x, "rows_per_column": k_rows,
+                                              "note": "h2sha_expand_compact: dictionary -> [instance][column][2^k] Fr vectors, 32-byte copies only"},
+                           "dict_bytes_per_instance": ci["dict_bytes_per_instance"], "cell_bytes_per_instance": lay.cells_per_instance * 32,
+                           "ratio": lay.cells_per_instance * 32 / ci["dict_bytes_per_instance"]}
+            del d_dict, h_dict, h_cols
+        except Exception as ex:
+            e2e_compact = {"error": str(ex)}
+
     # ---- correctness inside the bench: digests vs hashlib for all, cells vs oracle on a sample, gather over NCCL ----
     import hashlib
     last = (args.steps * L - 1) % RING          # result buffers of the last end-to-end launch
@@ -719,6 +766,19 @@ def main():
                     a_.record(stream); mult, bad = cfg.lookup_multiplicities(rv, usable); b_.record(stream); b_.synchronize()
                     tm.append(a_.elapsed_time(b_))
                 assert bad == 0, "witness cells outside the lookup tables"
+                # the same multiplicities counted by the expansion kernel itself while it writes the cells (no second pass over HBM)
+                fused = torch.empty_like(mult); fbad = torch.zeros(1, dtype=torch.int32, device=dev)
+                tf, tplain = [], []
+                for _ in range(6):
+                    cfg.digest_batch_raw(n_mult, d_blob.data_ptr(), True, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(), lookup_ptr=lookup.data_ptr(),
+                                         spread_ptr=spread.data_ptr(), lookup_mult_ptr=fused.data_ptr(), mult_usable_rows=usable, mult_bad_ptr=fbad.data_ptr(),
+                                         stream=sp, time_kernels=True)
+                    tf.append(cfg.last_kernel_ms()[1])
+                    cfg.digest_batch_raw(n_mult, d_blob.data_ptr(), True, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(), lookup_ptr=lookup.data_ptr(),
+                                         spread_ptr=spread.data_ptr(), stream=sp, time_kernels=True)
+                    tplain.append(cfg.last_kernel_ms()[1])
+                assert torch.equal(fused, mult) and int(fbad.item()) == 0, "fused multiplicities differ from the second pass"
+                fused_extra_ms = float(np.median(tf[1:]) - np.median(tplain[1:]))
                 n_perm = min(n_mult, 64)
                 tp = []
                 for _ in range(4):
@@ -726,12 +786,14 @@ def main():
                     a_.record(stream); pa, ps = cfg.permute_lookup(mult[:n_perm], 0, usable); b_.record(stream); b_.synchronize()
                     tp.append(a_.elapsed_time(b_))
                 read_b = n_mult * (lay.n_lookup_cells + 2 * lay.n_spread_limbs) * 32
-                prework = {"usable_rows": usable, "multiplicities_ms": min(tm[1:]), "multiplicities_instances": n_mult,
+                prework = {"usable_rows": usable, "multiplicities_fused_extra_ms": fused_extra_ms, "k_expand_with_multiplicities_ms": float(np.median(tf[1:])),
+                           "k_expand_plain_ms": float(np.median(tplain[1:])),
+                           "multiplicities_second_pass_ms": min(tm[1:]), "multiplicities_instances": n_mult,
                            "multiplicities_read_gbs": read_b / (min(tm[1:]) * 1e-3) / 1e9,
                            "permute_range_lookup_ms": min(tp[1:]), "permute_instances": n_perm,
                            "permute_write_gbs": n_perm * usable * 64 / (min(tp[1:]) * 1e-3) / 1e9,
                            "note": "h2sha_lookup_multiplicities / h2sha_permute_lookup incl. their memsets, allocation of the outputs and one host sync"}
-                del mult, pa, ps
+                del mult, pa, ps, fused
             del res_view
         except Exception as ex:
             prework = {"error": str(ex)}
@@ -797,6 +859,7 @@ def main():
             "e2e_sync_every_launch": e2e_sync,
             "e2e_two_handles": e2e_two,
             "e2e_witness_to_host": e2e_witness,
+            "e2e_witness_to_host_compact": e2e_compact,
             "gpu_launches": 2 * args.steps * L,
             "kernels_ms": {"k_trace": trace_ms, "k_expand": expand_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

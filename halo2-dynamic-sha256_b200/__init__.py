@@ -78,6 +78,7 @@ class _LookupInfo(C.Structure):
 
 
 _lib = None
+_OLD_OK = bool(os.environ.get("TUNE_LIB"))   # tools/tune.py A/B runs load the library of an earlier revision, which lacks the newer entry points
 
 
 def load_library():
@@ -88,34 +89,45 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). There is no CPU fallback.")
     L = C.CDLL(LIB_PATH)
-    L.h2sha_create.restype = C.c_int
-    L.h2sha_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
-    L.h2sha_destroy.argtypes = [C.c_void_p]
-    L.h2sha_last_error.restype = C.c_char_p
-    L.h2sha_get_layout.argtypes = [C.c_void_p, C.POINTER(_Layout)]
-    L.h2sha_get_breaks.argtypes = [C.c_void_p, C.c_void_p]
-    L.h2sha_get_handles.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.h2sha_get_digest_ranges.argtypes = [C.c_void_p, C.c_void_p]
-    L.h2sha_get_shape.argtypes = [C.c_void_p] + [C.c_void_p] * 6
-    L.h2sha_get_lookup_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
-    L.h2sha_digest_batch.argtypes = [C.c_void_p, C.POINTER(_Batch)]
-    L.h2sha_export_instance.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]
-    L.h2sha_export_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
-    L.h2sha_get_compact_info.argtypes = [C.c_void_p, C.POINTER(_CompactInfo)]
-    L.h2sha_get_compact_map.argtypes = [C.c_void_p] + [C.c_void_p] * 5
-    L.h2sha_expand_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32]
-    L.h2sha_get_lookup_info.argtypes = [C.c_void_p, C.POINTER(_LookupInfo)]
-    L.h2sha_lookup_multiplicities.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.h2sha_permute_lookup.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.h2sha_check_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.h2sha_gather.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.h2sha_zero_outputs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-    L.h2sha_debug_mont_from_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-    L.h2sha_debug_mont_from_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-    L.h2sha_debug_store_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-    L.h2sha_debug_int_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p]
-    L.h2sha_last_launch_count.argtypes = [C.c_void_p]
-    L.h2sha_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+
+    def sig(name, argtypes=None, restype=None):
+        f = getattr(L, name, None)
+        if f is None:
+            if _OLD_OK:   # an earlier revision's library (A/B timing): it simply lacks the newer entry points
+                return
+            raise ImportError(f"{LIB_PATH} does not export {name}: rebuild it (python __graft_entry__.py)")
+        if argtypes is not None:
+            f.argtypes = argtypes
+        if restype is not None:
+            f.restype = restype
+
+    sig("h2sha_create", [C.POINTER(_Config), C.POINTER(C.c_void_p)], C.c_int)
+    sig("h2sha_destroy", [C.c_void_p])
+    sig("h2sha_last_error", None, C.c_char_p)
+    sig("h2sha_get_layout", [C.c_void_p, C.POINTER(_Layout)])
+    sig("h2sha_get_breaks", [C.c_void_p, C.c_void_p])
+    sig("h2sha_get_handles", [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p])
+    sig("h2sha_get_digest_ranges", [C.c_void_p, C.c_void_p])
+    sig("h2sha_get_shape", [C.c_void_p] + [C.c_void_p] * 6)
+    sig("h2sha_get_lookup_tables", [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)])
+    sig("h2sha_digest_batch", [C.c_void_p, C.POINTER(_Batch)])
+    sig("h2sha_export_instance", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p])
+    sig("h2sha_export_batch", [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p])
+    sig("h2sha_get_compact_info", [C.c_void_p, C.POINTER(_CompactInfo)])
+    sig("h2sha_get_compact_map", [C.c_void_p] + [C.c_void_p] * 5)
+    sig("h2sha_expand_compact", [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32])
+    sig("h2sha_get_lookup_info", [C.c_void_p, C.POINTER(_LookupInfo)])
+    sig("h2sha_lookup_multiplicities", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p])
+    sig("h2sha_permute_lookup", [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+    sig("h2sha_check_batch", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+    sig("h2sha_gather", [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+    sig("h2sha_zero_outputs", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p])
+    sig("h2sha_debug_mont_from_u64", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p])
+    sig("h2sha_debug_mont_from_u32", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p])
+    sig("h2sha_debug_store_probe", [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p])
+    sig("h2sha_debug_int_probe", [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p])
+    sig("h2sha_last_launch_count", [C.c_void_p])
+    sig("h2sha_last_kernel_ms", [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)])
     _lib = L
     return L
 
