@@ -127,7 +127,10 @@ struct PermuteArgs {
   const uint32_t* vals;        // [n_vals][8]: Montgomery value at each sorted position, or null (value = position, range table)
   uint32_t n_vals, usable_rows;
   uint32_t* scan;              // workspace [n_inst][3][n_vals]: start | distinct-before | leftover-before   (+ [n_inst] totals after)
-  uint32_t* totals;            // [n_inst][2]: distinct inputs, sum of multiplicities
+  uint32_t* totals;            // [n_inst][4]: distinct inputs, sum of multiplicities, m[first sorted row], leftover copies of the first sorted row
+  // identity order only (range table): the two searches of the fill kernel inverted by the scan kernel --
+  uint32_t* vrow;              // [n_inst][usable_rows]: sorted position of the value in row r of A', for r >= m[0] (rows below are the run of 0)
+  uint32_t* llist;             // [n_inst][n_vals]: the unused table rows > 0 in increasing order (leftover element j >= lf0 is llist[j - lf0])
   uint32_t* errors;            // may be null
   uint64_t* out_input;         // [n_inst][usable_rows] Fr
   uint64_t* out_table;
@@ -203,10 +206,29 @@ __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
     } else if (k < A.n_vals) {
       start[k] = ex[0]; dpre[k] = ex[1]; lpre[k] = ex[2];
     }
+    if (A.vrow && A.order == nullptr) {
+      // inverse maps for the fill kernel (identity order: sorted position == table row).  Position 0 is implicit in both:
+      // its run is rows [0, m[0]) of A' and its leftover copies are elements [0, lf0) of the leftover sequence.
+      uint32_t* vr = A.vrow + (uint64_t)inst * A.usable_rows;
+      uint32_t* ll = A.llist + (uint64_t)inst * A.n_vals;
+      const uint32_t lf0 = 1u + pad - (m[0] ? 1u : 0u);
+      uint32_t st_k = ex[0], lp_k = ex[2];
+#pragma unroll
+      for (uint32_t q = 0; q < 4; q++) {
+        if (q < per && k + q < A.n_vals && k + q > 0) {
+          for (uint32_t r = 0; r < mk[q]; r++) vr[st_k + r] = k + q;
+          if (lf[q]) ll[lp_k - lf0] = k + q;   // leftover element j >= lf0 of the sequence is ll[j - lf0]
+        }
+        st_k += mk[q]; lp_k += lf[q];
+      }
+    }
   }
   if (tid == 0) {
-    A.totals[2 * inst] = base[1];
-    A.totals[2 * inst + 1] = base[0];
+    A.totals[4 * inst] = base[1];
+    A.totals[4 * inst + 1] = base[0];
+    const uint32_t m_first = m[A.order ? A.order[0] : 0];
+    A.totals[4 * inst + 2] = m_first;
+    A.totals[4 * inst + 3] = 1u + ((A.order ? A.order[0] : 0u) == 0u ? pad : 0u) - (m_first ? 1u : 0u);
     if (base[0] != A.usable_rows && A.errors) atomicAdd(A.errors, 1u);   // multiplicities do not cover the usable rows
   }
 }
@@ -239,14 +261,35 @@ __global__ void __launch_bounds__(256) k_permute_fill(const PermuteArgs A) {
   const uint32_t* start = A.scan + (uint64_t)inst * 3 * A.n_vals;
   const uint32_t* dpre = start + A.n_vals;
   const uint32_t* lpre = dpre + A.n_vals;
-  const uint32_t n_distinct = A.totals[2 * inst];
-  if (A.totals[2 * inst + 1] != A.usable_rows) return;   // inconsistent multiplicities: reported by the scan kernel
+  const uint32_t n_distinct = A.totals[4 * inst];
+  if (A.totals[4 * inst + 1] != A.usable_rows) return;   // inconsistent multiplicities: reported by the scan kernel
   const uint32_t n_rep = A.usable_rows - n_distinct;
+  uint32_t* out_a = reinterpret_cast<uint32_t*>(A.out_input) + (uint64_t)inst * A.usable_rows * 8;
+  uint32_t* out_s = reinterpret_cast<uint32_t*>(A.out_table) + (uint64_t)inst * A.usable_rows * 8;
+  if (A.vrow && A.order == nullptr) {
+    // identity order (range table): the scan kernel has inverted both searches.  Rows below m[0] are the run of value 0 (the
+    // never-assigned rows: almost all of them), whose repeated rows take leftover elements with ONE dependent load.
+    const uint32_t m0 = A.totals[4 * inst + 2], lf0 = A.totals[4 * inst + 3];
+    const uint32_t* vr = A.vrow + (uint64_t)inst * A.usable_rows;
+    const uint32_t* ll = A.llist + (uint64_t)inst * A.n_vals;
+    for (uint32_t row = blockIdx.x * 256u + threadIdx.x; row < A.usable_rows; row += gridDim.x * 256u) {
+      uint32_t k = 0, st = 0, dp = 0;
+      if (row >= m0) { k = __ldg(vr + row); st = __ldg(start + k); dp = __ldg(dpre + k); }
+      uint32_t x[8];
+      permuted_value(A, k, x);
+      store_cell2(out_a + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
+      if (row != st) {
+        const uint32_t j = n_rep - 1u - (row - dp - 1u);
+        const uint32_t w = j < lf0 ? 0u : __ldg(ll + (j - lf0));
+        permuted_value(A, w, x);
+      }
+      store_cell2(out_s + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
+    }
+    return;
+  }
   const uint32_t stride = max(1u, A.n_vals >> 8), n_coarse = A.n_vals / stride;
   for (uint32_t i = threadIdx.x; i < n_coarse; i += 256) { s_start[i] = __ldg(start + i * stride); s_lpre[i] = __ldg(lpre + i * stride); }
   __syncthreads();
-  uint32_t* out_a = reinterpret_cast<uint32_t*>(A.out_input) + (uint64_t)inst * A.usable_rows * 8;
-  uint32_t* out_s = reinterpret_cast<uint32_t*>(A.out_table) + (uint64_t)inst * A.usable_rows * 8;
   for (uint32_t row = blockIdx.x * 256u + threadIdx.x; row < A.usable_rows; row += gridDim.x * 256u) {
     const uint32_t c = last_leq(s_start, 0, n_coarse, row) * stride;
     const uint32_t k = last_leq(start, c, c + stride, row);
@@ -386,9 +429,10 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   // workspace: scans + totals of one chunk of instances (the chunks run one after the other on `stream` and share it)
   if (n_vals > (1u << 22)) return set_err(H2SHA_EINVAL, "lookup table too large for the permutation workspace (lookup_bits > 22)");
   // instances per pass: at most `lkchunk` (default 256) and at most ~1 GB of scans
-  const uint64_t by_mem = std::max<uint64_t>(1, (1ull << 30) / (3ull * n_vals * 4));
+  const uint64_t per_inst_words = 3ull * n_vals + 4 + (is_range ? (uint64_t)usable_rows + n_vals : 0);   // scans, totals, inverse maps (identity order)
+  const uint64_t by_mem = std::max<uint64_t>(1, (1ull << 30) / (per_inst_words * 4));
   const uint64_t chunk = std::min<uint64_t>(std::min<uint64_t>(n_instances, by_mem), (uint64_t)std::max(1, tune_value("lkchunk", 256)));
-  const uint64_t need = chunk * (3ull * n_vals + 2) * 4;
+  const uint64_t need = chunk * per_inst_words * 4;
   if (need > e->lk_ws_bytes) {
     cudaFree(e->d_lk_ws); e->d_lk_ws = nullptr; e->lk_ws_bytes = 0;
     CUDA_TRY(cudaMalloc(&e->d_lk_ws, need));
@@ -399,6 +443,7 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   A.mult = mult_dev + (is_range ? (uint64_t)lookup_idx * n_vals : ((uint64_t)n_range << G.lookup_bits) + (uint64_t)(lookup_idx - n_range) * n_vals);
   A.n_vals = n_vals; A.usable_rows = usable_rows;
   A.scan = e->d_lk_ws; A.totals = e->d_lk_ws + chunk * 3ull * n_vals;
+  if (is_range && tune_value("lkinv", 1)) { A.vrow = A.totals + chunk * 4; A.llist = A.vrow + chunk * (uint64_t)usable_rows; }
   A.errors = errors_dev;
   A.out_input = (uint64_t*)permuted_input_dev; A.out_table = (uint64_t*)permuted_table_dev;
   if (is_range) {
