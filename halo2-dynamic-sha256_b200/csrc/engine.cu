@@ -84,12 +84,11 @@ struct JobArgs {
   unsigned long long* cks;  // [n_inst][4] or null
   unsigned long long* job_counter;
   uint32_t only_digest;     // 0: all; d + 1: only the jobs of digest() call d
-  // table-row multiplicities of the two kinds of lookups, counted while the cells are written (null: not wanted)
-  uint32_t* mult;           // [n_inst][mult_words]: range lookups [n_lookup_cols][2^lookup_bits], then spread lookups [spread_cols][2^limb_bits]
-  uint32_t* mult_bad;       // cells that are no table row (null: not counted)
-  uint64_t mult_words;
-  uint32_t usable_rows;     // rows every lookup is evaluated on: never-assigned rows count as table row 0
-  uint32_t lookup_bits, limb_bits, n_lookup_total, n_limb_total;
+  // lookup multiplicities (MODE 1): the raw value of every looked-up cell and of every dense spread limb, written next to the
+  // cells (13.5 KB + 2 KB per block instead of a second pass over 371 KB of Montgomery cells); k_mult_from_raw bins them
+  uint32_t* lookup_raw;     // [n_inst][n_lookup_total] in cells_to_lookup order; 0xffffffff = a value that does not fit 32 bits
+  uint8_t* dense_raw;       // [n_inst][n_limb_total]
+  uint32_t limb_bits, n_lookup_total, n_limb_total;
   // compact hand-off: every DISTINCT value of an instance, once (null: not wanted)
   uint32_t* dict;           // [n_inst][dict_inst_cells] Fr as 8 x u32
   uint64_t dict_inst_cells;
@@ -423,9 +422,10 @@ __global__ void __launch_bounds__(64) k_trace(TraceArgs A) {
 // ---------------------------------------------------------------------------------------------------
 // per-consumer-warp scratch of phase 2: Montgomery values of the chunk's distinct non-constant cells (low / high
 // 16 bytes in separate arrays so that random 128-bit reads spread over all bank groups) + their checksum hashes
-struct WarpScratch {   // runtime-sized: lo[max_fill] | hi[max_fill]; slots [0, n_resident) hold the resident constants
+struct WarpScratch {   // runtime-sized: lo[max_fill] | hi[max_fill] (| raw[max_fill] in MODE 1); slots [0, n_resident) hold the resident constants
   uint4* lo;
   uint4* hi;
+  uint32_t* raw;         // MODE 1: raw value of the looked-up distinct values of the chunk
 };
 // job descriptor a producer warp leaves in its stage
 struct StageDesc {
@@ -608,16 +608,8 @@ __device__ __forceinline__ void flush_checksums(unsigned long long* cks, uint64_
   }
 }
 
-// one looked-up value with multiplicity `cnt` -> its bin of the range lookup (a value outside the table is counted as bad, not binned)
-__device__ __forceinline__ void count_range(uint32_t* bins, uint32_t* bad, uint64_t raw, uint32_t cnt, uint32_t lookup_bits) {
-  if ((raw >> lookup_bits) == 0) atomicAdd(&bins[(uint32_t)raw], cnt);
-  else if (bad) atomicAdd(bad, cnt);
-}
-
-// Warp-specialised persistent kernel: NPROD producer warps run phase 1 (job fetch, trace load, slot programs) into
-// their own stage buffer; NCONS consumer warps run phase 2 (fill + copy) stage after stage.  Stages are handed over
-// with mbarriers, so no warp ever waits at a CTA-wide barrier inside the job loop.
-// MODE 0: cells (+ checksums); 1: also count the lookup multiplicities (A.mult); 2: also write the dictionary of distinct values
+// MODE 0: cells (+ checksums); 1: also write the raw values of the looked-up cells (A.lookup_raw / A.dense_raw: the input of the
+// multiplicity kernel); 2: also write the dictionary of distinct values
 // (A.dict).  Separate instantiations: the extra code costs registers the plain path (80 per thread at 768 threads) does not have.
 template <int NCONS, int NPROD, int MODE>
 __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPlan P, const JobArgs A) {
@@ -713,21 +705,6 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
         lk0 = dd.dp.blk_lk_base + jb * dd.dp.blk_lk_stride;
         limb0 = dd.dp.blk_limb_base + jb * dd.dp.blk_limb_stride;
         dict0 = dd.dp.dict_base + dd.dp.dict_dig_len + jb * dd.dp.dict_blk_len;
-        if (MULT && cls == 0 && r == 0) {
-          // once per instance: the never-assigned rows of every lookup input column hold 0 = table row 0 of either table
-          uint32_t* mi = A.mult + inst * A.mult_words;
-          for (uint32_t c = lane; c < P.n_lookup_cols + P.spread_cols; c += 32) {
-            if (c < P.n_lookup_cols) {
-              const uint32_t first = c * P.max_rows;
-              const uint32_t used = A.n_lookup_total > first ? min(P.max_rows, A.n_lookup_total - first) : 0u;
-              if (A.usable_rows > used) atomicAdd(&mi[(uint64_t)c << A.lookup_bits], A.usable_rows - used);
-            } else {
-              const uint32_t cc = c - P.n_lookup_cols;
-              const uint32_t used = A.n_limb_total > cc ? (A.n_limb_total - cc + P.spread_cols - 1) / P.spread_cols : 0u;
-              if (A.usable_rows > used) atomicAdd(&mi[((uint64_t)P.n_lookup_cols << A.lookup_bits) + ((uint64_t)cc << A.limb_bits)], A.usable_rows - used);
-            }
-          }
-        }
         const uint32_t* tr_src = A.btrace + (uint64_t)r * A.n_inst + inst;
         const uint64_t tr_stride = (uint64_t)P.blocks_per_inst * A.n_inst;
         tr_words = TR_BLOCK_WORDS;
@@ -796,6 +773,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     uint8_t* base = smem + P.off_scratch + (size_t)warp * P.scratch_bytes;
     ws.lo = reinterpret_cast<uint4*>(base);
     ws.hi = ws.lo + P.max_fill;
+    ws.raw = reinterpret_cast<uint32_t*>(ws.hi + P.max_fill);   // only inside the scratch of a MODE 1 launch (larger scratch_bytes)
     for (uint32_t i = lane; i < P.n_resident; i += 32) { ws.lo[i] = s_table_lo[s_resident[i]]; ws.hi[i] = s_table_hi[s_resident[i]]; }
     __syncwarp();
   }
@@ -850,19 +828,6 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       // checksum weight of a value carried by cnt cells whose offsets sum to sumdst: sum (2*pos+1) = cnt*w0 + 2*sumdst
       const unsigned long long w0 = straddle ? 0ull : (unsigned long long)(2u * (g_lo + off0) + 1u);
       const unsigned long long w1 = straddle ? 0ull : 2ull;
-      // ---- lookup multiplicities: the chunk's looked-up cells all lie in one lookup column unless the column wraps inside the
-      // chunk (then they are counted cell by cell after the fill) ----
-      [[maybe_unused]] uint32_t* mult_inst = nullptr;
-      [[maybe_unused]] uint32_t* mult_range = nullptr;
-      [[maybe_unused]] bool lk_wrap_inside = false;
-      if constexpr (MULT) mult_inst = A.mult + inst * A.mult_words;
-      if (MULT && ch.lk_len) {
-        const uint32_t l_first = lk0 + item.lk_rel + H2SHA_CE_DST(s_cells[ch.lk_off]);
-        const uint32_t l_last = lk0 + item.lk_rel + H2SHA_CE_DST(s_cells[ch.lk_off + ch.lk_len - 1]);
-        const uint32_t colf = l_first / P.max_rows;
-        lk_wrap_inside = l_last / P.max_rows != colf;
-        if (!lk_wrap_inside) mult_range = mult_inst + ((uint64_t)colf << A.lookup_bits);
-      }
       // ---- compact hand-off: the chunk's distinct values also go to the instance's dictionary, fill entry i -> entry dict_chunk + i ----
       [[maybe_unused]] uint32_t* dict_chunk = nullptr;
       if constexpr (DICT) dict_chunk = A.dict + (inst * A.dict_inst_cells + desc->dict0 + s_item_dict[jc.item_off + it]) * 8;
@@ -875,7 +840,7 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           uint32_t raw;
           const uint32_t h = fill_table(e, slots, s_table_lo, s_table_hi, ws, &raw, DICT ? dict_chunk + (uint64_t)i * 8 : nullptr);
           ck_g += (unsigned long long)h * (H2SHA_FE_GATE_CNT(e) * w0 + e.sumdst * w1);
-          if constexpr (MULT) { if (mult_range && H2SHA_FE_LK_CNT(e)) count_range(mult_range, A.mult_bad, raw, H2SHA_FE_LK_CNT(e), A.lookup_bits); }
+          if constexpr (MULT) { if (H2SHA_FE_LK_CNT(e)) ws.raw[H2SHA_TE_DST(e)] = raw; }
         }
         for (uint32_t i0 = n_tab; i0 < n_all; i0 += 32) {
           const uint32_t i = i0 + lane;
@@ -885,30 +850,12 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           const uint32_t h = fill_generic(e, slots, ws, active, &raw, DICT ? dict_chunk + (uint64_t)i * 8 : nullptr);
           if (active) {
             ck_g += (unsigned long long)h * (H2SHA_FE_GATE_CNT(e) * w0 + e.sumdst * w1);
-            if constexpr (MULT) { if (mult_range && H2SHA_FE_LK_CNT(e)) count_range(mult_range, A.mult_bad, raw, H2SHA_FE_LK_CNT(e), A.lookup_bits); }
+            if constexpr (MULT) { if (H2SHA_FE_LK_CNT(e)) ws.raw[H2SHA_TE_DST(e)] = (raw >> 32) ? 0xffffffffu : (uint32_t)raw; }
           }
         }
         if (lane == 0 && !straddle) ck_g += ch.res_a + ch.res_b * w0;
       }
       __syncwarp();
-      if (MULT && lk_wrap_inside) {
-        // rare (once per lookup-column wrap): per fill entry, count the chunk's lookup cells that carry it on either side of the wrap
-        const FillEntry* fl = s_fill + ch.fill_off;
-        const uint32_t l_lo2 = lk0 + item.lk_rel;
-        for (uint32_t i = lane; i < ch.n_fill; i += 32) {
-          const FillEntry e = fl[i];
-          if (!H2SHA_FE_LK_CNT(e)) continue;
-          const uint64_t sv = slots[H2SHA_TE_SLOT(e)];
-          uint64_t raw = extract(sv, H2SHA_TE_SH(e), H2SHA_TE_W(e));
-          if (H2SHA_TE_KIND(e) != KIND_TABLE) raw <<= H2SHA_TE_SHL(e);
-          for (uint32_t k2 = 0; k2 < ch.lk_len; k2++) {
-            const CellEntry ce = s_cells[ch.lk_off + k2];
-            if (H2SHA_CE_SRC(ce) != H2SHA_TE_DST(e)) continue;
-            const uint32_t col = (l_lo2 + H2SHA_CE_DST(ce)) / P.max_rows;
-            count_range(mult_inst + ((uint64_t)col << A.lookup_bits), A.mult_bad, raw, 1u, A.lookup_bits);
-          }
-        }
-      }
       // ---- copy: gate cells ----
       if (ch.gate_len && (gate_out || (straddle && A.cks))) {   // nothing to do when only the dictionary / checksums of a non-straddling chunk are wanted
         const CellEntry* cells = s_cells + ch.gate_off;
@@ -965,14 +912,13 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           const uint32_t li = l_lo + H2SHA_CE_DST(ce);
           const uint32_t pos = li + ((li >= wrap) ? loff1 : loff0);
           if (lk_out) store_cell2(lk_out + (uint64_t)pos * 8, lo, hi);
+          if constexpr (MULT) A.lookup_raw[inst * A.n_lookup_total + li] = ws.raw[src];
           ck_l += (unsigned long long)hash8(lo, hi) * (unsigned long long)(2u * pos + 1u);
         }
       }
       // ---- spread-table columns: limb n -> column n % cols, row n / cols (spread.rs:202,228-231); dense then spread ----
       if (ch.limb_len && (sp_out || A.cks || MULT)) {
         const uint32_t m_lo = limb0 + item.limb_rel;
-        [[maybe_unused]] uint32_t* mult_spread = nullptr;
-        if constexpr (MULT) mult_spread = mult_inst + ((uint64_t)P.n_lookup_cols << A.lookup_bits);
         for (uint32_t i = lane; i < ch.limb_len; i += 32) {
           const CellEntry ce = s_cells[ch.limb_off + i];
           const uint32_t src = H2SHA_LE_SRC(ce);
@@ -981,9 +927,8 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
           uint32_t row, col;
           if (P.spread_cols_shift >= 0) { row = n >> P.spread_cols_shift; col = n & (P.spread_cols - 1u); }
           else { row = n / P.spread_cols; col = n - row * P.spread_cols; }
-          // the (dense, spread) pair of limb n is row `dense` of the spread table: count it once, with the dense cell
-          if (MULT && which == 0)
-            atomicAdd(&mult_spread[((uint64_t)col << A.limb_bits) + (uint32_t)extract(slots[H2SHA_LE_SLOT(ce)], H2SHA_LE_SH(ce), A.limb_bits)], 1u);
+          // the (dense, spread) pair of limb n is row `dense` of the spread table: its raw dense value goes to the multiplicity kernel
+          if (MULT && which == 0) A.dense_raw[inst * A.n_limb_total + n] = (uint8_t)extract(slots[H2SHA_LE_SLOT(ce)], H2SHA_LE_SH(ce), A.limb_bits);
           const uint32_t pos = (which * P.spread_cols + col) * P.spread_rows + row;
           if (sp_out) store_cell2(sp_out + (uint64_t)pos * 8, lo, hi);
           ck_s += (unsigned long long)hash8(lo, hi) * (unsigned long long)(2u * pos + 1u);
@@ -1006,6 +951,48 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
     printf("E cta %3d warp %2d: done at +%llu ns, waited %llu ns in %u waits\n", blockIdx.x, warp, t - dbg_t2, dbg_wait, dbg_nwait);
   }
 #endif
+}
+
+// Table-row multiplicities of one instance from the raw values k_expand<.., 1> left next to the cells: one CTA zeroes the
+// instance's bins (258 KB for a 16-bit range table: coalesced, and L2-resident for the atomics that follow), then bins the
+// 3.4 k looked-up values and 2 k dense limbs per block.  Never-assigned rows of every lookup input column hold 0 = table row 0.
+struct MultArgs {
+  const uint32_t* lookup_raw;
+  const uint8_t* dense_raw;
+  uint32_t* mult;
+  uint32_t* bad;
+  uint64_t mult_words;
+  uint32_t n_lookup, n_limb, max_rows, n_lookup_cols, spread_cols, lookup_bits, limb_bits, usable_rows;
+};
+__global__ void __launch_bounds__(512) k_mult_from_raw(const MultArgs A) {
+  const uint64_t inst = blockIdx.x;
+  uint32_t* bins = A.mult + inst * A.mult_words;
+  {
+    uint4* b4 = reinterpret_cast<uint4*>(bins);   // mult_words is a multiple of 4 (table sizes are powers of two >= 4) and the buffer is 16-byte aligned: checked on the host
+    for (uint64_t i = threadIdx.x; i < A.mult_words / 4; i += blockDim.x) b4[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  uint32_t n_bad = 0;
+  const uint32_t* lr = A.lookup_raw + inst * A.n_lookup;
+  for (uint32_t k = threadIdx.x; k < A.n_lookup; k += blockDim.x) {
+    const uint32_t v = lr[k], col = k / A.max_rows;   // range.finalize wraps at max_rows
+    if ((v >> A.lookup_bits) == 0) atomicAdd(&bins[((uint64_t)col << A.lookup_bits) + v], 1u); else n_bad++;
+  }
+  uint32_t* sp = bins + ((uint64_t)A.n_lookup_cols << A.lookup_bits);
+  const uint8_t* dr = A.dense_raw + inst * A.n_limb;
+  for (uint32_t n = threadIdx.x; n < A.n_limb; n += blockDim.x) atomicAdd(&sp[((n % A.spread_cols) << A.limb_bits) + dr[n]], 1u);
+  for (uint32_t c = threadIdx.x; c < A.n_lookup_cols + A.spread_cols; c += blockDim.x) {
+    if (c < A.n_lookup_cols) {
+      const uint32_t first = c * A.max_rows;
+      const uint32_t used = A.n_lookup > first ? min(A.max_rows, A.n_lookup - first) : 0u;
+      if (A.usable_rows > used) atomicAdd(&bins[(uint64_t)c << A.lookup_bits], A.usable_rows - used);
+    } else {
+      const uint32_t cc = c - A.n_lookup_cols;
+      const uint32_t used = A.n_limb > cc ? (A.n_limb - cc + A.spread_cols - 1) / A.spread_cols : 0u;
+      if (A.usable_rows > used) atomicAdd(&sp[cc << A.limb_bits], A.usable_rows - used);
+    }
+  }
+  if (n_bad && A.bad) atomicAdd(A.bad, n_bad);
 }
 
 __global__ void k_mont_debug(const uint64_t* vals, uint64_t* out, uint64_t n) {
@@ -1148,6 +1135,11 @@ struct h2sha_engine {
   int last_launches = 0;
   int expand_ctas = 0;
   ExpandVariant variant{};
+  DevPlan dplan_mult{};              // the plan as a MODE 1 launch sees it: the warps' scratch also holds the raw looked-up values
+  bool mult_fits = false;            // ... when that still fits in shared memory
+  uint32_t* d_lookup_raw = nullptr;  // [cap][n_lookup] raw looked-up values of the last MODE 1 batch
+  uint8_t* d_dense_raw = nullptr;    // [cap][n_limb]
+  uint64_t raw_cap = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // trace start/stop, expand start/stop
   bool timed = false, timed_expand = false;
   // lookup-argument pre-work (lookup_prework.cuh)
@@ -1374,6 +1366,8 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
     if (!ok) return set_err(H2SHA_EINVAL, "configuration needs more than 227 KB of shared memory (or H2SHA_TUNE names no launch variant)");
   }
   D.max_rows = pc.max_rows; D.spread_cols = pc.spread_cols;
+  const uint32_t mult_scratch = pc.max_fill * 36, mult_misc = align_up(D.off_scratch + e->variant.ncons * mult_scratch, 16);
+  e->mult_fits = mult_misc + 2 * e->variant.nprod * 8 <= 227 * 1024;
   D.spread_cols_shift = -1;
   for (int sh = 0; sh < 16; sh++) if ((1u << sh) == pc.spread_cols) D.spread_cols_shift = sh;
   D.n_gate_cols = P.n_gate_cols; D.gate_col_rows = P.gate_col_rows;
@@ -1408,6 +1402,8 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   }
   if (occ < 1) return set_err(H2SHA_ECUDA, "expand kernel does not fit on an SM");
   e->expand_ctas = occ * e->n_sms;
+  e->dplan_mult = e->dplan;
+  if (e->mult_fits) { e->dplan_mult.scratch_bytes = mult_scratch; e->dplan_mult.off_misc = mult_misc; e->dplan_mult.smem_bytes = mult_misc + 2 * e->variant.nprod * 8; }
   // ---- copy stream, events, job counters ----
   e->overlap_enabled = tune_value("overlap", 1) != 0;
   CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
@@ -1442,7 +1438,7 @@ void h2sha_destroy(h2sha_engine_t* e) {
     if (H.copied) cudaEventDestroy(H.copied);
   if (e->pinned_arena) cudaFreeHost(e->pinned_arena);
   for (int i = 0; i < 4; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
-  cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab); cudaFree(e->d_range_tab);
+  cudaFree(e->d_lk_ws); cudaFree(e->d_lk_tab); cudaFree(e->d_range_tab); cudaFree(e->d_lookup_raw); cudaFree(e->d_dense_raw);
   cudaFree(e->d_chk_gate_on); cudaFree(e->d_chk_pairs); cudaFree(e->d_chk_out_bytes); cudaFree(e->d_chk_fixed); cudaFree(e->d_chk_bytes); cudaFree(e->d_chk_viol);
   delete e;
 }
@@ -1538,6 +1534,8 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     if (b->only_digest) return set_err(H2SHA_EINVAL, "lookup multiplicities need every digest() call of the region (only_digest must be 0)");
     if (!b->gate || !b->lookup || !b->spread) return set_err(H2SHA_EINVAL, "lookup multiplicities are counted while the cells are written: gate, lookup and spread must be given");
     if (b->mult_usable_rows < lookup_rows_needed(P)) return set_err(H2SHA_EINVAL, "mult_usable_rows is smaller than an assigned column or a lookup table");
+    if (!e->mult_fits) return set_err(H2SHA_EINVAL, "this configuration leaves no shared memory for the fused multiplicity count: use h2sha_lookup_multiplicities");
+    if (P.cfg.lookup_bits < 2 || P.cfg.limb_bits < 2 || ((uintptr_t)b->lookup_mult_dev & 15u)) return set_err(H2SHA_EINVAL, "lookup_mult_dev must be 16-byte aligned (tables of >= 4 rows)");
   }
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)b->stream;
@@ -1611,9 +1609,13 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   ta.job_counter = expand ? S->d_counter : nullptr;
   ta.cks = cks_dev;
   if (b->lookup_mult_dev) {
-    // bins are zeroed on the caller's stream before anything of this batch runs there (the expansion kernel adds to them)
-    const uint64_t mw = ((uint64_t)P.n_lookup_cols << P.cfg.lookup_bits) + ((uint64_t)P.cfg.spread_cols << P.cfg.limb_bits);
-    CUDA_TRY(cudaMemsetAsync(b->lookup_mult_dev, 0, b->n_instances * mw * 4, st));
+    if (b->n_instances > e->raw_cap) {
+      e->raw_cap = 0;
+      int rc2;
+      if ((rc2 = dev_realloc(e->d_lookup_raw, b->n_instances * (uint64_t)P.n_lookup * 4))) return rc2;
+      if ((rc2 = dev_realloc(e->d_dense_raw, b->n_instances * (uint64_t)P.n_limb))) return rc2;
+      e->raw_cap = b->n_instances;
+    }
     if (b->mult_not_in_table_dev) CUDA_TRY(cudaMemsetAsync(b->mult_not_in_table_dev, 0, 4, st));
   }
   if (timed) CUDA_TRY(cudaEventRecord(e->ev[0], ts));
@@ -1632,9 +1634,8 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     ja.cks = cks_dev; ja.job_counter = S->d_counter; ja.only_digest = b->only_digest;
     if (b->compact_dict) { ja.dict = (uint32_t*)b->compact_dict; ja.dict_inst_cells = P.dict_cells; }
     if (b->lookup_mult_dev) {
-      ja.mult = b->lookup_mult_dev; ja.mult_bad = b->mult_not_in_table_dev; ja.usable_rows = b->mult_usable_rows;
-      ja.mult_words = ((uint64_t)P.n_lookup_cols << P.cfg.lookup_bits) + ((uint64_t)P.cfg.spread_cols << P.cfg.limb_bits);
-      ja.lookup_bits = P.cfg.lookup_bits; ja.limb_bits = P.cfg.limb_bits; ja.n_lookup_total = P.n_lookup; ja.n_limb_total = P.n_limb;
+      ja.lookup_raw = e->d_lookup_raw; ja.dense_raw = e->d_dense_raw;
+      ja.limb_bits = P.cfg.limb_bits; ja.n_lookup_total = P.n_lookup; ja.n_limb_total = P.n_limb;
     }
     uint64_t n_jobs = b->n_instances * (uint64_t)e->blocks_per_inst * P.n_block_parts;
     for (size_t c = P.n_block_parts; c < P.classes.size(); c++) n_jobs += (b->n_instances + P.classes[c].batch - 1) / P.classes[c].batch;
@@ -1642,10 +1643,11 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     if (timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     {
       // programmatic dependent launch: prologue (plan -> shared memory) overlaps the trace kernel when both are on one stream
-      void* args[2] = {(void*)&e->dplan, (void*)&ja};
+      const DevPlan& dp = b->lookup_mult_dev ? e->dplan_mult : e->dplan;
+      void* args[2] = {(void*)&dp, (void*)&ja};
       cudaLaunchConfig_t lc{};
       lc.gridDim = dim3(grid); lc.blockDim = dim3((e->variant.ncons + e->variant.nprod) * 32);
-      lc.dynamicSmemBytes = e->dplan.smem_bytes; lc.stream = st;
+      lc.dynamicSmemBytes = dp.smem_bytes; lc.stream = st;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = (timed || overlap) ? 0 : 1;   // plain serialisation when kernels are timed individually
@@ -1654,6 +1656,16 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     }
     launches++;
     CUDA_TRY(cudaGetLastError());
+    if (b->lookup_mult_dev) {
+      MultArgs ma{};
+      ma.lookup_raw = e->d_lookup_raw; ma.dense_raw = e->d_dense_raw; ma.mult = b->lookup_mult_dev; ma.bad = b->mult_not_in_table_dev;
+      ma.mult_words = ((uint64_t)P.n_lookup_cols << P.cfg.lookup_bits) + ((uint64_t)P.cfg.spread_cols << P.cfg.limb_bits);
+      ma.n_lookup = P.n_lookup; ma.n_limb = P.n_limb; ma.max_rows = P.cfg.max_rows; ma.n_lookup_cols = P.n_lookup_cols; ma.spread_cols = P.cfg.spread_cols;
+      ma.lookup_bits = P.cfg.lookup_bits; ma.limb_bits = P.cfg.limb_bits; ma.usable_rows = b->mult_usable_rows;
+      k_mult_from_raw<<<(unsigned)b->n_instances, 512, 0, st>>>(ma);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
     if (timed) { CUDA_TRY(cudaEventRecord(e->ev[3], st)); e->timed_expand = true; }
   }
   if (b->digests_host) CUDA_TRY(cudaMemcpyAsync(b->digests_host, dig_dev, n_msgs * 32, cudaMemcpyDeviceToHost, st));

@@ -275,13 +275,17 @@ __global__ void __launch_bounds__(256) k_permute_fill(const PermuteArgs A) {
     for (uint32_t row = blockIdx.x * 256u + threadIdx.x; row < A.usable_rows; row += gridDim.x * 256u) {
       uint32_t k = 0, st = 0, dp = 0;
       if (row >= m0) { k = __ldg(vr + row); st = __ldg(start + k); dp = __ldg(dpre + k); }
-      uint32_t x[8];
-      permuted_value(A, k, x);
+      uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // value 0 is 0 in Montgomery form as well
+      if (k) permuted_value(A, k, x);
       store_cell2(out_a + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
       if (row != st) {
         const uint32_t j = n_rep - 1u - (row - dp - 1u);
         const uint32_t w = j < lf0 ? 0u : __ldg(ll + (j - lf0));
-        permuted_value(A, w, x);
+        if (w) permuted_value(A, w, x);
+        else {
+#pragma unroll
+          for (int q = 0; q < 8; q++) x[q] = 0;
+        }
       }
       store_cell2(out_s + (uint64_t)row * 8, make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
     }
@@ -489,7 +493,8 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
     A.out_table = (uint64_t*)permuted_table_dev + i0 * (uint64_t)usable_rows * 4;
     k_permute_scan<<<(unsigned)ni, 1024, 0, st>>>(A);
     CUDA_TRY(cudaGetLastError());
-    const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, std::max<uint64_t>(16, ((uint64_t)e->n_sms * 16 + ni - 1) / ni));
+    const uint64_t min_tiles = (uint64_t)std::max(1, tune_value("lktiles", A.vrow ? 64 : 16));   // more rows in flight when a row costs one or two loads
+    const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, std::max<uint64_t>(min_tiles, ((uint64_t)e->n_sms * 16 + ni - 1) / ni));
     k_permute_fill<<<dim3(tiles, (unsigned)ni), 256, 0, st>>>(A);
     CUDA_TRY(cudaGetLastError());
   }
