@@ -676,10 +676,19 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
 #ifdef H2SHA_DEBUG_TIMING
       unsigned long long dbg_p0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p0));
 #endif
+      // the first job of every producer is assigned statically (job = producer * grid + CTA), the later ones come from the global
+      // counter: with fewer jobs than producers (a single digest: latency, not throughput) every CTA gets at most one job instead
+      // of the quickest CTA grabbing four
       unsigned long long job = 0;
+      bool static_job = (k == 0);
     next_job:
-      if (lane == 0) job = atomicAdd(A.job_counter, 1ULL);
-      job = __shfl_sync(0xffffffffu, job, 0);
+      if (static_job) {
+        job = (unsigned long long)st * gridDim.x + blockIdx.x;
+        static_job = false;
+      } else {
+        if (lane == 0) job = (unsigned long long)gridDim.x * NPROD + atomicAdd(A.job_counter, 1ULL);
+        job = __shfl_sync(0xffffffffu, job, 0);
+      }
 #ifdef H2SHA_DEBUG_TIMING
       unsigned long long dbg_p1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_p1));
 #endif
@@ -964,33 +973,59 @@ struct MultArgs {
   uint64_t mult_words;
   uint32_t n_lookup, n_limb, max_rows, n_lookup_cols, spread_cols, lookup_bits, limb_bits, usable_rows;
 };
+enum { MULT_SMALL_BINS = 4096 };   // looked-up values below this (bytes, zeros: the hot bins) are binned in shared memory
 __global__ void __launch_bounds__(512) k_mult_from_raw(const MultArgs A) {
+  extern __shared__ uint32_t s_bins[];   // [MULT_SMALL_BINS] range bins of lookup column 0 | [spread_cols << limb_bits] spread bins
   const uint64_t inst = blockIdx.x;
   uint32_t* bins = A.mult + inst * A.mult_words;
-  {
-    uint4* b4 = reinterpret_cast<uint4*>(bins);   // mult_words is a multiple of 4 (table sizes are powers of two >= 4) and the buffer is 16-byte aligned: checked on the host
-    for (uint64_t i = threadIdx.x; i < A.mult_words / 4; i += blockDim.x) b4[i] = make_uint4(0, 0, 0, 0);
-  }
+  const uint32_t n_small = min((uint32_t)MULT_SMALL_BINS, 1u << A.lookup_bits), n_sp = A.spread_cols << A.limb_bits;
+  uint32_t* s_sp = s_bins + MULT_SMALL_BINS;
+  for (uint32_t i = threadIdx.x; i < MULT_SMALL_BINS + n_sp; i += blockDim.x) s_bins[i] = 0;
   __syncthreads();
+  // pass A: the hot bins in shared memory (same-address atomics on the zeros and small bytes would serialise in L2)
   uint32_t n_bad = 0;
   const uint32_t* lr = A.lookup_raw + inst * A.n_lookup;
-  for (uint32_t k = threadIdx.x; k < A.n_lookup; k += blockDim.x) {
-    const uint32_t v = lr[k], col = k / A.max_rows;   // range.finalize wraps at max_rows
-    if ((v >> A.lookup_bits) == 0) atomicAdd(&bins[((uint64_t)col << A.lookup_bits) + v], 1u); else n_bad++;
+  const uint32_t n0 = min(A.n_lookup, A.max_rows);   // cells of lookup column 0 (range.finalize wraps at max_rows)
+  for (uint32_t k = threadIdx.x; k < n0; k += blockDim.x) {
+    const uint32_t v = lr[k];
+    if (v < n_small) atomicAdd(&s_bins[v], 1u);
   }
-  uint32_t* sp = bins + ((uint64_t)A.n_lookup_cols << A.lookup_bits);
   const uint8_t* dr = A.dense_raw + inst * A.n_limb;
-  for (uint32_t n = threadIdx.x; n < A.n_limb; n += blockDim.x) atomicAdd(&sp[((n % A.spread_cols) << A.limb_bits) + dr[n]], 1u);
-  for (uint32_t c = threadIdx.x; c < A.n_lookup_cols + A.spread_cols; c += blockDim.x) {
-    if (c < A.n_lookup_cols) {
-      const uint32_t first = c * A.max_rows;
-      const uint32_t used = A.n_lookup > first ? min(A.max_rows, A.n_lookup - first) : 0u;
-      if (A.usable_rows > used) atomicAdd(&bins[(uint64_t)c << A.lookup_bits], A.usable_rows - used);
-    } else {
+  for (uint32_t n = threadIdx.x; n < A.n_limb; n += blockDim.x) atomicAdd(&s_sp[((n % A.spread_cols) << A.limb_bits) + dr[n]], 1u);
+  if (threadIdx.x < A.n_lookup_cols + A.spread_cols) {   // never-assigned rows of every lookup input column hold 0 = table row 0
+    const uint32_t c = threadIdx.x;
+    if (c == 0) { if (A.usable_rows > n0) atomicAdd(&s_bins[0], A.usable_rows - n0); }
+    else if (c >= A.n_lookup_cols) {
       const uint32_t cc = c - A.n_lookup_cols;
       const uint32_t used = A.n_limb > cc ? (A.n_limb - cc + A.spread_cols - 1) / A.spread_cols : 0u;
-      if (A.usable_rows > used) atomicAdd(&sp[cc << A.limb_bits], A.usable_rows - used);
+      if (A.usable_rows > used) atomicAdd(&s_sp[cc << A.limb_bits], A.usable_rows - used);
     }
+  }
+  __syncthreads();
+  // pass B: every bin of the instance written once, coalesced: the shared-memory counts where they exist, zero elsewhere
+  {
+    uint4* b4 = reinterpret_cast<uint4*>(bins);   // mult_words is a multiple of 4 and the buffer 16-byte aligned: checked on the host
+    const uint64_t sp0 = (uint64_t)A.n_lookup_cols << A.lookup_bits;
+    for (uint64_t i = threadIdx.x; i < A.mult_words / 4; i += blockDim.x) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      const uint64_t w = i * 4;
+      if (w < n_small) v = *reinterpret_cast<const uint4*>(s_bins + w);
+      else if (w >= sp0) v = *reinterpret_cast<const uint4*>(s_sp + (w - sp0));
+      b4[i] = v;
+    }
+  }
+  __syncthreads();
+  // pass C: the (spread-out) large values and the further lookup columns, with global atomics on bins that are now L2-resident
+  for (uint32_t k = threadIdx.x; k < A.n_lookup; k += blockDim.x) {
+    const uint32_t v = lr[k], col = k / A.max_rows;
+    if ((v >> A.lookup_bits) != 0) { n_bad++; continue; }
+    if (col == 0 && v < n_small) continue;
+    atomicAdd(&bins[((uint64_t)col << A.lookup_bits) + v], 1u);
+  }
+  if (threadIdx.x >= 1 && threadIdx.x < A.n_lookup_cols) {
+    const uint32_t c = threadIdx.x, first = c * A.max_rows;
+    const uint32_t used = A.n_lookup > first ? min(A.max_rows, A.n_lookup - first) : 0u;
+    if (A.usable_rows > used) atomicAdd(&bins[(uint64_t)c << A.lookup_bits], A.usable_rows - used);
   }
   if (n_bad && A.bad) atomicAdd(A.bad, n_bad);
 }
@@ -1662,7 +1697,9 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
       ma.mult_words = ((uint64_t)P.n_lookup_cols << P.cfg.lookup_bits) + ((uint64_t)P.cfg.spread_cols << P.cfg.limb_bits);
       ma.n_lookup = P.n_lookup; ma.n_limb = P.n_limb; ma.max_rows = P.cfg.max_rows; ma.n_lookup_cols = P.n_lookup_cols; ma.spread_cols = P.cfg.spread_cols;
       ma.lookup_bits = P.cfg.lookup_bits; ma.limb_bits = P.cfg.limb_bits; ma.usable_rows = b->mult_usable_rows;
-      k_mult_from_raw<<<(unsigned)b->n_instances, 512, 0, st>>>(ma);
+      const size_t mult_smem = ((size_t)MULT_SMALL_BINS + ((size_t)P.cfg.spread_cols << P.cfg.limb_bits)) * 4;
+      if (mult_smem > 48 * 1024) return set_err(H2SHA_EINVAL, "spread tables too large for the multiplicity kernel's shared memory");
+      k_mult_from_raw<<<(unsigned)b->n_instances, 512, mult_smem, st>>>(ma);
       launches++;
       CUDA_TRY(cudaGetLastError());
     }

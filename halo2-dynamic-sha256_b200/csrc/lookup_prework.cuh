@@ -457,7 +457,7 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(st));   // one-time: later calls may come on another stream
     }
-    A.vals = e->d_range_tab;
+    A.vals = tune_value("lktab", 1) ? e->d_range_tab : nullptr;   // lktab=0: convert each value on the fly (mont_from_u32) instead of the 32-byte gather
   } else {
     // compressed table expression dense * theta + spread (halo2 `compress_expressions`), sorted by canonical value
     // (`impl Ord for Fr`): 2^num_bits_lookup field multiplications, done on the host with the plan-time helpers
