@@ -4,6 +4,7 @@
 //   k_trace   one thread per message: padding (lib.rs:77-117), precomputed-prefix state (lib.rs:153-160),
 //             then the scalar SHA-256 of every block with register-resident state, writing the 200-word
 //             per-block trace (W[64], a/e working variables) and the digest.
+//   k_trace_warp  the same for small batches (<= 256 messages), one warp per message: latency instead of throughput.
 //   k_expand  persistent CTAs; one job = one sha256_compression (69 348 gate + 3 184 lookup + 8 240
 //             spread-column cells) or one digest prologue/epilogue.  Phase 1 runs the planner's slot
 //             programs (lanes = unit instances), phase 2 expands the templates: raw value -> BN254 Fr
@@ -419,6 +420,115 @@ __global__ void __launch_bounds__(64) k_trace(TraceArgs A) {
   }
 }
 
+// Small batches (latency, not throughput: BASELINE config 1 is ONE message): one warp per message.  The chain of compressions
+// cannot be shortened, so everything around it is taken off the thread that walks it: all lanes build the padded words
+// (coalesced byte reads) into shared memory, lane = block expands the message schedules of up to 32 blocks at once, lane 0 then
+// runs only the 64 rounds per block (schedule word + round constant from shared memory, working variables into shared memory),
+// and all lanes write the traces out.  Same outputs as k_trace, bit for bit (tests/test_gpu_boundary.py compares the two).
+enum { TW_PASS = 32, TW_WSTRIDE = 65 };   // blocks per pass; schedule stride in words (odd: lanes = blocks hit different banks)
+__global__ void __launch_bounds__(32) k_trace_warp(TraceArgs A) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __shared__ uint32_t sW[TW_PASS * TW_WSTRIDE];   // schedule W[64] per block
+  __shared__ uint32_t sA[TW_PASS * 68], sE[TW_PASS * 68];   // working variables a / e: [0..3] = input state (d,c,b,a / h,g,f,e), [4 + t] after round t
+  __shared__ uint32_t sS[(TW_PASS + 1) * 8];      // chaining state before every block of the pass (+ after the last one)
+  const int lane = threadIdx.x;
+  const uint64_t m = blockIdx.x;
+  if (m == 0 && lane == 0 && A.job_counter) *A.job_counter = 0ull;
+  if (m >= A.n_msgs) return;
+  const uint32_t d = (uint32_t)(m % A.n_digests);
+  const uint64_t inst = m / A.n_digests;
+  if (d == 0 && A.cks && lane < 4) A.cks[inst * 4 + lane] = 0;
+  const DevDigest dd = A.digests_plan[d];
+  const uint32_t R = dd.dp.n_blocks;
+  const uint8_t* msg = A.msgs + A.offsets[m];
+  const uint32_t len = A.lens[m];
+  const uint32_t pre = A.pre_lens ? A.pre_lens[m] : 0u;
+  const uint32_t num_round = (len + 9 + 63) / 64;          // lib.rs:80-84
+  const uint32_t pre_round = pre / 64;                     // lib.rs:93
+  const uint64_t n_inst = A.n_msgs / A.n_digests;
+  uint32_t* dt = A.dtrace + (uint64_t)dd.dtrace_off * n_inst + inst;
+  uint32_t* bt = A.btrace + (uint64_t)dd.blk_prefix * n_inst + inst;
+  const uint64_t bstride = (uint64_t)A.blocks_per_inst * n_inst;
+  const uint32_t words_base = TD_STATES + 8 * (R + 1);
+  const uint32_t total = pre_round + R;
+  uint32_t st[8], hfin[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { st[i] = c_H0[i]; hfin[i] = 0; }
+  for (uint32_t b0 = 0; b0 < total; b0 += TW_PASS) {
+    const uint32_t nb = min((uint32_t)TW_PASS, total - b0);
+    // (1) padded message words of the pass (lib.rs:98-117)
+    for (uint32_t idx = lane; idx < nb * 16; idx += 32) sW[(idx >> 4) * TW_WSTRIDE + (idx & 15)] = padded_word(msg, len, num_round, b0 + (idx >> 4), (int)(idx & 15));
+    __syncwarp();
+    // (2) message schedules, lane = block (compression.rs:57-96 computes the same words in-circuit)
+    if ((uint32_t)lane < nb) {
+      uint32_t* w = sW + lane * TW_WSTRIDE;
+      for (int t = 16; t < 64; t++) {
+        const uint32_t w15 = w[t - 15], w2 = w[t - 2];
+        const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+        const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+        w[t] = w[t - 16] + s0 + w[t - 7] + s1;
+      }
+    }
+    __syncwarp();
+    // (3) the chain: one lane, rounds only
+    if (lane == 0) {
+      for (uint32_t lb = 0; lb < nb; lb++) {
+        const uint32_t* w = sW + lb * TW_WSTRIDE;
+        uint32_t* pa = sA + lb * 68;
+        uint32_t* pe = sE + lb * 68;
+#pragma unroll
+        for (int i = 0; i < 8; i++) sS[lb * 8 + i] = st[i];
+        uint32_t a = st[0], b = st[1], c = st[2], dd_ = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+        pa[3] = a; pa[2] = b; pa[1] = c; pa[0] = dd_; pe[3] = e; pe[2] = f; pe[1] = g; pe[0] = h;
+#pragma unroll 8
+        for (int t = 0; t < 64; t++) {
+          const uint32_t t1 = h + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & f) ^ (~e & g)) + c_K[t] + w[t];
+          const uint32_t t2 = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+          h = g; g = f; f = e; e = dd_ + t1; dd_ = c; c = b; b = a; a = t1 + t2;
+          pa[4 + t] = a; pe[4 + t] = e;
+        }
+        st[0] += a; st[1] += b; st[2] += c; st[3] += dd_; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+        if (b0 + lb + 1 == num_round) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) hfin[i] = st[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) sS[nb * 8 + i] = st[i];
+    }
+    __syncwarp();
+    // (4) traces of the constrained blocks of the pass (blocks below pre_round are the unconstrained prefix, lib.rs:153-160)
+    for (uint32_t lb = 0; lb < nb; lb++) {
+      const uint32_t blk = b0 + lb;
+      if (blk < pre_round) continue;
+      const uint32_t j = blk - pre_round;
+      uint32_t* tw = bt + (uint64_t)j * n_inst;   // word k at tw + k * bstride
+      for (uint32_t k = lane; k < TR_BLOCK_WORDS; k += 32) {
+        const uint32_t v = k < TR_A ? sW[lb * TW_WSTRIDE + k] : (k < TR_E ? sA[lb * 68 + (k - TR_A)] : sE[lb * 68 + (k - TR_E)]);
+        tw[(uint64_t)k * bstride] = v;
+      }
+      if (lane < 8) dt[(uint64_t)(TD_STATES + 8 * j + lane) * n_inst] = sS[lb * 8 + lane];
+      else if (lane < 24) dt[(uint64_t)(words_base + 16 * j + (lane - 8)) * n_inst] = sW[lb * TW_WSTRIDE + (lane - 8)];
+    }
+    if (b0 + nb == total && lane < 8) dt[(uint64_t)(TD_STATES + 8 * R + lane) * n_inst] = sS[nb * 8 + lane];
+    __syncwarp();
+  }
+  if (lane == 0) {
+    dt[(uint64_t)(TD_LEN) * n_inst] = len; dt[(uint64_t)(TD_NUM_ROUND) * n_inst] = num_round; dt[(uint64_t)(TD_PRE_ROUND) * n_inst] = pre_round;
+    dt[(uint64_t)(TD_TARGET) * n_inst] = num_round - pre_round;
+#pragma unroll
+    for (int i = 0; i < 8; i++) dt[(uint64_t)(TD_H + i) * n_inst] = hfin[i];
+    if (A.digests) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const uint32_t x = hfin[i];
+        A.digests[m * 32 + 4 * i + 0] = (uint8_t)(x >> 24); A.digests[m * 32 + 4 * i + 1] = (uint8_t)(x >> 16);
+        A.digests[m * 32 + 4 * i + 2] = (uint8_t)(x >> 8);  A.digests[m * 32 + 4 * i + 3] = (uint8_t)x;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_expand
 // ---------------------------------------------------------------------------------------------------
@@ -507,6 +617,8 @@ __device__ __forceinline__ void run_unit_program(const UnitGroup& g, const UnitT
     int32_t base = g.in[k].base;
     slots[k] = (base < 0) ? (uint64_t)(g.in[k].stride + (int32_t)uu) : (uint64_t)trace[base + g.in[k].stride * (int32_t)uu];
   }
+  // (Round 2: fetching the next instruction word early and reading all three operands before the opcode dispatch changed neither the
+  // 11.5 us a 49-instruction program takes nor the sustained launch time -- the chain through the result slots dominates.)
   const VmIns* ins = prog + ut.prog_off;
   for (uint32_t pc = 0; pc < ut.prog_len; pc++) {
     const VmIns I = ins[pc];
@@ -1338,6 +1450,7 @@ struct h2sha_engine {
   uint64_t seq = 0;                  // calls that uploaded inputs
   int resident_set = -1;             // set holding the inputs of the last such call
   bool overlap_enabled = true;       // H2SHA_TUNE overlap=0: everything on the caller's stream
+  uint64_t trace_warp_below = 256;   // batches of at most this many messages take k_trace_warp
   uint32_t blocks_per_inst = 0, dtrace_words_per_inst = 0;
   int last_launches = 0;
   int expand_ctas = 0;
@@ -1624,6 +1737,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   if (e->mult_fits) { e->dplan_mult.scratch_bytes = mult_scratch; e->dplan_mult.off_misc = mult_misc; e->dplan_mult.smem_bytes = mult_misc + 2 * e->variant.nprod * 8; }
   // ---- copy stream, events, job counters ----
   e->overlap_enabled = tune_value("overlap", 1) != 0;
+  e->trace_warp_below = (uint64_t)tune_value("tracewarp", 256);
   CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   for (InputSet& S : e->sets) {
     CUDA_TRY(cudaEventCreateWithFlags(&S.trace_done, cudaEventDisableTiming));
@@ -1837,7 +1951,9 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     if (b->mult_not_in_table_dev) CUDA_TRY(cudaMemsetAsync(b->mult_not_in_table_dev, 0, 4, st));
   }
   if (timed) CUDA_TRY(cudaEventRecord(e->ev[0], ts));
-  k_trace<<<(unsigned)((n_msgs + 63) / 64), 64, 0, ts>>>(ta);
+  // few messages: the warp-per-message kernel (latency); many: one thread per message (throughput).  H2SHA_TUNE "tracewarp=N" moves the switch.
+  if (n_msgs <= e->trace_warp_below) k_trace_warp<<<(unsigned)n_msgs, 32, 0, ts>>>(ta);
+  else k_trace<<<(unsigned)((n_msgs + 63) / 64), 64, 0, ts>>>(ta);
   launches++;
   CUDA_TRY(cudaGetLastError());
   if (timed) CUDA_TRY(cudaEventRecord(e->ev[1], ts));

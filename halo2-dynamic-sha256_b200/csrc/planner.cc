@@ -1655,12 +1655,16 @@ class Builder {
       uint64_t total = 0;
       for (const GroupRec& g : c.groups) total += (uint64_t)g.count * P.types[type_idx_.at(g.type)].gate_len;
       const uint32_t parts = std::max(1u, cfg_.block_parts);
-      // atoms: runs of <= 32 instances of one group (one phase-1 warp task each); greedy packing into `parts` bins
+      // atoms: runs of <= 32 instances of one group (one phase-1 warp task each); greedy packing into `parts` bins.  Twelve parts or
+      // more ask for latency rather than throughput (one digest at a time, BASELINE config 1): the atoms shrink to 8 instances so that a
+      // compression really is cut into that many jobs for that many SMs -- the slot VM's latency per task is the same at 8 lanes as at 32,
+      // so this costs phase-1 throughput and is not for batches.
       struct Atom { const GroupRec* g; uint32_t first, count; uint64_t cells; };
       std::vector<Atom> atoms;
+      const uint32_t atom_len = parts >= 12 ? 8u : 32u;
       for (const GroupRec& g : c.groups)
-        for (uint32_t first = 0; first < g.count; first += 32) {
-          uint32_t cnt = std::min(32u, g.count - first);
+        for (uint32_t first = 0; first < g.count; first += atom_len) {
+          uint32_t cnt = std::min(atom_len, g.count - first);
           atoms.push_back(Atom{&g, first, cnt, (uint64_t)cnt * P.types[type_idx_.at(g.type)].gate_len});
         }
       std::vector<std::vector<UnitGroup>> part_groups(1);

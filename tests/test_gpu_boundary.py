@@ -147,3 +147,26 @@ def test_zero_outputs_handles_more_than_65535_instances(pkg):
         assert int(tail.abs().sum().item()) == 0
     assert int((lookup[n - 1, 0, 0] == -1).all().item()) == 1
     cfg.close()
+
+
+def test_warp_per_message_trace_kernel_equals_thread_per_message(pkg, monkeypatch):
+    """Small batches take k_trace_warp (one warp per message: latency), large ones k_trace (one thread per message).  Both must
+    leave the same traces: every cell, digest and checksum of a batch with dynamic lengths, the padding edges (0, 55, 56, 63,
+    64, 119 ...), a precomputed prefix and two digests per context is identical under either kernel."""
+    sizes = [192, 1088]
+    rng = np.random.default_rng(11)
+    lens_a = [0, 1, 55, 56, 63, 64, 119, 120, 183, 100, 7, 64]
+    msgs = [[bytes(rng.integers(0, 256, la, dtype=np.uint8)), bytes(rng.integers(0, 256, int(rng.integers(0, 1080)), dtype=np.uint8))] for la in lens_a]
+    pre = [[0, 64 * int(rng.integers(0, 1 + len(m[1]) // 64))] for m in msgs]
+    results = []
+    for knob in ("tracewarp=0", "tracewarp=100000"):
+        monkeypatch.setenv("H2SHA_TUNE", knob)
+        cfg = pkg.Sha256DynamicConfig.configure(sizes, device=0)
+        res = cfg.digest_batch(msgs, pre)
+        results.append((res.digests.copy(), res.checksums.copy(), res.gate.cpu().numpy().copy(), res.lookup.cpu().numpy().copy(), res.spread.cpu().numpy().copy()))
+        cfg.close()
+    for a, b in zip(*results):
+        assert (a == b).all()
+    for k, m in enumerate(msgs):
+        for d in range(2):
+            assert bytes(results[0][0][2 * k + d]) == hashlib.sha256(m[d]).digest()
