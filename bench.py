@@ -270,8 +270,11 @@ def measure_latency_cfg1(ctx):
     import torch
     pkg, local_rank, dev = ctx["pkg"], ctx["local_rank"], ctx["dev"]
     out = {}
-    for name, sizes, msg in (("bench_shape_56B_max1024", [1024], b"\x01" * 56), ("cfg1_64B_max128", [128], bytes(range(64)))):
-        cfg = pkg.Sha256DynamicConfig.configure(sizes, device=local_rank)
+    shapes = (("bench_shape_56B_max1024", [1024], b"\x01" * 56), ("cfg1_64B_max128", [128], bytes(range(64))))
+    # block_parts = 0: the engine as the throughput runs configure it (3 jobs per compression); 24: the latency setting of
+    # h2sha_config_t.block_parts (>= 12 cuts a compression into 8-instance jobs for as many SMs)
+    for name, sizes, msg, parts in [(n_ + suffix, s_, m_, p_) for (n_, s_, m_) in shapes for (suffix, p_) in (("", 0), ("_latency_tuned", 24))]:
+        cfg = pkg.Sha256DynamicConfig.configure(sizes, device=local_rank, block_parts=parts)
         lay = cfg.layout
         gate, lookup, spread = cfg.alloc_outputs(1, zero=True)
         blob, offs, lens = pkg.pack_messages([[msg]])
@@ -296,10 +299,11 @@ def measure_latency_cfg1(ctx):
         assert bytes(hd.numpy()[0]) == hashlib.sha256(msg).digest()
         out[name] = {"wall_us_median": 1e6 * float(np.median(ts)), "wall_us_min": 1e6 * float(np.min(ts)), "k_trace_us": 1e3 * float(np.median([k[0] for k in km])),
                      "k_expand_us": 1e3 * float(np.median([k[1] for k in km])), "blocks": lay.n_blocks, "cells": lay.cells_per_instance,
-                     "gate_columns": lay.n_gate_cols}
+                     "gate_columns": lay.n_gate_cols, "block_parts": parts or 3}
         cfg.close()
         del gate, lookup, spread
-    out["note"] = "one instance per call, host buffers in, digest + checksums out, host synchronises after every call (latency, not throughput)"
+    out["note"] = ("one instance per call, host buffers in, digest + checksums out, host synchronises after every call (latency, not throughput); "
+                   "small batches take the warp-per-message trace kernel; *_latency_tuned = an engine created with block_parts = 24")
     return out
 
 

@@ -58,7 +58,9 @@ typedef struct {
   uint32_t spread_rows;                     /* 0 -> tight                                                       */
   int32_t device;                           /* CUDA device ordinal; -1 = plan-only (host queries, no witness)   */
   uint32_t build_shape;                     /* also build selectors / copy constraints / fixed column (host)    */
-  uint32_t block_parts;                     /* tuning: GPU jobs per sha256_compression; 0 -> default            */
+  uint32_t block_parts;                     /* tuning: GPU jobs per sha256_compression; 0 -> default (3: throughput).
+                                               >= 12 = latency setting for one digest at a time (e.g. 24): the compression is
+                                               cut into 8-instance jobs for as many SMs; not for batches                        */
   uint32_t num_lookup_advice;               /* RangeConfig's NUM_LOOKUP_ADVICE (lib.rs:413,492): lookup advice columns the circuit has;
                                                0 -> as many as the looked-up cells need.  Fewer than needed -> H2SHA_EINVAL (halo2-base
                                                would panic); more -> the extra columns stay empty.  Cells fill column 0 up to max_rows,
