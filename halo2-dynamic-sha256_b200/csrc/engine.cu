@@ -4,7 +4,7 @@
 //   k_trace   one thread per message: padding (lib.rs:77-117), precomputed-prefix state (lib.rs:153-160),
 //             then the scalar SHA-256 of every block with register-resident state, writing the 200-word
 //             per-block trace (W[64], a/e working variables) and the digest.
-//   k_trace_warp  the same for small batches (<= 256 messages), one warp per message: latency instead of throughput.
+//   k_trace_warp  the same for batches of <= 2048 messages, one warp per message: latency instead of throughput.
 //   k_expand  persistent CTAs; one job = one sha256_compression (69 348 gate + 3 184 lookup + 8 240
 //             spread-column cells) or one digest prologue/epilogue.  Phase 1 runs the planner's slot
 //             programs (lanes = unit instances), phase 2 expands the templates: raw value -> BN254 Fr
@@ -120,7 +120,7 @@ __constant__ FrConsts c_fr;
 // ---------------------------------------------------------------------------------------------------
 // Montgomery form of a raw value v < 2^64:  v * 2^256 mod p, by one 64x256 multiply and a Barrett
 // reduction with a 64-bit quotient estimate (q_hat in {q-2, q-1, q}; checked exhaustively on edge
-// cases in tests/test_field.py).  Replaces halo2curves `Fr::from(u64)` (one full Montgomery multiply).
+// cases in tests/test_gpu_parity.py::test_montgomery_conversion_matches_python_ints).  Replaces halo2curves `Fr::from(u64)` (one full Montgomery multiply).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mont_from_u64(uint64_t v, uint64_t r[4]) {
   const uint64_t R0 = c_fr.r1[0], R1 = c_fr.r1[1], R2 = c_fr.r1[2], R3 = c_fr.r1[3];
@@ -975,8 +975,12 @@ __global__ void __launch_bounds__((NCONS + NPROD) * 32, 1) k_expand(const DevPla
       // ---- positions of the chunk's gate cells; a column break inside the chunk (rare) takes the per-cell path ----
       const uint32_t g_lo = gate0 + item.gate_rel;   // instance-relative gate-stream index of the unit's first cell
       uint32_t c0 = 0;
-      if (P.n_breaks > 1)
+      if (P.n_breaks > 1) {
+        // a column holds at most max_rows cells, so column c starts at or before c * max_rows: start the search at the quotient
+        // (a linear search from column 0 cost ~0.7 % of the launch per gate column: config 5 has 18)
+        c0 = min((g_lo + ch.gate_dst_min) / P.max_rows, P.n_breaks - 1u);
         while (c0 + 1 < P.n_breaks && s_breaks[c0 + 1] <= g_lo + ch.gate_dst_min) c0++;
+      }
       const uint32_t next_brk = (c0 + 1 < P.n_breaks) ? s_breaks[c0 + 1] : 0xffffffffu;
       const uint32_t off0 = c0 * P.gate_col_rows - s_breaks[c0];          // pos = gidx + off0 before the break,
       const uint32_t off1 = (c0 + 1) * P.gate_col_rows - next_brk;        //       gidx + off1 from the break on
@@ -1450,7 +1454,7 @@ struct h2sha_engine {
   uint64_t seq = 0;                  // calls that uploaded inputs
   int resident_set = -1;             // set holding the inputs of the last such call
   bool overlap_enabled = true;       // H2SHA_TUNE overlap=0: everything on the caller's stream
-  uint64_t trace_warp_below = 256;   // batches of at most this many messages take k_trace_warp
+  uint64_t trace_warp_below = 2048;  // batches of at most this many messages take k_trace_warp (measured crossover: 1024 x 1 block 13.6 vs 17.8 us, 4096 x 1 block 35 vs 21 us, 512 x 33 blocks 95 vs 373 us)
   uint32_t blocks_per_inst = 0, dtrace_words_per_inst = 0;
   int last_launches = 0;
   int expand_ctas = 0;
@@ -1737,7 +1741,7 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   if (e->mult_fits) { e->dplan_mult.scratch_bytes = mult_scratch; e->dplan_mult.off_misc = mult_misc; e->dplan_mult.smem_bytes = mult_misc + 2 * e->variant.nprod * 8; }
   // ---- copy stream, events, job counters ----
   e->overlap_enabled = tune_value("overlap", 1) != 0;
-  e->trace_warp_below = (uint64_t)tune_value("tracewarp", 256);
+  e->trace_warp_below = (uint64_t)tune_value("tracewarp", 2048);
   CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   for (InputSet& S : e->sets) {
     CUDA_TRY(cudaEventCreateWithFlags(&S.trace_done, cudaEventDisableTiming));

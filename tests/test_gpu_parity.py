@@ -31,8 +31,8 @@ def _engine(pkg, kw, **extra):
                                              is_input_range_check=kw.get("is_input_range_check", True), device=0, **extra)
 
 
-def _compare(pkg, kw, instances, pre=None, threads=NCPU):
-    cfg = _engine(pkg, kw)
+def _compare(pkg, kw, instances, pre=None, threads=NCPU, **extra):
+    cfg = _engine(pkg, kw, **extra)
     lay = cfg.layout
     res = cfg.digest_batch(instances, pre)
     olay = O.Layout(lay.n_gate_cols, lay.gate_col_rows, lay.n_lookup_cols, lay.lookup_col_rows, lay.spread_rows)
@@ -166,6 +166,17 @@ def test_alternative_configurations(pkg, kw):
     instances = [[bytes(rng.integers(0, 256, int(rng.integers(0, m - 8)), dtype=np.uint8)) for m in kw["max_variable_byte_sizes"]] for _ in range(3)]
     assert all(len(i) == D for i in instances)
     _compare(pkg, kw, instances)
+
+
+@pytest.mark.parametrize("parts", [1, 6, 12, 24])
+def test_job_granularity_does_not_change_the_cells(pkg, parts):
+    """h2sha_config_t.block_parts only decides how a compression is cut into GPU jobs (>= 12: the latency setting, 8-instance jobs);
+    cells, digests and checksums stay bit-exact, for one digest per call and for a batch with two digests per context."""
+    rng = np.random.default_rng(parts)
+    _compare(pkg, dict(max_variable_byte_sizes=(128,)), [[bytes(range(64))]], block_parts=parts)
+    kw = dict(max_variable_byte_sizes=(192, 1088))
+    instances = [[bytes(rng.integers(0, 256, int(rng.integers(0, m - 8)), dtype=np.uint8)) for m in kw["max_variable_byte_sizes"]] for _ in range(5)]
+    _compare(pkg, kw, instances, block_parts=parts)
 
 
 def test_wider_strides_leave_unassigned_cells_untouched(pkg):

@@ -36,10 +36,10 @@ def run(workload, tune, n_inst=None, steps=10):
     cfg.digest_batch_raw(n, d_blob.data_ptr(), True, int(blob.size), offs, lens, None, **kw)
     for _ in range(3):
         cfg.digest_batch_raw(n, 0, True, 0, offs, lens, None, reuse_inputs=True, **kw)
-    ts = []
+    ts, tr = [], []
     for _ in range(steps):
         cfg.digest_batch_raw(n, 0, True, 0, offs, lens, None, reuse_inputs=True, time_kernels=True, **kw)
-        ts.append(cfg.last_kernel_ms()[1])
+        ts.append(cfg.last_kernel_ms()[1]); tr.append(cfg.last_kernel_ms()[0])
     torch.cuda.synchronize()
     sustained = ""
     if os.environ.get("TUNE_SUSTAIN"):
@@ -63,7 +63,7 @@ def run(workload, tune, n_inst=None, steps=10):
     torch.cuda.empty_cache()
     ms = float(np.median(ts))
     gbs = n * lay.cells_per_instance * 32 / ms / 1e6
-    return f"{tune:40s} n={n:6d} k_expand {ms:8.4f} ms  {n * lay.n_blocks / ms / 1e3:8.3f} Mblk/s  {gbs:7.1f} GB/s  ck={ck:#x}{sustained}"
+    return f"{tune:40s} n={n:6d} k_expand {ms:8.4f} ms  {n * lay.n_blocks / ms / 1e3:8.3f} Mblk/s  {gbs:7.1f} GB/s  ck={ck:#x}{sustained}  k_trace {float(np.median(tr)) * 1e3:.1f} us"
 
 
 if __name__ == "__main__":
