@@ -8,7 +8,7 @@
 # pairs of the reference's tests (src/lib.rs:497-611) and compares every advice column of every run with the oracle.
 # Expected output, if the recalled halo2-base patterns are right: four lines
 #     "8 columns x 131072 rows compared; 0 cells differ"
-# Any other outcome names the first differing (column,row) and gate-stream index; DESIGN.md §1b says what to suspect.
+# Any other outcome names the first differing (column,row) and gate-stream index; DESIGN.md §1 ("Parity status") lists what to suspect first.
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
 root="$(cd "$here/../../.." && pwd)"
