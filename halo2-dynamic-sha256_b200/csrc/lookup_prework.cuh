@@ -139,6 +139,10 @@ struct PermuteArgs {
 // one CTA per instance: exclusive scans, in sorted order, of m (-> first row of each value's run in A'), of [m > 0]
 // (-> how many runs start before it) and of the leftover table multiplicity t - [m > 0]
 // (t = 1 per table row; the row holding the padding value -- table row 0 -- also takes the usable_rows - n_vals padded rows)
+// VPT = consecutive sorted positions per thread and round: 1 (any order / size), or 4 with 128-bit loads and stores when the order is the
+// identity and the table size allows.  (16 per thread -- four rounds instead of sixteen for the 2^16-row range table -- was measured
+// slower in round 2: 0.593 vs 0.504 ms per 256 instances; 64-byte strides per lane and spills cost more than the saved barriers.)
+template <int VPT>
 __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
   __shared__ uint32_t s_part[2][3][32];   // double-buffered by round: two barriers per round
   const uint32_t inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,26 +151,31 @@ __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
   uint32_t* dpre = start + A.n_vals;
   uint32_t* lpre = dpre + A.n_vals;
   const uint32_t pad = A.usable_rows - A.n_vals;
-  // rounds of 1024 threads x `per` consecutive sorted positions; 128-bit loads / stores when the order is the identity
-  const bool vec = A.order == nullptr && (A.n_vals & 4095u) == 0 && (A.mult_stride & 3u) == 0 && ((uintptr_t)A.mult & 15u) == 0;
-  const uint32_t per = vec ? 4u : 1u;
+  constexpr bool vec = VPT > 1;
   uint32_t base[3] = {0, 0, 0};
   uint32_t round = 0;
-  for (uint32_t k0 = 0; k0 < A.n_vals; k0 += 1024u * per, round++) {
-    const uint32_t k = k0 + tid * per;
-    uint32_t mk[4] = {0, 0, 0, 0}, lf[4] = {0, 0, 0, 0};
-    if (vec) {
-      const uint4 q4 = *reinterpret_cast<const uint4*>(m + k);
-      mk[0] = q4.x; mk[1] = q4.y; mk[2] = q4.z; mk[3] = q4.w;
+  for (uint32_t k0 = 0; k0 < A.n_vals; k0 += 1024u * VPT, round++) {
+    const uint32_t k = k0 + tid * VPT;
+    uint32_t mk[VPT], lf[VPT];
+    if constexpr (vec) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) lf[i] = 1u + ((k + i) == 0 ? pad : 0u) - (mk[i] ? 1u : 0u);
-    } else if (k < A.n_vals) {
-      const uint32_t row = A.order ? A.order[k] : k;
-      mk[0] = m[row];
-      lf[0] = 1u + (row == 0 ? pad : 0u) - (mk[0] ? 1u : 0u);
+      for (int q4 = 0; q4 < VPT / 4; q4++) {
+        const uint4 q = *reinterpret_cast<const uint4*>(m + k + 4 * q4);
+        mk[4 * q4] = q.x; mk[4 * q4 + 1] = q.y; mk[4 * q4 + 2] = q.z; mk[4 * q4 + 3] = q.w;
+      }
+#pragma unroll
+      for (int i = 0; i < VPT; i++) lf[i] = 1u + ((k + i) == 0 ? pad : 0u) - (mk[i] ? 1u : 0u);
+    } else {
+      mk[0] = 0; lf[0] = 0;
+      if (k < A.n_vals) {
+        const uint32_t row = A.order ? A.order[k] : k;
+        mk[0] = m[row];
+        lf[0] = 1u + (row == 0 ? pad : 0u) - (mk[0] ? 1u : 0u);
+      }
     }
-    uint32_t v[3] = {mk[0] + mk[1] + mk[2] + mk[3], (mk[0] ? 1u : 0u) + (mk[1] ? 1u : 0u) + (mk[2] ? 1u : 0u) + (mk[3] ? 1u : 0u),
-                     lf[0] + lf[1] + lf[2] + lf[3]};
+    uint32_t v[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < VPT; i++) { v[0] += mk[i]; v[1] += mk[i] ? 1u : 0u; v[2] += lf[i]; }
     uint32_t (*part)[32] = s_part[round & 1u];
     uint32_t incl[3];
 #pragma unroll
@@ -197,12 +206,16 @@ __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
       ex[q] = base[q] + (warp ? part[q][warp - 1] : 0u) + incl[q] - v[q];
       base[q] += part[q][31];
     }
-    if (vec) {
-      uint4 o0, o1, o2;
-      o0.x = ex[0]; o0.y = o0.x + mk[0]; o0.z = o0.y + mk[1]; o0.w = o0.z + mk[2];
-      o1.x = ex[1]; o1.y = o1.x + (mk[0] ? 1u : 0u); o1.z = o1.y + (mk[1] ? 1u : 0u); o1.w = o1.z + (mk[2] ? 1u : 0u);
-      o2.x = ex[2]; o2.y = o2.x + lf[0]; o2.z = o2.y + lf[1]; o2.w = o2.z + lf[2];
-      *reinterpret_cast<uint4*>(start + k) = o0; *reinterpret_cast<uint4*>(dpre + k) = o1; *reinterpret_cast<uint4*>(lpre + k) = o2;
+    if constexpr (vec) {
+      uint32_t o0 = ex[0], o1 = ex[1], o2 = ex[2];
+#pragma unroll
+      for (int q4 = 0; q4 < VPT / 4; q4++) {
+        uint4 a, b, c;
+        a.x = o0; o0 += mk[4 * q4]; a.y = o0; o0 += mk[4 * q4 + 1]; a.z = o0; o0 += mk[4 * q4 + 2]; a.w = o0; o0 += mk[4 * q4 + 3];
+        b.x = o1; o1 += mk[4 * q4] ? 1u : 0u; b.y = o1; o1 += mk[4 * q4 + 1] ? 1u : 0u; b.z = o1; o1 += mk[4 * q4 + 2] ? 1u : 0u; b.w = o1; o1 += mk[4 * q4 + 3] ? 1u : 0u;
+        c.x = o2; o2 += lf[4 * q4]; c.y = o2; o2 += lf[4 * q4 + 1]; c.z = o2; o2 += lf[4 * q4 + 2]; c.w = o2; o2 += lf[4 * q4 + 3];
+        *reinterpret_cast<uint4*>(start + k + 4 * q4) = a; *reinterpret_cast<uint4*>(dpre + k + 4 * q4) = b; *reinterpret_cast<uint4*>(lpre + k + 4 * q4) = c;
+      }
     } else if (k < A.n_vals) {
       start[k] = ex[0]; dpre[k] = ex[1]; lpre[k] = ex[2];
     }
@@ -214,8 +227,8 @@ __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
       const uint32_t lf0 = 1u + pad - (m[0] ? 1u : 0u);
       uint32_t st_k = ex[0], lp_k = ex[2];
 #pragma unroll
-      for (uint32_t q = 0; q < 4; q++) {
-        if (q < per && k + q < A.n_vals && k + q > 0) {
+      for (uint32_t q = 0; q < (uint32_t)VPT; q++) {
+        if (k + q < A.n_vals && k + q > 0) {
           for (uint32_t r = 0; r < mk[q]; r++) vr[st_k + r] = k + q;
           if (lf[q]) ll[lp_k - lf0] = k + q;   // leftover element j >= lf0 of the sequence is ll[j - lf0]
         }
@@ -491,7 +504,11 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
     A.mult = mult0 + i0 * A.mult_stride;
     A.out_input = (uint64_t*)permuted_input_dev + i0 * (uint64_t)usable_rows * 4;
     A.out_table = (uint64_t*)permuted_table_dev + i0 * (uint64_t)usable_rows * 4;
-    k_permute_scan<<<(unsigned)ni, 1024, 0, st>>>(A);
+    {
+      const bool aligned = A.order == nullptr && (A.mult_stride & 3u) == 0 && ((uintptr_t)A.mult & 15u) == 0;
+      if (aligned && (A.n_vals % (1024u * 4u)) == 0) k_permute_scan<4><<<(unsigned)ni, 1024, 0, st>>>(A);
+      else k_permute_scan<1><<<(unsigned)ni, 1024, 0, st>>>(A);
+    }
     CUDA_TRY(cudaGetLastError());
     const uint64_t min_tiles = (uint64_t)std::max(1, tune_value("lktiles", A.vrow ? 64 : 16));   // more rows in flight when a row costs one or two loads
     const unsigned tiles = (unsigned)std::min<uint64_t>((usable_rows + 255) / 256, std::max<uint64_t>(min_tiles, ((uint64_t)e->n_sms * 16 + ni - 1) / ni));
