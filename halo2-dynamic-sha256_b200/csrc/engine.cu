@@ -1740,7 +1740,9 @@ int h2sha_create(const h2sha_config_t* cfg, h2sha_engine_t** out) {
   e->dplan_mult = e->dplan;
   if (e->mult_fits) { e->dplan_mult.scratch_bytes = mult_scratch; e->dplan_mult.off_misc = mult_misc; e->dplan_mult.smem_bytes = mult_misc + 2 * e->variant.nprod * 8; }
   // ---- copy stream, events, job counters ----
-  e->overlap_enabled = tune_value("overlap", 1) != 0;
+  // the latency setting keeps everything on the caller's stream (trace kernel -> expansion with programmatic dependent launch): handing
+  // the copy and the trace kernel to the second stream costs two event hops, 6 us of a 64 us digest
+  e->overlap_enabled = tune_value("overlap", pc.block_parts >= 12 ? 0 : 1) != 0;
   e->trace_warp_below = (uint64_t)tune_value("tracewarp", 2048);
   CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   for (InputSet& S : e->sets) {
