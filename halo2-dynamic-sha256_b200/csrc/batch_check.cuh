@@ -245,7 +245,7 @@ int h2sha_check_batch(h2sha_engine_t* e, uint64_t n_instances, const void* gate,
     k_range_mult<<<dim3(rt, ni), 256, 0, st>>>(G, A.lookup, nullptr, bad32);
     CUDA_TRY(cudaGetLastError());
     const unsigned stl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((G.n_limb + 1023) / 1024, 32));
-    k_spread_mult<<<dim3(stl, ni), 256, (size_t)G.spread_cols * (1u << G.limb_bits) * 4, st>>>(G, A.spread, nullptr, bad32 + 2);
+    k_spread_mult<<<dim3(stl, ni), 256, 0, st>>>(G, A.spread, nullptr, bad32 + 2);   // check-only: no histogram, no shared memory
     CUDA_TRY(cudaGetLastError());
   }
   if (digests_dev) {

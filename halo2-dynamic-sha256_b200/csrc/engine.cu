@@ -1874,6 +1874,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     if (b->mult_usable_rows < lookup_rows_needed(P)) return set_err(H2SHA_EINVAL, "mult_usable_rows is smaller than an assigned column or a lookup table");
     if (!e->mult_fits) return set_err(H2SHA_EINVAL, "this configuration leaves no shared memory for the fused multiplicity count: use h2sha_lookup_multiplicities");
     if (P.cfg.lookup_bits < 2 || P.cfg.limb_bits < 2 || ((uintptr_t)b->lookup_mult_dev & 15u)) return set_err(H2SHA_EINVAL, "lookup_mult_dev must be 16-byte aligned (tables of >= 4 rows)");
+    if (P.cfg.limb_bits > 8) return set_err(H2SHA_EINVAL, "the fused multiplicity count keeps the spread-table bins in shared memory: num_bits_lookup <= 8");
   }
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)b->stream;

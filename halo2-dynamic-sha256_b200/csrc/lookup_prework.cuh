@@ -89,10 +89,12 @@ __global__ void __launch_bounds__(256) k_range_mult(const LookupGeom G, const ui
 // shared memory, flushed with one global atomic per non-empty bin.  grid = (tiles, instances); dynamic smem = cols * 2^bits * 4.
 __global__ void __launch_bounds__(256) k_spread_mult(const LookupGeom G, const uint64_t* __restrict__ spread, uint32_t* __restrict__ mult,
                                                     uint32_t* __restrict__ bad) {
-  extern __shared__ uint32_t s_hist[];
+  extern __shared__ uint32_t s_hist[];   // [spread_cols << limb_bits]; not allocated in check-only mode (mult == null), which therefore also serves 16-bit limbs
   const uint32_t n_vals = 1u << G.limb_bits, n_bins = G.spread_cols * n_vals;
-  for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) s_hist[i] = 0;
-  __syncthreads();
+  if (mult) {
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+  }
   const uint64_t inst = blockIdx.y;
   const uint64_t* base = spread + inst * G.spread_inst_cells * 4;
   uint32_t* m_inst = mult + inst * G.mult_words + (uint64_t)G.n_lookup_cols * (1u << G.lookup_bits);
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(256) k_spread_mult(const LookupGeom G, const u
     mont_reduce(x, s);
     bool ok = (d[1] | d[2] | d[3]) == 0 && d[0] < n_vals && (s[1] | s[2] | s[3]) == 0;
     if (ok) ok = spread32(d[0]) == s[0];   // the pair has to be a table row, not just the dense half
-    if (ok) atomicAdd(&s_hist[col * n_vals + (uint32_t)d[0]], 1u); else n_bad++;
+    if (!ok) n_bad++;
+    else if (mult) atomicAdd(&s_hist[col * n_vals + (uint32_t)d[0]], 1u);
   }
   if (n_bad && bad) atomicAdd(bad, n_bad);
   __syncthreads();

@@ -100,7 +100,6 @@ class Builder {
   void run() {
     if (cfg_.max_variable_byte_sizes.empty()) fail("max_variable_byte_sizes is empty");
     if (cfg_.limb_bits == 0 || 16 % cfg_.limb_bits != 0) fail("num_bits_lookup must divide 16 (spread.rs:37)");
-    if (cfg_.limb_bits > 8) fail("num_bits_lookup > 8 is not supported by this engine (shared-memory spread table)");
     if (cfg_.spread_cols == 0) fail("num_advice_columns must be >= 1");
     if (cfg_.lookup_bits < 8 || cfg_.lookup_bits > 32) fail("lookup_bits must be in [8, 32]");
     if (cfg_.max_rows < 64) fail("max_rows too small");
@@ -423,8 +422,10 @@ class Builder {
   // src/spread.rs
   // ======================================================================================
   // spread.rs:196-233
-  AV spread_limb(const AV& limb) {
-    Sym sp = table(T_SBYTE, limb.s);
+  // `whole_spread`: with 16-bit limbs (num_bits_lookup = 16: one limb per `spread`, no 2^16-entry table in shared memory) the limb's
+  // spread is the caller's 32-bit spread slot itself, a plain extract the Barrett path converts
+  AV spread_limb(const AV& limb, const Sym* whole_spread = nullptr) {
+    Sym sp = whole_spread ? *whole_spread : table(T_SBYTE, limb.s);
     cur_.limb.push_back(limb.s);  // dense column cell (:203-208)
     cur_.limb.push_back(sp);      // spread column cell (:219-224)
     cur_.ev.push_back(Event{EV_LIMB, limb.s});
@@ -445,8 +446,9 @@ class Builder {
     assert_equal(sum, dense);                                                                             // :104-108
     AV acc = load_zero();                                                                                 // :110
     for (uint32_t i = 0; i < nl; i++) {                                                                   // :112-121
-      AV sl = spread_limb(limbs[i]);
-      Sym partial = (i == 0) ? table(T_SBYTE, limbs[0].s) : sub(out, 0, 2 * lb * (i + 1));
+      const Sym whole = sub(out, 0, 32);
+      AV sl = spread_limb(limbs[i], lb == 16 ? &whole : nullptr);
+      Sym partial = (i == 0) ? (lb == 16 ? whole : table(T_SBYTE, limbs[0].s)) : sub(out, 0, 2 * lb * (i + 1));
       acc = mul_add(EX(sl), C(1ULL << (2 * lb * i)), EX(acc), partial);
     }
     return acc;
@@ -906,6 +908,12 @@ class Builder {
   }
   std::map<uint32_t, uint32_t> resident_slot_;   // const table index -> fixed scratch slot
   bool is_resident(const Sym& s) const { return s.kind == KIND_TABLE && s.w == 0 && resident_slot_.count(table_index(s)); }
+  // a spread-column cell: the dense cell (even dst) is a limb-wide extract whose slot / shift the kernel also uses for the table-row
+  // multiplicities; the spread cell is its table image (num_bits_lookup <= 8) or the 32-bit spread slot (num_bits_lookup = 16)
+  bool limb_cell_ok(const Sym& s, uint32_t dst) const {
+    if ((dst & 1u) == 0) return (s.kind == KIND_TABLE && s.table == T_BYTE && s.w == cfg_.limb_bits) || (s.kind == KIND_GENERIC && !s.neg && s.shl == 0 && s.w == cfg_.limb_bits);
+    return (s.kind == KIND_TABLE && s.table == T_SBYTE && s.w == cfg_.limb_bits) || (cfg_.limb_bits == 16 && s.kind == KIND_GENERIC && !s.neg && s.shl == 0 && s.w == 32);
+  }
   // sort class of a fill entry: table copies, then <= 32-bit Barrett, then the full 64-bit / signed path
   static int fill_class(const Sym& s) {
     if (s.kind == KIND_TABLE) return 0;
@@ -977,7 +985,7 @@ class Builder {
         if (!ok || res || dst >= 0xffff) fail("a looked-up cell holds a constant, a negated or a signed value");
         ld[vi].push_back((uint16_t)dst); n_lk++;
       } else {
-        if (res || dst >= 0xffff || ps.kind != KIND_TABLE || ps.w != cfg_.limb_bits) fail("spread-column cell does not fit its descriptor");
+        if (res || dst >= 0xffff || !limb_cell_ok(ps, dst)) fail("spread-column cell does not fit its descriptor");
         md[vi].push_back((uint16_t)dst); n_limb++;
       }
     });
@@ -1373,7 +1381,7 @@ class Builder {
           const uint32_t sl = loc[index.at(sym_key(pc.s))];
           if (kind == EV_LIMB) {
             // src (8) | dst (10) | slot (8) | sh (6): where the limb's raw value sits (dense: the extract itself; spread: its table index)
-            if (sl > 0xff || pc.dst > 0x3ff || pc.s.kind != KIND_TABLE || pc.s.w != cfg_.limb_bits) fail("spread-column cell does not fit its descriptor");
+            if (sl > 0xff || pc.dst > 0x3ff || !limb_cell_ok(pc.s, pc.dst)) fail("spread-column cell does not fit its descriptor");
             P.cells.push_back(CellEntry{sl | (pc.dst << 8) | ((uint32_t)pc.s.slot << 18) | ((uint32_t)pc.s.sh << 26)});
           } else {
             P.cells.push_back(CellEntry{sl | (pc.dst << 16)});
@@ -1580,11 +1588,12 @@ class Builder {
     // ---- Montgomery table ----
     P.tb_byte = (uint32_t)consts_.size();
     P.tb_sbyte = P.tb_byte + 256;
-    P.tb_inv = P.tb_sbyte + (1u << cfg_.limb_bits);
+    const uint32_t n_sbyte = cfg_.limb_bits <= 8 ? (1u << cfg_.limb_bits) : 0u;   // 16-bit limbs use no spread table (see spread_limb)
+    P.tb_inv = P.tb_sbyte + n_sbyte;
     P.inv_bias = inv_bias_;
     for (auto& c : consts_) P.mont_table.push_back(fr::to_mont(c));
     for (uint32_t i = 0; i < 256; i++) P.mont_table.push_back(fr::to_mont(fr::from_u64(i)));
-    for (uint32_t i = 0; i < (1u << cfg_.limb_bits); i++) {
+    for (uint32_t i = 0; i < n_sbyte; i++) {
       uint64_t sp = 0;
       for (int b = 0; b < 8; b++) sp |= (uint64_t)((i >> b) & 1) << (2 * b);
       P.mont_table.push_back(fr::to_mont(fr::from_u64(sp)));

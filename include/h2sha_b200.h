@@ -50,7 +50,7 @@ typedef struct {
                                                (inverse table of is_zero); larger -> H2SHA_EINVAL */
   uint32_t max_rows;                        /* range.gate.max_rows = 2^k - minimum_rows; 0 -> 2^17 - 9          */
   uint32_t lookup_bits;                     /* RangeConfig lookup_bits; 0 -> 16                                 */
-  uint32_t num_bits_lookup;                 /* SpreadConfig limb bits, divides 16, <= 8; 0 -> 8                 */
+  uint32_t num_bits_lookup;                 /* SpreadConfig limb bits, divides 16 (1, 2, 4, 8, 16); 0 -> 8      */
   uint32_t num_advice_columns;              /* SpreadConfig column pairs; 0 -> 2                                */
   uint32_t is_input_range_check;            /* lib.rs:55,174-178                                                */
   uint32_t gate_col_rows;                   /* row stride of a gate column in the output; 0 -> tight            */

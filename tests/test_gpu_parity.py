@@ -168,6 +168,29 @@ def test_alternative_configurations(pkg, kw):
     _compare(pkg, kw, instances)
 
 
+@pytest.mark.parametrize("kw", [dict(max_variable_byte_sizes=(64,), limb_bits=16), dict(max_variable_byte_sizes=(192, 128), limb_bits=16, spread_cols=1),
+                                dict(max_variable_byte_sizes=(128,), limb_bits=16, spread_cols=3, lookup_bits=12)],
+                         ids=["1block", "2digests-1col", "3cols-12bit"])
+def test_sixteen_bit_spread_limbs(pkg, kw):
+    """num_bits_lookup = 16 is legal in the reference (`16 % num_bits_lookup == 0`, spread.rs:37): one limb per `spread`, no shared-memory
+    spread table -- the limb's spread is the 32-bit spread slot itself.  Cells bit-exact against the oracle, a corrupted spread cell is
+    caught by the device-side spread-lookup check, and the two calls that keep table bins in shared memory refuse cleanly."""
+    import torch
+    rng = np.random.default_rng(16)
+    instances = [[bytes(rng.integers(0, 256, int(rng.integers(0, m - 8)), dtype=np.uint8)) for m in kw["max_variable_byte_sizes"]] for _ in range(3)]
+    res, _ = _compare(pkg, kw, instances)
+    cfg = _engine(pkg, kw)
+    res = cfg.digest_batch(instances)
+    assert all(v == 0 for v in cfg.check_batch(res).values())
+    res.spread[1, kw.get("spread_cols", 2), 5, 0] ^= 4      # spread half of column pair 0, row 5 of instance 1: no longer the spread of its dense cell
+    torch.cuda.synchronize()
+    bad = cfg.check_batch(res)
+    assert bad["spread_lookups"] >= 1 and bad["gates"] == 0
+    with pytest.raises(pkg.EngineError):
+        cfg.lookup_multiplicities(res, (1 << 17) - 6)
+    cfg.close()
+
+
 @pytest.mark.parametrize("parts", [1, 6, 12, 24])
 def test_job_granularity_does_not_change_the_cells(pkg, parts):
     """h2sha_config_t.block_parts only decides how a compression is cut into GPU jobs (>= 12: the latency setting, 8-instance jobs);

@@ -18,6 +18,7 @@ CONFIGS = [
     dict(max_variable_byte_sizes=(64,), limb_bits=2, spread_cols=3),
     dict(max_variable_byte_sizes=(128,), spread_cols=1),
     dict(max_variable_byte_sizes=(128,), is_input_range_check=False),
+    dict(max_variable_byte_sizes=(128,), limb_bits=16),       # one 16-bit limb per spread (legal in the reference: 16 % num_bits_lookup == 0, spread.rs:37)
     dict(max_variable_byte_sizes=(6144, 64)),      # a 96-block digest: its prologue/epilogue job is cut into several job classes
 ]
 
@@ -61,7 +62,7 @@ def test_cell_accounting_matches_survey(pkg):
 
 
 @pytest.mark.parametrize("bad", [dict(max_variable_byte_sizes=(100,)), dict(max_variable_byte_sizes=()), dict(max_variable_byte_sizes=(64,), limb_bits=3),
-                                 dict(max_variable_byte_sizes=(64,), limb_bits=16), dict(max_variable_byte_sizes=(64,), lookup_bits=40)])
+                                 dict(max_variable_byte_sizes=(64,), limb_bits=32), dict(max_variable_byte_sizes=(64,), lookup_bits=40)])
 def test_rejected_configurations(pkg, bad):
     with pytest.raises(pkg.EngineError):
         _engine(pkg, bad)
