@@ -810,14 +810,14 @@ def main():
         torch.cuda.empty_cache()
         # BASELINE config 4: 2^16 256-byte messages (5 blocks each, 853 GB of witness) split by instance over the N ranks; each rank
         # streams its shard through HBM in chunks when it does not fit
-        north_star = measure_full(ctx, S.WORKLOADS["cfg4"], min_seconds=0.5, max_steps=16, mem_frac=0.6, split=True, verify=4)
+        north_star = measure_full(ctx, S.WORKLOADS["cfg4"], min_seconds=0.6, max_steps=64, mem_frac=0.6, split=True, verify=4)
         north_star["note"] = ("BASELINE.json configs[3] / north_star: 2^16 instances of 256-byte messages sharded by instance across the ranks "
                               "(strong scaling: the job is fixed, N GPUs share it); value = whole-job blocks/s, max over ranks, >= 0.5 s timed")
         if world == 1:
             other_configs = {}
             for name, lim in (("cfg3", 1024), ("cfg5", 512)):
                 try:
-                    r_ = measure_full(ctx, S.WORKLOADS[name], min_seconds=0.3, max_steps=32, mem_frac=0.5, split=True, verify=2, limit_instances=lim)
+                    r_ = measure_full(ctx, S.WORKLOADS[name], min_seconds=0.6, max_steps=96, mem_frac=0.5, split=True, verify=2, limit_instances=lim)
                     r_["note"] = f"the first {lim} instances of the configuration (one HBM-sized shard); the whole configuration: bench.py --workload {name} --full-workload"
                     other_configs[name] = r_
                 except Exception as ex:
