@@ -783,20 +783,35 @@ def main():
                     tplain.append(cfg.last_kernel_ms()[1])
                 assert torch.equal(fused, mult) and int(fbad.item()) == 0, "fused multiplicities differ from the second pass"
                 fused_extra_ms = float(np.median(tf[1:]) - np.median(tplain[1:]))
-                n_perm = min(n_mult, 64)
-                tp = []
-                for _ in range(4):
-                    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a_.record(stream); pa, ps = cfg.permute_lookup(mult[:n_perm], 0, usable); b_.record(stream); b_.synchronize()
-                    tp.append(a_.elapsed_time(b_))
+                # permuted (A', S') pairs: 64 B written per usable row and instance; outputs preallocated, the C-ABI call timed with CUDA events
+                # (range lookup = lookup 0; the first spread lookup needs a theta: any reduced field element serves for timing)
+                import ctypes as C_
+                Lc = pkg.load_library()
+                n_perm = int(min(n_mult, 256, int(0.25 * torch.cuda.mem_get_info(dev)[0]) // (2 * usable * 32)))
+                pa = torch.empty((n_perm, usable, 4), dtype=torch.int64, device=dev); ps = torch.empty_like(pa)
+                theta = np.array([3, 5, 7, 11], dtype=np.uint64)
+                perm_ms = {}
+                for name, lidx, th in (("range", 0, None), ("spread", info["n_range_lookups"], theta.ctypes.data)):
+                    tp = []
+                    for _ in range(4):
+                        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a_.record(stream)
+                        rc_ = Lc.h2sha_permute_lookup(cfg._h, n_perm, lidx, C_.c_void_p(mult.data_ptr()), usable, C_.c_void_p(th), C_.c_void_p(pa.data_ptr()),
+                                                      C_.c_void_p(ps.data_ptr()), None, C_.c_void_p(sp))
+                        b_.record(stream); b_.synchronize()
+                        assert rc_ == 0, Lc.h2sha_last_error().decode()
+                        tp.append(a_.elapsed_time(b_))
+                    perm_ms[name] = min(tp[1:])
                 read_b = n_mult * (lay.n_lookup_cells + 2 * lay.n_spread_limbs) * 32
                 prework = {"usable_rows": usable, "multiplicities_fused_extra_ms": fused_extra_ms, "k_expand_with_multiplicities_ms": float(np.median(tf[1:])),
                            "k_expand_plain_ms": float(np.median(tplain[1:])),
                            "multiplicities_second_pass_ms": min(tm[1:]), "multiplicities_instances": n_mult,
-                           "multiplicities_read_gbs": read_b / (min(tm[1:]) * 1e-3) / 1e9,
-                           "permute_range_lookup_ms": min(tp[1:]), "permute_instances": n_perm,
-                           "permute_write_gbs": n_perm * usable * 64 / (min(tp[1:]) * 1e-3) / 1e9,
-                           "note": "h2sha_lookup_multiplicities / h2sha_permute_lookup incl. their memsets, allocation of the outputs and one host sync"}
+                           "multiplicities_second_pass_read_gbs": read_b / (min(tm[1:]) * 1e-3) / 1e9,
+                           "permute_instances": n_perm,
+                           "permute_range_lookup_ms": perm_ms["range"], "permute_range_write_gbs": n_perm * usable * 64 / (perm_ms["range"] * 1e-3) / 1e9,
+                           "permute_spread_lookup_ms": perm_ms["spread"], "permute_spread_write_gbs": n_perm * usable * 64 / (perm_ms["spread"] * 1e-3) / 1e9,
+                           "note": "multiplicities: fused = counted by k_expand while it writes the cells (+ k_mult_from_raw), second pass = h2sha_lookup_multiplicities over the witness in HBM "
+                                   "(incl. its memset and the allocation of the output); permute = h2sha_permute_lookup (scan + fill kernels) into preallocated outputs, CUDA events"}
                 del mult, pa, ps, fused
             del res_view
         except Exception as ex:
