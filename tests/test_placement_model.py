@@ -17,6 +17,8 @@ BASELINE_SHAPES = [
     dict(max_variable_byte_sizes=(2112,)),                # cfg 5
     dict(max_variable_byte_sizes=(128, 128)),             # the reference's TestCircuit (lib.rs:487-494)
     dict(max_variable_byte_sizes=(1024,)),                # the reference's bench circuit (benches/digest.rs:102-109)
+    dict(max_variable_byte_sizes=(128,), limb_bits=16),   # num_bits_lookup = 16: one limb per spread (spread.rs:37 accepts it)
+    dict(max_variable_byte_sizes=(128,), limb_bits=1),    # ... and 1: sixteen limbs per spread
 ]
 
 
@@ -45,7 +47,7 @@ def _assert_agree(m, planner, reg, what):
     assert (ml == sh.lookup_src).all() and (ml == reg.lookup_idx).all(), f"{what}: lookup push order differs"
 
 
-@pytest.mark.parametrize("kw", BASELINE_SHAPES, ids=lambda k: "x".join(str(s) for s in k["max_variable_byte_sizes"]))
+@pytest.mark.parametrize("kw", BASELINE_SHAPES, ids=lambda k: "x".join(str(s) for s in k["max_variable_byte_sizes"]) + (f"-limb{k['limb_bits']}" if "limb_bits" in k else ""))
 def test_baseline_shapes(pkg, kw):
     m, planner, reg = _three_ways(pkg, kw)
     _assert_agree(m, planner, reg, str(kw))
