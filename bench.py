@@ -802,6 +802,27 @@ def main():
                         assert rc_ == 0, Lc.h2sha_last_error().decode()
                         tp.append(a_.elapsed_time(b_))
                     perm_ms[name] = min(tp[1:])
+                # the same permuted pair without any dense multiplicity array: k_expand leaves the raw value lists (keep_lookup_raw), the
+                # permutation bins the one lookup it needs on the fly
+                traw = []
+                for _ in range(6):
+                    cfg.digest_batch_raw(n_mult, d_blob.data_ptr(), True, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(), lookup_ptr=lookup.data_ptr(),
+                                         spread_ptr=spread.data_ptr(), keep_lookup_raw=True, stream=sp, time_kernels=True)
+                    traw.append(cfg.last_kernel_ms()[1])
+                raw_extra_ms = float(np.median(traw[1:]) - np.median(tplain[1:]))
+                pa2 = torch.empty_like(pa); ps2 = torch.empty_like(ps)
+                tp = []
+                for _ in range(4):
+                    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a_.record(stream)
+                    rc_ = Lc.h2sha_permute_lookup_from_raw(cfg._h, 0, n_perm, 0, usable, None, C_.c_void_p(pa2.data_ptr()), C_.c_void_p(ps2.data_ptr()), None, C_.c_void_p(sp))
+                    b_.record(stream); b_.synchronize()
+                    assert rc_ == 0, Lc.h2sha_last_error().decode()
+                    tp.append(a_.elapsed_time(b_))
+                rc_ = Lc.h2sha_permute_lookup(cfg._h, n_perm, 0, C_.c_void_p(mult.data_ptr()), usable, None, C_.c_void_p(pa.data_ptr()), C_.c_void_p(ps.data_ptr()), None, C_.c_void_p(sp))
+                assert rc_ == 0 and torch.equal(pa, pa2) and torch.equal(ps, ps2), "permuted pair from the raw lists differs"
+                perm_ms["range_from_raw"] = min(tp[1:])
+                del pa2, ps2
                 read_b = n_mult * (lay.n_lookup_cells + 2 * lay.n_spread_limbs) * 32
                 prework = {"usable_rows": usable, "multiplicities_fused_extra_ms": fused_extra_ms, "k_expand_with_multiplicities_ms": float(np.median(tf[1:])),
                            "k_expand_plain_ms": float(np.median(tplain[1:])),
@@ -810,8 +831,11 @@ def main():
                            "permute_instances": n_perm,
                            "permute_range_lookup_ms": perm_ms["range"], "permute_range_write_gbs": n_perm * usable * 64 / (perm_ms["range"] * 1e-3) / 1e9,
                            "permute_spread_lookup_ms": perm_ms["spread"], "permute_spread_write_gbs": n_perm * usable * 64 / (perm_ms["spread"] * 1e-3) / 1e9,
+                           "raw_lists_extra_ms": raw_extra_ms, "permute_range_from_raw_ms": perm_ms["range_from_raw"],
+                           "permute_range_from_raw_write_gbs": n_perm * usable * 64 / (perm_ms["range_from_raw"] * 1e-3) / 1e9,
                            "note": "multiplicities: fused = counted by k_expand while it writes the cells (+ k_mult_from_raw), second pass = h2sha_lookup_multiplicities over the witness in HBM "
-                                   "(incl. its memset and the allocation of the output); permute = h2sha_permute_lookup (scan + fill kernels) into preallocated outputs, CUDA events"}
+                                   "(incl. its memset and the allocation of the output); permute = h2sha_permute_lookup (scan + fill kernels) into preallocated outputs, CUDA events; "
+                                   "raw lists = keep_lookup_raw (no dense multiplicities at all) + h2sha_permute_lookup_from_raw, output checked equal"}
                 del mult, pa, ps, fused
             del res_view
         except Exception as ex:

@@ -29,7 +29,7 @@ H2SHA_OK, H2SHA_EINVAL, H2SHA_EPANIC, H2SHA_ECUDA, H2SHA_ENOMEM = 0, -1, -2, -3,
 # symbols include/h2sha_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "h2sha_create", "h2sha_destroy", "h2sha_last_error", "h2sha_build_id", "h2sha_get_layout", "h2sha_get_breaks", "h2sha_get_handles", "h2sha_get_digest_ranges", "h2sha_get_shape", "h2sha_get_lookup_tables",
-    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_export_batch", "h2sha_get_compact_info", "h2sha_get_compact_map", "h2sha_expand_compact", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_check_batch", "h2sha_gather", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_debug_int_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
+    "h2sha_digest_batch", "h2sha_export_instance", "h2sha_export_batch", "h2sha_get_compact_info", "h2sha_get_compact_map", "h2sha_expand_compact", "h2sha_get_lookup_info", "h2sha_lookup_multiplicities", "h2sha_permute_lookup", "h2sha_permute_lookup_from_raw", "h2sha_check_batch", "h2sha_gather", "h2sha_zero_outputs", "h2sha_debug_mont_from_u64", "h2sha_debug_mont_from_u32", "h2sha_debug_store_probe", "h2sha_debug_int_probe", "h2sha_last_launch_count", "h2sha_last_kernel_ms", "H2SHA_CK_M",
 ]
 
 
@@ -65,7 +65,7 @@ class _Batch(C.Structure):
                 ("spread", C.c_void_p), ("digests_dev", C.c_void_p), ("checksums_dev", C.c_void_p), ("digests_host", C.c_void_p),
                 ("checksums_host", C.c_void_p), ("stream", C.c_void_p), ("reuse_inputs", C.c_int32), ("time_kernels", C.c_int32),
                 ("only_digest", C.c_uint32), ("lookup_mult_dev", C.c_void_p), ("mult_usable_rows", C.c_uint32), ("mult_not_in_table_dev", C.c_void_p),
-                ("compact_dict", C.c_void_p)]
+                ("compact_dict", C.c_void_p), ("keep_lookup_raw", C.c_uint32)]
 
 
 class _CompactInfo(C.Structure):
@@ -119,6 +119,7 @@ def load_library():
     sig("h2sha_get_lookup_info", [C.c_void_p, C.POINTER(_LookupInfo)])
     sig("h2sha_lookup_multiplicities", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p])
     sig("h2sha_permute_lookup", [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+    sig("h2sha_permute_lookup_from_raw", [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
     sig("h2sha_check_batch", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
     sig("h2sha_gather", [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
     sig("h2sha_zero_outputs", [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p])
@@ -318,7 +319,8 @@ class Sha256DynamicConfig:
                          precomputed_lens: Optional[np.ndarray], *, gate_ptr: int = 0, lookup_ptr: int = 0, spread_ptr: int = 0,
                          digests_dev_ptr: int = 0, checksums_dev_ptr: int = 0, digests_host_ptr: int = 0, checksums_host_ptr: int = 0,
                          stream: int = 0, reuse_inputs: bool = False, time_kernels: bool = False, only_digest: int = 0,
-                         lookup_mult_ptr: int = 0, mult_usable_rows: int = 0, mult_bad_ptr: int = 0, compact_dict_ptr: int = 0):
+                         lookup_mult_ptr: int = 0, mult_usable_rows: int = 0, mult_bad_ptr: int = 0, compact_dict_ptr: int = 0,
+                         keep_lookup_raw: bool = False):
         """Thin wrapper over h2sha_digest_batch (all pointers are integers)."""
         if reuse_inputs:
             off_p = len_p = pre_p = None
@@ -329,7 +331,7 @@ class Sha256DynamicConfig:
         b = _Batch(n_instances, msgs_ptr or None, 1 if msgs_on_device else 0, msgs_bytes, off_p, len_p, pre_p, gate_ptr or None,
                    lookup_ptr or None, spread_ptr or None, digests_dev_ptr or None, checksums_dev_ptr or None, digests_host_ptr or None,
                    checksums_host_ptr or None, stream or None, 1 if reuse_inputs else 0, 1 if time_kernels else 0, only_digest,
-                   lookup_mult_ptr or None, mult_usable_rows, mult_bad_ptr or None, compact_dict_ptr or None)
+                   lookup_mult_ptr or None, mult_usable_rows, mult_bad_ptr or None, compact_dict_ptr or None, 1 if keep_lookup_raw else 0)
         _check(load_library().h2sha_digest_batch(self._h, C.byref(b)))
 
     def last_kernel_ms(self) -> Tuple[float, float]:
@@ -469,6 +471,23 @@ class Sha256DynamicConfig:
             assert th.shape == (4,)
         _check(load_library().h2sha_permute_lookup(self._h, n, lookup_idx, mult.data_ptr(), usable_rows, th.ctypes.data if th is not None else None,
                                                    a.data_ptr(), s.data_ptr(), err.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        if int(err.item()):
+            raise EngineError(H2SHA_EINVAL, f"{int(err.item())} instance(s) whose multiplicities do not cover usable_rows")
+        return a, s
+
+    def permute_lookup_from_raw(self, first_instance: int, n_instances: int, lookup_idx: int, usable_rows: int, theta_mont: Optional[np.ndarray] = None):
+        """(A', S') like permute_lookup, from the raw value lists the last keep_lookup_raw / lookup_mult batch left in the engine."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        a = torch.empty((n_instances, usable_rows, 4), dtype=torch.int64, device=dev)
+        s = torch.empty((n_instances, usable_rows, 4), dtype=torch.int64, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        th = None
+        if theta_mont is not None:
+            th = np.ascontiguousarray(theta_mont, dtype=np.uint64)
+            assert th.shape == (4,)
+        _check(load_library().h2sha_permute_lookup_from_raw(self._h, first_instance, n_instances, lookup_idx, usable_rows, th.ctypes.data if th is not None else None,
+                                                            a.data_ptr(), s.data_ptr(), err.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
         if int(err.item()):
             raise EngineError(H2SHA_EINVAL, f"{int(err.item())} instance(s) whose multiplicities do not cover usable_rows")
         return a, s

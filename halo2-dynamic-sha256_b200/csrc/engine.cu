@@ -1464,6 +1464,7 @@ struct h2sha_engine {
   uint32_t* d_lookup_raw = nullptr;  // [cap][n_lookup] raw looked-up values of the last MODE 1 batch
   uint8_t* d_dense_raw = nullptr;    // [cap][n_limb]
   uint64_t raw_cap = 0;
+  uint64_t raw_n = 0;                // instances of the last batch that left raw lists (0: none valid)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // trace start/stop, expand start/stop
   bool timed = false, timed_expand = false;
   // lookup-argument pre-work (lookup_prework.cuh)
@@ -1866,15 +1867,18 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   const uint64_t n_msgs = b->n_instances * D;
   if (n_msgs > 0xffffffffull) return set_err(H2SHA_EINVAL, "batch too large");
   if (b->only_digest > D) return set_err(H2SHA_EINVAL, "only_digest names a digest() call the configuration does not have");
-  if (b->compact_dict && (b->lookup_mult_dev || b->only_digest))
+  const bool want_raw = b->lookup_mult_dev || b->keep_lookup_raw;
+  if (b->compact_dict && (want_raw || b->only_digest))
     return set_err(H2SHA_EINVAL, "compact_dict cannot be combined with lookup_mult_dev or only_digest (separate kernel instantiations): issue two calls");
-  if (b->lookup_mult_dev) {
+  if (want_raw) {
     if (b->only_digest) return set_err(H2SHA_EINVAL, "lookup multiplicities need every digest() call of the region (only_digest must be 0)");
     if (!b->gate || !b->lookup || !b->spread) return set_err(H2SHA_EINVAL, "lookup multiplicities are counted while the cells are written: gate, lookup and spread must be given");
-    if (b->mult_usable_rows < lookup_rows_needed(P)) return set_err(H2SHA_EINVAL, "mult_usable_rows is smaller than an assigned column or a lookup table");
     if (!e->mult_fits) return set_err(H2SHA_EINVAL, "this configuration leaves no shared memory for the fused multiplicity count: use h2sha_lookup_multiplicities");
-    if (P.cfg.lookup_bits < 2 || P.cfg.limb_bits < 2 || ((uintptr_t)b->lookup_mult_dev & 15u)) return set_err(H2SHA_EINVAL, "lookup_mult_dev must be 16-byte aligned (tables of >= 4 rows)");
     if (P.cfg.limb_bits > 8) return set_err(H2SHA_EINVAL, "the fused multiplicity count keeps the spread-table bins in shared memory: num_bits_lookup <= 8");
+  }
+  if (b->lookup_mult_dev) {
+    if (b->mult_usable_rows < lookup_rows_needed(P)) return set_err(H2SHA_EINVAL, "mult_usable_rows is smaller than an assigned column or a lookup table");
+    if (P.cfg.lookup_bits < 2 || P.cfg.limb_bits < 2 || ((uintptr_t)b->lookup_mult_dev & 15u)) return set_err(H2SHA_EINVAL, "lookup_mult_dev must be 16-byte aligned (tables of >= 4 rows)");
   }
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)b->stream;
@@ -1947,7 +1951,8 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
   const bool expand = b->gate || b->lookup || b->spread || cks_dev || b->compact_dict;
   ta.job_counter = expand ? S->d_counter : nullptr;
   ta.cks = cks_dev;
-  if (b->lookup_mult_dev) {
+  if (want_raw) {
+    e->raw_n = 0;
     if (b->n_instances > e->raw_cap) {
       e->raw_cap = 0;
       int rc2;
@@ -1955,7 +1960,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
       if ((rc2 = dev_realloc(e->d_dense_raw, b->n_instances * (uint64_t)P.n_limb))) return rc2;
       e->raw_cap = b->n_instances;
     }
-    if (b->mult_not_in_table_dev) CUDA_TRY(cudaMemsetAsync(b->mult_not_in_table_dev, 0, 4, st));
+    if (b->lookup_mult_dev && b->mult_not_in_table_dev) CUDA_TRY(cudaMemsetAsync(b->mult_not_in_table_dev, 0, 4, st));
   }
   if (timed) CUDA_TRY(cudaEventRecord(e->ev[0], ts));
   // few messages: the warp-per-message kernel (latency); many: one thread per message (throughput).  H2SHA_TUNE "tracewarp=N" moves the switch.
@@ -1974,7 +1979,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     ja.gate = (uint32_t*)b->gate; ja.lookup = (uint32_t*)b->lookup; ja.spread = (uint32_t*)b->spread;
     ja.cks = cks_dev; ja.job_counter = S->d_counter; ja.only_digest = b->only_digest;
     if (b->compact_dict) { ja.dict = (uint32_t*)b->compact_dict; ja.dict_inst_cells = P.dict_cells; }
-    if (b->lookup_mult_dev) {
+    if (want_raw) {
       ja.lookup_raw = e->d_lookup_raw; ja.dense_raw = e->d_dense_raw;
       ja.limb_bits = P.cfg.limb_bits; ja.n_lookup_total = P.n_lookup; ja.n_limb_total = P.n_limb;
     }
@@ -1984,7 +1989,7 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
     if (timed) CUDA_TRY(cudaEventRecord(e->ev[2], st));
     {
       // programmatic dependent launch: prologue (plan -> shared memory) overlaps the trace kernel when both are on one stream
-      const DevPlan& dp = b->lookup_mult_dev ? e->dplan_mult : e->dplan;
+      const DevPlan& dp = want_raw ? e->dplan_mult : e->dplan;
       void* args[2] = {(void*)&dp, (void*)&ja};
       cudaLaunchConfig_t lc{};
       lc.gridDim = dim3(grid); lc.blockDim = dim3((e->variant.ncons + e->variant.nprod) * 32);
@@ -1993,10 +1998,11 @@ int h2sha_digest_batch(h2sha_engine_t* e, const h2sha_batch_t* b) {
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = (timed || overlap) ? 0 : 1;   // plain serialisation when kernels are timed individually
       lc.attrs = at; lc.numAttrs = 1;
-      CUDA_TRY(cudaLaunchKernelExC(&lc, e->variant.fn[b->lookup_mult_dev ? 1 : (b->compact_dict ? 2 : 0)], args));
+      CUDA_TRY(cudaLaunchKernelExC(&lc, e->variant.fn[want_raw ? 1 : (b->compact_dict ? 2 : 0)], args));
     }
     launches++;
     CUDA_TRY(cudaGetLastError());
+    if (want_raw) e->raw_n = b->n_instances;
     if (b->lookup_mult_dev) {
       MultArgs ma{};
       ma.lookup_raw = e->d_lookup_raw; ma.dense_raw = e->d_dense_raw; ma.mult = b->lookup_mult_dev; ma.bad = b->mult_not_in_table_dev;

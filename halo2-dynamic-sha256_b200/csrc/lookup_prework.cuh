@@ -249,6 +249,54 @@ __global__ void __launch_bounds__(1024) k_permute_scan(const PermuteArgs A) {
   }
 }
 
+// Multiplicities of ONE lookup of instances [first, first + gridDim.x) from the raw value lists k_expand<.., MODE 1> left in the engine
+// (h2sha_permute_lookup_from_raw): one CTA per instance, out[blockIdx.x][n_vals].  Hot values (< 4096: zeros, bytes) are binned in
+// shared memory, the bins are written once (coalesced), the rest follows with global atomics on lines that are L2-resident by then.
+struct MultOneArgs {
+  const uint32_t* lookup_raw;   // [n][n_lookup]
+  const uint8_t* dense_raw;     // [n][n_limb]
+  uint32_t* out;                // [gridDim.x][n_vals]
+  uint32_t* bad;                // may be null
+  uint64_t first;
+  uint32_t n_lookup, n_limb, max_rows, spread_cols, n_vals, usable_rows, is_range, col;
+};
+enum { MULT_ONE_SMALL = 4096 };
+__global__ void __launch_bounds__(512) k_mult_one(const MultOneArgs A) {
+  __shared__ uint32_t s_small[MULT_ONE_SMALL];
+  const uint64_t inst = A.first + blockIdx.x;
+  uint32_t* bins = A.out + (uint64_t)blockIdx.x * A.n_vals;
+  const uint32_t n_small = min((uint32_t)MULT_ONE_SMALL, A.n_vals);
+  for (uint32_t i = threadIdx.x; i < n_small; i += blockDim.x) s_small[i] = 0;
+  __syncthreads();
+  uint32_t n_bad = 0, used = 0;
+  const uint32_t* lr = A.lookup_raw + inst * A.n_lookup;
+  const uint8_t* dr = A.dense_raw + inst * A.n_limb;
+  uint32_t k0 = 0, k1 = 0;
+  if (A.is_range) {
+    k0 = min(A.n_lookup, A.col * A.max_rows); k1 = min(A.n_lookup, (A.col + 1) * A.max_rows);   // range.finalize wraps at max_rows
+    used = k1 - k0;
+    for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+      const uint32_t v = lr[k];
+      if (v < n_small) atomicAdd(&s_small[v], 1u);
+    }
+  } else {
+    used = A.n_limb > A.col ? (A.n_limb - A.col + A.spread_cols - 1) / A.spread_cols : 0u;
+    for (uint32_t n = A.col + threadIdx.x * A.spread_cols; n < A.n_limb; n += blockDim.x * A.spread_cols) atomicAdd(&s_small[dr[n]], 1u);   // dense limbs are < 2^8 <= n_small
+  }
+  if (threadIdx.x == 0 && A.usable_rows > used) atomicAdd(&s_small[0], A.usable_rows - used);   // never-assigned rows hold 0 = table row 0
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < A.n_vals; i += blockDim.x) bins[i] = i < n_small ? s_small[i] : 0u;
+  __syncthreads();
+  if (A.is_range) {
+    for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+      const uint32_t v = lr[k];
+      if (v >= A.n_vals) n_bad++;
+      else if (v >= n_small) atomicAdd(&bins[v], 1u);
+    }
+  }
+  if (n_bad && A.bad) atomicAdd(A.bad, n_bad);
+}
+
 // last index k in [lo, hi) with a[k] <= x (a non-decreasing, a[lo] <= x)
 __device__ __forceinline__ uint32_t last_leq(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t x) {
   while (hi - lo > 1) {   // invariant: a[lo] <= x, (hi == end or a[hi] > x)
@@ -431,9 +479,14 @@ int h2sha_lookup_multiplicities(h2sha_engine_t* e, uint64_t n_instances, const v
   return H2SHA_OK;
 }
 
-int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint32_t usable_rows,
-                         const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream) {
-  if (!e || !mult_dev || !permuted_input_dev || !permuted_table_dev) return set_err(H2SHA_EINVAL, "null argument");
+}  // extern "C"
+
+namespace {
+// mult_dev == null: the multiplicities come from the engine's raw value lists (instances first_raw .. of the last keep_lookup_raw batch)
+int permute_lookup_impl(h2sha_engine_t* e, uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint64_t first_raw, uint32_t usable_rows,
+                        const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream) {
+  if (!e || !permuted_input_dev || !permuted_table_dev) return set_err(H2SHA_EINVAL, "null argument");
+  const bool from_raw = mult_dev == nullptr;
   if (e->device < 0) return set_err(H2SHA_ECUDA, "plan-only engine (device = -1): there is no CPU path");
   const Plan& P = e->plan;
   const uint32_t n_range = P.n_lookup_cols, n_spread = P.cfg.spread_cols;
@@ -449,7 +502,7 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   // workspace: scans + totals of one chunk of instances (the chunks run one after the other on `stream` and share it)
   if (n_vals > (1u << 22)) return set_err(H2SHA_EINVAL, "lookup table too large for the permutation workspace (lookup_bits > 22)");
   // instances per pass: at most `lkchunk` (default 256) and at most ~1 GB of scans
-  const uint64_t per_inst_words = 3ull * n_vals + 4 + (is_range ? (uint64_t)usable_rows + n_vals : 0);   // scans, totals, inverse maps (identity order)
+  const uint64_t per_inst_words = 3ull * n_vals + 4 + (is_range ? (uint64_t)usable_rows + n_vals : 0) + (from_raw ? align_up(n_vals, 4) : 0);   // scans, totals, inverse maps (identity order), this lookup's bins
   const uint64_t by_mem = std::max<uint64_t>(1, (1ull << 30) / (per_inst_words * 4));
   const uint64_t chunk = std::min<uint64_t>(std::min<uint64_t>(n_instances, by_mem), (uint64_t)std::max(1, tune_value("lkchunk", 256)));
   const uint64_t need = chunk * per_inst_words * 4;
@@ -459,10 +512,19 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
     e->lk_ws_bytes = need;
   }
   PermuteArgs A{};
-  A.mult_stride = G.mult_words;
-  A.mult = mult_dev + (is_range ? (uint64_t)lookup_idx * n_vals : ((uint64_t)n_range << G.lookup_bits) + (uint64_t)(lookup_idx - n_range) * n_vals);
+  uint32_t* raw_bins = nullptr;   // from_raw: [chunk][n_vals] at the start of the workspace (16-byte aligned rows for the vectorised scan)
+  uint32_t* ws = e->d_lk_ws;
+  if (from_raw) {
+    raw_bins = ws;
+    ws += chunk * (uint64_t)align_up(n_vals, 4);
+    A.mult_stride = align_up(n_vals, 4);
+    A.mult = raw_bins;
+  } else {
+    A.mult_stride = G.mult_words;
+    A.mult = mult_dev + (is_range ? (uint64_t)lookup_idx * n_vals : ((uint64_t)n_range << G.lookup_bits) + (uint64_t)(lookup_idx - n_range) * n_vals);
+  }
   A.n_vals = n_vals; A.usable_rows = usable_rows;
-  A.scan = e->d_lk_ws; A.totals = e->d_lk_ws + chunk * 3ull * n_vals;
+  A.scan = ws; A.totals = ws + chunk * 3ull * n_vals;
   if (is_range && tune_value("lkinv", 1)) { A.vrow = A.totals + chunk * 4; A.llist = A.vrow + chunk * (uint64_t)usable_rows; }
   A.errors = errors_dev;
   A.out_input = (uint64_t*)permuted_input_dev; A.out_table = (uint64_t*)permuted_table_dev;
@@ -504,7 +566,17 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
   const uint32_t* mult0 = A.mult;
   for (uint64_t i0 = 0; i0 < n_instances; i0 += chunk) {
     const uint64_t ni = std::min<uint64_t>(chunk, n_instances - i0);
-    A.mult = mult0 + i0 * A.mult_stride;
+    if (from_raw) {
+      MultOneArgs M{};
+      M.lookup_raw = e->d_lookup_raw; M.dense_raw = e->d_dense_raw; M.out = raw_bins; M.bad = nullptr; M.first = first_raw + i0;
+      M.n_lookup = P.n_lookup; M.n_limb = P.n_limb; M.max_rows = P.cfg.max_rows; M.spread_cols = P.cfg.spread_cols; M.n_vals = n_vals;
+      M.usable_rows = usable_rows; M.is_range = is_range ? 1u : 0u; M.col = is_range ? lookup_idx : lookup_idx - n_range;
+      if (A.mult_stride != n_vals) return set_err(H2SHA_EINVAL, "lookup tables of fewer than 4 rows are not supported by the raw-list path");
+      k_mult_one<<<(unsigned)ni, 512, 0, st>>>(M);
+      CUDA_TRY(cudaGetLastError());
+    } else {
+      A.mult = mult0 + i0 * A.mult_stride;
+    }
     A.out_input = (uint64_t*)permuted_input_dev + i0 * (uint64_t)usable_rows * 4;
     A.out_table = (uint64_t*)permuted_table_dev + i0 * (uint64_t)usable_rows * 4;
     {
@@ -519,6 +591,23 @@ int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t looku
     CUDA_TRY(cudaGetLastError());
   }
   return H2SHA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint32_t usable_rows,
+                         const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream) {
+  if (!mult_dev) return set_err(H2SHA_EINVAL, "null argument");
+  return permute_lookup_impl(e, n_instances, lookup_idx, mult_dev, 0, usable_rows, theta_mont, permuted_input_dev, permuted_table_dev, errors_dev, stream);
+}
+
+int h2sha_permute_lookup_from_raw(h2sha_engine_t* e, uint64_t first_instance, uint64_t n_instances, uint32_t lookup_idx, uint32_t usable_rows,
+                                  const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream) {
+  if (!e) return set_err(H2SHA_EINVAL, "null argument");
+  if (first_instance + n_instances > e->raw_n)
+    return set_err(H2SHA_EINVAL, "the engine holds no raw value lists for these instances: generate the batch with keep_lookup_raw (or lookup_mult_dev) first");
+  return permute_lookup_impl(e, n_instances, lookup_idx, nullptr, first_instance, usable_rows, theta_mont, permuted_input_dev, permuted_table_dev, errors_dev, stream);
 }
 
 }  // extern "C"

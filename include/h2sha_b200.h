@@ -145,6 +145,9 @@ typedef struct {
                                         value of an instance once (3.7x fewer bytes than its cells); h2sha_get_compact_map says which
                                         entry each cell copies, h2sha_expand_compact rebuilds the columns on the host.  gate / lookup /
                                         spread may be NULL then (nothing but the dictionary is written)                         */
+  uint32_t keep_lookup_raw;          /* 1: like lookup_mult_dev, but nothing dense is written: the raw values of the looked-up cells stay in the
+                                        engine (17.6 KB per block) and h2sha_permute_lookup_from_raw bins them per lookup on the fly.  Needs
+                                        gate, lookup and spread; valid until the next batch with lookup_mult_dev / keep_lookup_raw       */
 } h2sha_batch_t;
 
 /* Replaces `digest` (lib.rs:71-349) for a whole batch: padding and length selection, the precomputed
@@ -224,6 +227,12 @@ int h2sha_lookup_multiplicities(h2sha_engine_t* e, uint64_t n_instances, const v
  * for every instance whose multiplicities do not sum to usable_rows (its rows are then not written). */
 int h2sha_permute_lookup(h2sha_engine_t* e, uint64_t n_instances, uint32_t lookup_idx, const uint32_t* mult_dev, uint32_t usable_rows,
                          const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream);
+
+/* The same permuted pair straight from the raw value lists of the last batch generated with keep_lookup_raw (or lookup_mult_dev):
+ * instances [first_instance, first_instance + n_instances) of that batch.  The multiplicities of the one lookup are binned into the
+ * engine's workspace (L2-resident) right before the scan; no dense multiplicity array is ever written to or read from HBM. */
+int h2sha_permute_lookup_from_raw(h2sha_engine_t* e, uint64_t first_instance, uint64_t n_instances, uint32_t lookup_idx, uint32_t usable_rows,
+                                  const uint64_t* theta_mont, void* permuted_input_dev, void* permuted_table_dev, uint32_t* errors_dev, void* stream);
 
 /* MockProver-style check of a whole batch where it lies, in HBM -- what the reference's tests accept a witness by
  * (`MockProver::run(..).verify() == Ok(())`, lib.rs:525-526), for every instance instead of one:

@@ -337,3 +337,45 @@ def test_multiplicities_counted_while_the_cells_are_written(pkg, kw):
         cfg.digest_batch_raw(n, blob.ctypes.data if blob.size else 0, False, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(),
                              lookup_ptr=lookup.data_ptr(), spread_ptr=spread.data_ptr(), lookup_mult_ptr=fused.data_ptr(), mult_usable_rows=10)
     cfg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(sizes=[64], n=5), dict(sizes=[128, 64], n=3, max_rows=4099), dict(sizes=[192], n=3, lookup_bits=9, num_bits_lookup=4, num_advice_columns=3)],
+                         ids=["cfg2", "2digests-wraps", "9bit-3cols"])
+def test_permuted_pairs_from_the_raw_value_lists(pkg, kw):
+    """h2sha_batch_t.keep_lookup_raw + h2sha_permute_lookup_from_raw: no dense multiplicity array is written at all; the permuted pair of
+    every lookup (range lookups and, with a theta, spread lookups), for the whole batch and for a slice of it, is bit-identical to
+    h2sha_permute_lookup on the second-pass multiplicities (which the tests above pin against the oracle)."""
+    import torch
+    kw = dict(kw)
+    sizes, n = kw.pop("sizes"), kw.pop("n")
+    cfg = pkg.Sha256DynamicConfig.configure(sizes, device=0, **kw)
+    info = cfg.lookup_info()
+    usable = info["min_usable_rows"] + 5
+    rng = np.random.default_rng(23)
+    msgs = [[bytes(rng.integers(0, 256, int(rng.integers(0, s - 8)), dtype=np.uint8)) for s in sizes] for _ in range(n)]
+    blob, offs, lens = pkg.pack_messages(msgs)
+    gate, lookup, spread = cfg.alloc_outputs(n)
+    with pytest.raises(pkg.EngineError):   # nothing generated with keep_lookup_raw yet
+        cfg.permute_lookup_from_raw(0, n, 0, usable)
+    try:
+        cfg.digest_batch_raw(n, blob.ctypes.data if blob.size else 0, False, int(blob.size), offs, lens, None, gate_ptr=gate.data_ptr(),
+                             lookup_ptr=lookup.data_ptr(), spread_ptr=spread.data_ptr(), keep_lookup_raw=True, stream=torch.cuda.current_stream(0).cuda_stream)
+    except pkg.EngineError as ex:
+        assert "no shared memory for the fused multiplicity count" in str(ex) and kw.get("num_bits_lookup", 8) < 8
+        cfg.close()
+        return
+    torch.cuda.synchronize()
+    mult, bad = cfg.lookup_multiplicities(pkg.BatchResult(None, None, gate, lookup, spread), usable)
+    assert bad == 0
+    theta = O.int_to_mont(int.from_bytes(rng.bytes(32), "little") % O.P)
+    for l in range(info["n_range_lookups"] + info["n_spread_lookups"]):
+        th = None if l < info["n_range_lookups"] else theta
+        want_a, want_s = cfg.permute_lookup(mult, l, usable, th)
+        got_a, got_s = cfg.permute_lookup_from_raw(0, n, l, usable, th)
+        assert torch.equal(got_a, want_a) and torch.equal(got_s, want_s), f"lookup {l}"
+        got_a, got_s = cfg.permute_lookup_from_raw(1, n - 1, l, usable, th)      # a slice of the batch
+        assert torch.equal(got_a, want_a[1:]) and torch.equal(got_s, want_s[1:]), f"lookup {l}, instances 1.."
+    with pytest.raises(pkg.EngineError):
+        cfg.permute_lookup_from_raw(1, n, 0, usable)                               # beyond the batch
+    cfg.close()
